@@ -1,0 +1,109 @@
+"""CPU: the oracle restatements (python + C) reproduce every golden vector generated from the
+unmodified reference by oracle/make_golden.py."""
+import glob
+import os
+import sys
+
+import numpy as np
+import pytest
+
+from oracle import sgns_oracle, walk_oracle
+from oracle.c_oracle import c_walks
+
+GOLDEN = os.path.join(os.path.dirname(os.path.abspath(__file__)), 'golden')
+WALK_CASES = sorted(os.path.basename(p)[len('walks_'):-len('.npz')] for p in glob.glob(os.path.join(GOLDEN, 'walks_*.npz')))
+SGNS_CASES = sorted(os.path.basename(p)[len('sgns_'):-len('.npz')] for p in glob.glob(os.path.join(GOLDEN, 'sgns_*.npz')))
+
+
+def load_walk_case(tag):
+    z = np.load(os.path.join(GOLDEN, f'walks_{tag}.npz'))
+    rowptr, col = z['rowptr'], z['col']
+    w = z['w'] if bool(z['weighted']) else None
+    adj = [list(map(int, col[rowptr[i]:rowptr[i + 1]])) for i in range(len(rowptr) - 1)]
+    wts = None
+    if w is not None:
+        conv = (lambda x: int(x)) if bool(z['w_is_int']) else (lambda x: float(x))
+        wts = [[conv(x) for x in w[rowptr[i]:rowptr[i + 1]]] for i in range(len(rowptr) - 1)]
+    g = walk_oracle.OracleGraph(adj, wts, [str(s) for s in z['names']])
+    return z, g, w
+
+
+def test_fixture_inventory():
+    assert len(WALK_CASES) >= 10 and len(SGNS_CASES) >= 5
+
+
+@pytest.mark.parametrize('tag', WALK_CASES)
+def test_python_walk_oracle_matches_reference(tag):
+    z, g, _ = load_walk_case(tag)
+    got = walk_oracle.walks(g, z['starts'], int(z['length']), z['uniforms'], float(z['p']), float(z['q']),
+                            node2vec=bool(z['node2vec']))
+    assert np.array_equal(got, z['walks'])
+
+
+@pytest.mark.parametrize('tag', WALK_CASES)
+def test_c_walk_oracle_matches_reference(tag):
+    z, g, w = load_walk_case(tag)
+    for sorted_membership in (False, True):
+        col_sorted = None
+        if sorted_membership:
+            col_sorted = np.concatenate([np.sort(z['col'][z['rowptr'][i]:z['rowptr'][i + 1]]) for i in range(g.n_nodes)])
+        got = c_walks(z['rowptr'], z['col'], w, bool(z['w_is_int']), z['starts'], int(z['length']), float(z['p']),
+                      float(z['q']), bool(z['node2vec']), 0, z['uniforms'], col_sorted=col_sorted)
+        assert np.array_equal(got, z['walks'])
+
+
+@pytest.mark.skipif(sys.version_info < (3, 12), reason='builtin sum() is Neumaier-compensated from 3.12')
+def test_py312_sum_restatement_equals_builtin():
+    rng = np.random.default_rng(0)
+    for _ in range(2000):
+        n = int(rng.integers(1, 40))
+        vals = []
+        for _ in range(n):
+            if rng.random() < 0.5:
+                vals.append(int(rng.integers(1, 9)))
+            else:
+                vals.append(float(rng.random() * 10.0 ** int(rng.integers(-8, 8))))
+        a, b = walk_oracle.py312_sum(vals), sum(vals)
+        assert type(a) is type(b) and a == b
+
+
+def test_paper_rule_differs_from_code_rule():
+    # SURVEY trap #1: 4-node graph, p=4, q=.25 -> code rule favours the common neighbour
+    adj = [[1, 2], [0, 2, 3], [0, 1], [1]]           # t=0, v=1: x=0 (return), x=2 (common nbr), x=3 (distance 2)
+    g = walk_oracle.OracleGraph(adj)
+    ref = walk_oracle.transition_probabilities(g, 0, 1, 4.0, 0.25, True, walk_oracle.RULE_REFERENCE)
+    pap = walk_oracle.transition_probabilities(g, 0, 1, 4.0, 0.25, True, walk_oracle.RULE_PAPER)
+    np.testing.assert_allclose(ref, np.array([0.25, 4.0, 1.0]) / 5.25)
+    np.testing.assert_allclose(pap, np.array([0.25, 1.0, 4.0]) / 5.25)
+
+
+def test_collate_golden():
+    z = np.load(os.path.join(GOLDEN, 'collate.npz'))
+    i, t = sgns_oracle.collate_sg([np.arange(10, 18)], 3, 256)
+    assert np.array_equal(i, z['worked_inputs']) and np.array_equal(t, z['worked_targets'])
+    for tag in ('karate', 'clip', 'tri'):
+        i, t = sgns_oracle.collate_sg(list(z[f'{tag}_texts']), int(z[f'{tag}_r']), int(z[f'{tag}_max_length']))
+        assert np.array_equal(i, z[f'{tag}_inputs']) and np.array_equal(t, z[f'{tag}_targets'])
+    with pytest.raises(AssertionError):
+        sgns_oracle.collate_sg([np.arange(4)], 2, 256)   # shorter than 2r+1 (torch_dataset.py:298)
+
+
+@pytest.mark.parametrize('tag', SGNS_CASES)
+@pytest.mark.parametrize('prec', ['f32', 'f64'])
+def test_sgns_oracle_matches_reference_autograd(tag, prec):
+    z = np.load(os.path.join(GOLDEN, f'sgns_{tag}.npz'))
+    o = sgns_oracle.training_step(z[f'w_in_{prec}'], z[f'w_out_{prec}'], z['inputs'], z['targets'], z['noise'])
+    tol = 1e-12 if prec == 'f64' else 1e-5
+    got = np.array([o['loss'], o['positive-loss'], o['negative-loss']], dtype=np.float64)
+    np.testing.assert_allclose(got, z[f'loss_{prec}'], rtol=tol)
+    den = max(np.abs(z[f'grad_in_{prec}']).max(), np.abs(z[f'grad_out_{prec}']).max())
+    assert np.abs(o['grad_in'] - z[f'grad_in_{prec}']).max() / den <= tol
+    assert np.abs(o['grad_out'] - z[f'grad_out_{prec}']).max() / den <= tol
+    np.testing.assert_allclose([o['recall'], o['precision']], z[f'metrics_{prec}'], atol=1e-6)
+
+
+def test_vocab_golden_order():
+    z = np.load(os.path.join(GOLDEN, 'vocab.npz'))
+    itos = [str(s) for s in z['karate_itos']]
+    assert itos[0] == '<unk>' and itos[1:] == [f'n{i:02d}' for i in range(1, 35)]
+    assert [str(s) for s in z['triplets_itos']] == ['<unk>', 'a1', 'a2', 'a3', 'b1', 'b2', 'b3', 'c1', 'c2', 'c3']
