@@ -1,0 +1,414 @@
+// Skip-gram negative-sampling kernels for sm_100a (HBM-bound gather / dot / sigmoid / scatter).
+//
+// One GROUP of G lanes (G = 32 for emb >= 128) owns one centre: it keeps the centre row of W_in and the centre's
+// accumulated gradient in registers for the whole window (read once, written once), and for every context gathers
+// the context row and its K negative rows of W_out with 128-bit loads issued back to back (all rows of a chunk
+// are in flight before the first is used), reduces the dot products with warp shuffles, applies
+// sigmoid / clamp / log exactly as shallow_encoders/word2vec/loss.py:15-16, and scatters the updates in place.
+//
+// Three entry kernels share that body:
+//   MODE_GRAD  explicit (inputs, targets, noise) -> loss sums + DENSE gradients of the mean loss (parity kernel,
+//              word2vec/trainer.py:131-152 + autograd)
+//   MODE_STEP  explicit batch, in-place SGD (noise optional: in-kernel Philox negatives)
+//   MODE_WALK  tokens[n_seq x L] -> windows (word2vec/dataloader/torch_dataset.py:300-309) + in-kernel negatives
+//              (word2vec/utils/sampling.py:21 distribution, or alias table) + in-place SGD.  Nothing materialised.
+#include "common.cuh"
+
+namespace se {
+namespace {
+
+constexpr int SGNS_THREADS = 256;
+constexpr float CLAMP_MIN = 1e-6f;
+enum { MODE_GRAD = 0, MODE_STEP = 1, MODE_WALK = 2 };
+
+template <int VEC> struct VecT;
+template <> struct VecT<4> { using type = float4; };
+template <> struct VecT<2> { using type = float2; };
+template <> struct VecT<1> { using type = float; };
+
+// L2-only loads: rows are updated by other SMs (and by our own red.global), so L1 must not serve them.
+template <int VEC> __device__ __forceinline__ void load_vec(const float *p, float (&v)[VEC]) {
+    if constexpr (VEC == 4) { float4 t = __ldcg(reinterpret_cast<const float4 *>(p)); v[0] = t.x; v[1] = t.y; v[2] = t.z; v[3] = t.w; }
+    else if constexpr (VEC == 2) { float2 t = __ldcg(reinterpret_cast<const float2 *>(p)); v[0] = t.x; v[1] = t.y; }
+    else { v[0] = __ldcg(p); }
+}
+template <int VEC> __device__ __forceinline__ void store_vec(float *p, const float (&v)[VEC]) {
+    if constexpr (VEC == 4) __stcg(reinterpret_cast<float4 *>(p), make_float4(v[0], v[1], v[2], v[3]));
+    else if constexpr (VEC == 2) __stcg(reinterpret_cast<float2 *>(p), make_float2(v[0], v[1]));
+    else __stcg(p, v[0]);
+}
+// no-return vector reduction at L2 (sm_90+): one instruction per 16 bytes
+template <int VEC> __device__ __forceinline__ void red_vec(float *p, const float (&v)[VEC]) {
+    if constexpr (VEC == 4)
+        asm volatile("red.relaxed.gpu.global.add.v4.f32 [%0], {%1, %2, %3, %4};" ::"l"(p), "f"(v[0]), "f"(v[1]), "f"(v[2]), "f"(v[3]) : "memory");
+    else if constexpr (VEC == 2)
+        asm volatile("red.relaxed.gpu.global.add.v2.f32 [%0], {%1, %2};" ::"l"(p), "f"(v[0]), "f"(v[1]) : "memory");
+    else
+        asm volatile("red.relaxed.gpu.global.add.f32 [%0], %1;" ::"l"(p), "f"(v[0]) : "memory");
+}
+
+// Shuffles name only the lanes of the calling group: groups of one warp may run different trip counts.
+template <int G> __device__ __forceinline__ unsigned group_mask() {
+    if constexpr (G == 32) return FULL;
+    else return ((1u << G) - 1u) << ((threadIdx.x & 31) & ~(G - 1));
+}
+template <int G> __device__ __forceinline__ float group_sum(float v, unsigned mask) {
+#pragma unroll
+    for (int off = G >> 1; off > 0; off >>= 1) v += __shfl_xor_sync(mask, v, off, G);
+    return v;
+}
+
+struct SgnsArgs {
+    float *w_in, *w_out;                 // tables (read-only in MODE_GRAD)
+    float *grad_in, *grad_out;           // MODE_GRAD only (may be null)
+    const int64_t *inputs, *targets, *noise;   // explicit modes
+    const int32_t *tokens;               // MODE_WALK
+    const float *alias_prob; const int32_t *alias_idx;
+    double *stats;
+    int64_t n_units;                     // batch rows (explicit) or n_seq * (L - 2r) centres (walk)
+    int64_t vocab;
+    int emb, n_ctx, n_neg;
+    int seq_len, radius, n_cen, row_offset;
+    float lr, grad_scale;
+    uint64_t seed; int64_t id_base;
+    int scatter_store;
+};
+
+template <bool FAST> __device__ __forceinline__ float sigmoidf_(float x) {
+    if constexpr (FAST) return __fdividef(1.0f, 1.0f + __expf(-x));
+    else return 1.0f / (1.0f + expf(-x));
+}
+template <bool FAST> __device__ __forceinline__ float logf_(float x) {
+    if constexpr (FAST) return __logf(x); else return logf(x);
+}
+
+template <int MODE, int VEC, int G, int R>
+__global__ void __launch_bounds__(SGNS_THREADS)
+sgns_kernel(const SgnsArgs a) {
+    constexpr int GROUPS_PER_BLOCK = SGNS_THREADS / G;
+    constexpr int CH = (G < 8) ? G : (8 / R);       // target rows in flight per chunk; every lane owns <= 1 of them
+    constexpr bool FAST = MODE != MODE_GRAD;
+    const int lg = threadIdx.x & (G - 1);
+    const int64_t gid = (int64_t)blockIdx.x * GROUPS_PER_BLOCK + (threadIdx.x / G);
+    const int64_t n_groups = (int64_t)gridDim.x * GROUPS_PER_BLOCK;
+    const int E = a.emb, N = a.n_ctx, K = a.n_neg, T = 1 + a.n_neg;
+    const unsigned gmask = group_mask<G>();
+
+    int eoff[R]; bool ok[R];
+#pragma unroll
+    for (int j = 0; j < R; ++j) { eoff[j] = (lg + j * G) * VEC; ok[j] = eoff[j] < E; }
+
+    float loss_pos = 0.f, loss_neg = 0.f;
+    unsigned cnt_recall = 0, cnt_fp = 0, cnt_pairs = 0;
+
+    // MODE_WALK: contiguous span of centres per group (neighbouring centres of a walk share rows -> L2 locality and
+    // no intra-walk races); explicit modes: grid-stride.
+    int64_t u_begin, u_end, u_step;
+    if constexpr (MODE == MODE_WALK) {
+        const int64_t span = (a.n_units + n_groups - 1) / n_groups;
+        u_begin = gid * span; u_end = min(a.n_units, u_begin + span); u_step = 1;
+    } else {
+        u_begin = gid; u_end = a.n_units; u_step = n_groups;
+    }
+
+    for (int64_t u = u_begin; u < u_end; u += u_step) {
+        int64_t crow; const int32_t *seq = nullptr; int pos = 0;
+        if constexpr (MODE == MODE_WALK) {
+            const int64_t s = u / a.n_cen;
+            pos = a.radius + (int)(u - s * a.n_cen);
+            seq = a.tokens + s * a.seq_len;
+            crow = (int64_t)__ldg(seq + pos) + a.row_offset;
+        } else {
+            crow = __ldg(a.inputs + u);
+        }
+        float cen[R][VEC], acc[R][VEC];
+        const float *cptr = a.w_in + crow * E;
+#pragma unroll
+        for (int j = 0; j < R; ++j) {
+#pragma unroll
+            for (int e = 0; e < VEC; ++e) { cen[j][e] = 0.f; acc[j][e] = 0.f; }
+            if (ok[j]) load_vec<VEC>(cptr + eoff[j], cen[j]);
+        }
+
+        for (int n = 0; n < N; ++n) {
+            for (int t0 = 0; t0 < T; t0 += CH) {
+                const int cnt = min(CH, T - t0);
+                // lane `lg` resolves the row id of target t0 + lg (0 = the context, 1.. = negatives)
+                int my = 0;
+                if (lg < cnt) {
+                    const int tj = t0 + lg;
+                    if (tj == 0) {
+                        if constexpr (MODE == MODE_WALK) {
+                            const int off = (n < a.radius) ? (pos - a.radius + n) : (pos + 1 + n - a.radius);
+                            my = __ldg(seq + off) + a.row_offset;
+                        } else {
+                            my = (int)__ldg(a.targets + u * N + n);
+                        }
+                    } else if (MODE != MODE_WALK && a.noise != nullptr) {
+                        my = (int)__ldg(a.noise + (u * N + n) * K + (tj - 1));
+                    } else {
+                        const uint4 r = philox(a.seed, (uint64_t)(a.id_base + u), (uint32_t)(n * K + (tj - 1)), STREAM_NEG);
+                        my = (int)draw_row(a.alias_prob, a.alias_idx, (uint32_t)a.vocab, r.x, r.y);
+                    }
+                }
+                int tid[CH];
+                float row[CH][R][VEC];
+                float dot[CH];
+#pragma unroll
+                for (int c = 0; c < CH; ++c) tid[c] = __shfl_sync(gmask, my, c, G);
+#pragma unroll
+                for (int c = 0; c < CH; ++c) {
+                    const float *rp = a.w_out + (int64_t)tid[c] * E;
+#pragma unroll
+                    for (int j = 0; j < R; ++j) {
+#pragma unroll
+                        for (int e = 0; e < VEC; ++e) row[c][j][e] = 0.f;
+                        if (c < cnt && ok[j]) load_vec<VEC>(rp + eoff[j], row[c][j]);
+                    }
+                }
+#pragma unroll
+                for (int c = 0; c < CH; ++c) {
+                    float d = 0.f;
+#pragma unroll
+                    for (int j = 0; j < R; ++j)
+#pragma unroll
+                        for (int e = 0; e < VEC; ++e) d = fmaf(row[c][j][e], cen[j][e], d);
+                    dot[c] = group_sum<G>(d, gmask);
+                }
+#pragma unroll
+                for (int c = 0; c < CH; ++c) {
+                    if (c < cnt) {
+                        const bool positive = (t0 + c) == 0;
+                        const float s = dot[c];
+                        float g;   // dL_pair / ds
+                        if (positive) {
+                            const float sig = sigmoidf_<FAST>(s);
+                            loss_pos -= logf_<FAST>(fmaxf(sig, CLAMP_MIN));
+                            g = (sig > CLAMP_MIN) ? -sigmoidf_<FAST>(-s) : 0.f;
+                            cnt_recall += sig >= 0.5f;
+                            cnt_pairs += 1;
+                        } else {
+                            const float sig_m = sigmoidf_<FAST>(-s);
+                            loss_neg -= logf_<FAST>(fmaxf(sig_m, CLAMP_MIN));
+                            const float sig = sigmoidf_<FAST>(s);
+                            g = (sig_m > CLAMP_MIN) ? sig : 0.f;
+                            cnt_fp += sig >= 0.5f;
+                        }
+                        if constexpr (MODE == MODE_GRAD) {
+                            const float gs = g * a.grad_scale;
+#pragma unroll
+                            for (int j = 0; j < R; ++j) {
+                                float d[VEC];
+#pragma unroll
+                                for (int e = 0; e < VEC; ++e) { acc[j][e] = fmaf(gs, row[c][j][e], acc[j][e]); d[e] = gs * cen[j][e]; }
+                                if (a.grad_out && ok[j]) red_vec<VEC>(a.grad_out + (int64_t)tid[c] * E + eoff[j], d);
+                            }
+                        } else {
+                            const float step = -a.lr * g;
+                            float *rp = a.w_out + (int64_t)tid[c] * E;
+#pragma unroll
+                            for (int j = 0; j < R; ++j) {
+                                float d[VEC];
+#pragma unroll
+                                for (int e = 0; e < VEC; ++e) {
+                                    acc[j][e] = fmaf(step, row[c][j][e], acc[j][e]);
+                                    d[e] = step * cen[j][e];
+                                }
+                                if (ok[j]) {
+                                    if (a.scatter_store) {
+#pragma unroll
+                                        for (int e = 0; e < VEC; ++e) d[e] += row[c][j][e];
+                                        store_vec<VEC>(rp + eoff[j], d);
+                                    } else {
+                                        red_vec<VEC>(rp + eoff[j], d);
+                                    }
+                                }
+                            }
+                        }
+                    }
+                }
+            }
+        }
+        // centre row: one write per centre for the whole window
+#pragma unroll
+        for (int j = 0; j < R; ++j) {
+            if (!ok[j]) continue;
+            if constexpr (MODE == MODE_GRAD) {
+                if (a.grad_in) red_vec<VEC>(a.grad_in + crow * E + eoff[j], acc[j]);
+            } else {
+                float *cp = a.w_in + crow * E + eoff[j];
+                if (a.scatter_store) {
+                    float d[VEC];
+#pragma unroll
+                    for (int e = 0; e < VEC; ++e) d[e] = cen[j][e] + acc[j][e];
+                    store_vec<VEC>(cp, d);
+                } else {
+                    red_vec<VEC>(cp, acc[j]);
+                }
+            }
+        }
+    }
+
+    // block-level reduction of the statistics: one double atomic per block per statistic
+    __shared__ double sred[SE_STATS_LEN];
+    if (threadIdx.x < SE_STATS_LEN) sred[threadIdx.x] = 0.0;
+    __syncthreads();
+    if (lg == 0 && (cnt_pairs != 0)) {
+        atomicAdd(&sred[0], (double)loss_pos);
+        atomicAdd(&sred[1], (double)loss_neg);
+        atomicAdd(&sred[2], (double)cnt_recall);
+        atomicAdd(&sred[3], (double)cnt_fp);
+        atomicAdd(&sred[4], (double)cnt_pairs);
+        atomicAdd(&sred[5], (double)cnt_pairs * (double)K);
+    }
+    __syncthreads();
+    if (threadIdx.x < SE_STATS_LEN && a.stats && sred[threadIdx.x] != 0.0) atomicAdd(a.stats + threadIdx.x, sred[threadIdx.x]);
+}
+
+template <int MODE, int VEC, int G, int R>
+int launch_one(const SgnsArgs &a, cudaStream_t stream) {
+    auto kern = sgns_kernel<MODE, VEC, G, R>;
+    int occ = 0;
+    if (check_cuda(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, kern, SGNS_THREADS, 0), "occupancy") != SE_OK) return SE_ERR_CUDA;
+    if (occ < 1) occ = 1;
+    const int sms = sm_count();
+    if (sms <= 0) return SE_ERR_CUDA;
+    constexpr int GPB = SGNS_THREADS / G;
+    int64_t blocks = (a.n_units + GPB - 1) / GPB;
+    const int64_t cap = (int64_t)sms * occ;          // persistent: exactly one resident wave
+    if (blocks > cap) blocks = cap;
+    if (blocks < 1) blocks = 1;
+    kern<<<(int)blocks, SGNS_THREADS, 0, stream>>>(a);
+    return check_cuda(cudaGetLastError(), "sgns_kernel launch");
+}
+
+template <int MODE, int VEC>
+int launch_vec(const SgnsArgs &a, int nvec, cudaStream_t stream) {
+    if (nvec <= 1) return launch_one<MODE, VEC, 1, 1>(a, stream);
+    if (nvec <= 2) return launch_one<MODE, VEC, 2, 1>(a, stream);
+    if (nvec <= 4) return launch_one<MODE, VEC, 4, 1>(a, stream);
+    if (nvec <= 8) return launch_one<MODE, VEC, 8, 1>(a, stream);
+    if (nvec <= 16) return launch_one<MODE, VEC, 16, 1>(a, stream);
+    if (nvec <= 32) return launch_one<MODE, VEC, 32, 1>(a, stream);
+    if (nvec <= 64) return launch_one<MODE, VEC, 32, 2>(a, stream);
+    if (nvec <= 128) return launch_one<MODE, VEC, 32, 4>(a, stream);
+    if (nvec <= 256) return launch_one<MODE, VEC, 32, 8>(a, stream);
+    set_error("embedding size %d not supported (max %d)", a.emb, 256 * VEC);
+    return SE_ERR_UNSUPPORTED;
+}
+
+template <int MODE>
+int launch(const SgnsArgs &a, cudaStream_t stream) {
+    if (a.n_units <= 0) return SE_OK;
+    const bool al16 = ((uintptr_t)a.w_in % 16 == 0) && ((uintptr_t)a.w_out % 16 == 0) &&
+                      (MODE != MODE_GRAD || (((uintptr_t)a.grad_in % 16 == 0) && ((uintptr_t)a.grad_out % 16 == 0)));
+    const bool al8 = ((uintptr_t)a.w_in % 8 == 0) && ((uintptr_t)a.w_out % 8 == 0) &&
+                     (MODE != MODE_GRAD || (((uintptr_t)a.grad_in % 8 == 0) && ((uintptr_t)a.grad_out % 8 == 0)));
+    if (a.emb % 4 == 0 && al16) return launch_vec<MODE, 4>(a, a.emb / 4, stream);
+    if (a.emb % 2 == 0 && al8) return launch_vec<MODE, 2>(a, a.emb / 2, stream);
+    return launch_vec<MODE, 1>(a, a.emb, stream);
+}
+
+// SkipGram.forward: one group per (b, j) score would starve small batches; one group per b, loop over m.
+template <int G>
+__global__ void __launch_bounds__(256)
+scores_kernel(const float *__restrict__ w_in, const float *__restrict__ w_out, int emb, const int64_t *__restrict__ inputs,
+              const int64_t *__restrict__ outputs, int64_t total, int m, int proba, float *__restrict__ out) {
+    const int lg = threadIdx.x & (G - 1);
+    const int64_t gid = ((int64_t)blockIdx.x * blockDim.x + threadIdx.x) / G;
+    const int64_t n_groups = (int64_t)gridDim.x * blockDim.x / G;
+    for (int64_t i = gid; i < total; i += n_groups) {
+        const float *c = w_in + __ldg(inputs + i / m) * emb;
+        const float *o = w_out + __ldg(outputs + i) * emb;
+        float d = 0.f;
+        for (int e = lg; e < emb; e += G) d = fmaf(__ldcg(o + e), __ldcg(c + e), d);
+        d = group_sum<G>(d, group_mask<G>());
+        if (lg == 0) out[i] = proba ? 1.0f / (1.0f + expf(-d)) : d;
+    }
+}
+
+int common_checks(const char *fn, const void *w_in, const void *w_out, int64_t vocab, int emb, int n_neg) {
+    if (!w_in || !w_out) { set_error("%s: null embedding table", fn); return SE_ERR_INVALID_ARG; }
+    if (vocab < 1 || vocab > 0x7fffffffll) { set_error("%s: vocab %lld out of range", fn, (long long)vocab); return SE_ERR_INVALID_ARG; }
+    if (emb < 1) { set_error("%s: embedding size must be >= 1", fn); return SE_ERR_INVALID_ARG; }
+    if (n_neg < 0) { set_error("%s: negative sample count must be >= 0", fn); return SE_ERR_INVALID_ARG; }
+    return SE_OK;
+}
+
+}  // namespace
+}  // namespace se
+
+extern "C" int se_skipgram_scores(const float *w_in, const float *w_out, int64_t vocab, int emb, const int64_t *inputs,
+                                  const int64_t *outputs, int64_t batch, int m, int proba, float *out, void *stream) {
+    int rc = se::common_checks("se_skipgram_scores", w_in, w_out, vocab, emb, 0);
+    if (rc != SE_OK) return rc;
+    SE_REQUIRE(inputs && outputs && out && batch >= 0 && m >= 1, "se_skipgram_scores: bad arguments");
+    const int64_t total = batch * m;
+    if (total == 0) return SE_OK;
+    const int sms = se::sm_count();
+    if (sms <= 0) return SE_ERR_CUDA;
+    if (emb >= 32) {
+        int64_t blocks = (total + 7) / 8; if (blocks > sms * 8) blocks = sms * 8;
+        se::scores_kernel<32><<<(int)blocks, 256, 0, (cudaStream_t)stream>>>(w_in, w_out, emb, inputs, outputs, total, m, proba, out);
+    } else {
+        int64_t blocks = (total + 63) / 64; if (blocks > sms * 8) blocks = sms * 8;
+        se::scores_kernel<4><<<(int)blocks, 256, 0, (cudaStream_t)stream>>>(w_in, w_out, emb, inputs, outputs, total, m, proba, out);
+    }
+    return se::check_cuda(cudaGetLastError(), "scores_kernel launch");
+}
+
+extern "C" int se_sgns_grad(const float *w_in, const float *w_out, int64_t vocab, int emb, const int64_t *inputs,
+                            const int64_t *targets, const int64_t *noise, int64_t batch, int n_ctx, int n_neg,
+                            double *stats, float *grad_in, float *grad_out, void *stream) {
+    int rc = se::common_checks("se_sgns_grad", w_in, w_out, vocab, emb, n_neg);
+    if (rc != SE_OK) return rc;
+    SE_REQUIRE(inputs && targets && (noise || n_neg == 0), "se_sgns_grad: null index tensor");
+    SE_REQUIRE(batch >= 0 && n_ctx >= 1, "se_sgns_grad: bad batch shape");
+    SE_REQUIRE((grad_in == nullptr) == (grad_out == nullptr), "se_sgns_grad: pass both gradient buffers or neither");
+    se::SgnsArgs a{};
+    a.w_in = const_cast<float *>(w_in); a.w_out = const_cast<float *>(w_out);
+    a.grad_in = grad_in; a.grad_out = grad_out;
+    a.inputs = inputs; a.targets = targets; a.noise = noise;
+    a.stats = stats; a.n_units = batch; a.vocab = vocab; a.emb = emb; a.n_ctx = n_ctx; a.n_neg = n_neg;
+    a.grad_scale = batch > 0 ? 1.0f / (float)(batch * n_ctx) : 0.f;
+    return se::launch<se::MODE_GRAD>(a, (cudaStream_t)stream);
+}
+
+extern "C" int se_sgns_step(float *w_in, float *w_out, int64_t vocab, int emb, const int64_t *inputs,
+                            const int64_t *targets, const int64_t *noise, int64_t batch, int n_ctx, int n_neg,
+                            const float *alias_prob, const int32_t *alias_idx, float lr, uint64_t seed,
+                            int64_t pair_id_base, int flags, double *stats, void *stream) {
+    int rc = se::common_checks("se_sgns_step", w_in, w_out, vocab, emb, n_neg);
+    if (rc != SE_OK) return rc;
+    SE_REQUIRE(inputs && targets, "se_sgns_step: null index tensor");
+    SE_REQUIRE(batch >= 0 && n_ctx >= 1, "se_sgns_step: bad batch shape");
+    SE_REQUIRE((alias_prob == nullptr) == (alias_idx == nullptr), "se_sgns_step: pass both alias arrays or neither");
+    SE_REQUIRE(flags == SE_SGNS_SCATTER_RED || flags == SE_SGNS_SCATTER_STORE, "se_sgns_step: unknown flags %d", flags);
+    se::SgnsArgs a{};
+    a.w_in = w_in; a.w_out = w_out; a.inputs = inputs; a.targets = targets; a.noise = noise;
+    a.alias_prob = alias_prob; a.alias_idx = alias_idx;
+    a.stats = stats; a.n_units = batch; a.vocab = vocab; a.emb = emb; a.n_ctx = n_ctx; a.n_neg = n_neg;
+    a.lr = lr; a.seed = seed; a.id_base = pair_id_base; a.scatter_store = flags == SE_SGNS_SCATTER_STORE;
+    return se::launch<se::MODE_STEP>(a, (cudaStream_t)stream);
+}
+
+extern "C" int se_sgns_update_walks(float *w_in, float *w_out, int64_t vocab, int emb, const int32_t *tokens,
+                                    int64_t n_seq, int seq_len, int radius, int n_neg, int row_offset,
+                                    const float *alias_prob, const int32_t *alias_idx, float lr, uint64_t seed,
+                                    int64_t centre_id_base, int flags, double *stats, void *stream) {
+    int rc = se::common_checks("se_sgns_update_walks", w_in, w_out, vocab, emb, n_neg);
+    if (rc != SE_OK) return rc;
+    SE_REQUIRE(tokens && n_seq >= 0, "se_sgns_update_walks: null tokens");
+    SE_REQUIRE(radius >= 1, "se_sgns_update_walks: context radius must be >= 1");
+    // W2VCollateFunctional asserts text_length >= 2r+1 (torch_dataset.py:298)
+    SE_REQUIRE(seq_len >= 2 * radius + 1, "Text is too short! [text_length=%d] < [min_text_length=%d]", seq_len, 2 * radius + 1);
+    SE_REQUIRE((alias_prob == nullptr) == (alias_idx == nullptr), "se_sgns_update_walks: pass both alias arrays or neither");
+    SE_REQUIRE(flags == SE_SGNS_SCATTER_RED || flags == SE_SGNS_SCATTER_STORE, "se_sgns_update_walks: unknown flags %d", flags);
+    se::SgnsArgs a{};
+    a.w_in = w_in; a.w_out = w_out; a.tokens = tokens; a.alias_prob = alias_prob; a.alias_idx = alias_idx;
+    a.stats = stats; a.vocab = vocab; a.emb = emb; a.n_ctx = 2 * radius; a.n_neg = n_neg;
+    a.seq_len = seq_len; a.radius = radius; a.n_cen = seq_len - 2 * radius; a.row_offset = row_offset;
+    a.n_units = n_seq * a.n_cen;
+    a.lr = lr; a.seed = seed; a.id_base = centre_id_base; a.scatter_store = flags == SE_SGNS_SCATTER_STORE;
+    return se::launch<se::MODE_WALK>(a, (cudaStream_t)stream);
+}

@@ -1,0 +1,311 @@
+"""
+ctypes binding of the C ABI in include/se_b200.h (deepwalk-and-node2vec_b200/lib/libse_b200.so).
+
+This is the ONLY compute path of the package: every wrapper raises if the library is missing, if a symbol
+declared in the header is not exported, or if its tensors are not CUDA tensors.  torch is used for device
+memory and streams only -- pointers and sizes cross the boundary, never torch types.
+"""
+import ctypes
+import os
+import re
+from typing import Dict, Optional
+
+import torch
+
+PKG_ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+REPO_ROOT = os.path.dirname(PKG_ROOT)
+LIB_PATH = os.environ.get('SE_B200_LIB', os.path.join(PKG_ROOT, 'lib', 'libse_b200.so'))
+HEADER_PATH = os.path.join(REPO_ROOT, 'include', 'se_b200.h')
+
+SE_OK = 0
+RULE_REFERENCE = 0
+RULE_PAPER = 1
+SCATTER_RED = 0
+SCATTER_STORE = 1
+STATS_LEN = 6
+
+_lib = None
+_launches = 0    # kernels launched through this module (bench.py reports it as gpu_launches)
+
+c_i64, c_i32, c_int, c_f64, c_f32, c_u64, c_p = (ctypes.c_int64, ctypes.c_int32, ctypes.c_int, ctypes.c_double,
+                                                 ctypes.c_float, ctypes.c_uint64, ctypes.c_void_p)
+
+_SIGNATURES = {
+    'se_version': (ctypes.c_char_p, []),
+    'se_last_error': (ctypes.c_char_p, []),
+    'se_device_info': (c_int, [c_p, c_p, c_p]),
+    'se_walk_exact_scratch_bytes': (c_i64, [c_i64, c_i64]),
+    'se_walk_exact': (c_int, [c_p, c_p, c_p, c_p, c_int, c_i64, c_i64, c_p, c_i64, c_int, c_f64, c_f64, c_int, c_int,
+                              c_p, c_p, c_i64, c_p, c_p]),
+    'se_walk': (c_int, [c_p, c_p, c_p, c_i64, c_int, c_p, c_i64, c_int, c_f64, c_f64, c_int, c_int, c_u64, c_i64, c_i64,
+                        c_p, c_p, c_p]),
+    'se_alias_build_host': (c_int, [c_p, c_i64, c_f64, c_p, c_p]),
+    'se_sample_negatives': (c_int, [c_p, c_p, c_i64, c_u64, c_i64, c_i64, c_p, c_p]),
+    'se_skipgram_scores': (c_int, [c_p, c_p, c_i64, c_int, c_p, c_p, c_i64, c_int, c_int, c_p, c_p]),
+    'se_sgns_grad': (c_int, [c_p, c_p, c_i64, c_int, c_p, c_p, c_p, c_i64, c_int, c_int, c_p, c_p, c_p, c_p]),
+    'se_sgns_step': (c_int, [c_p, c_p, c_i64, c_int, c_p, c_p, c_p, c_i64, c_int, c_int, c_p, c_p, c_f32, c_u64, c_i64,
+                             c_int, c_p, c_p]),
+    'se_sgns_update_walks': (c_int, [c_p, c_p, c_i64, c_int, c_p, c_i64, c_int, c_int, c_int, c_int, c_p, c_p, c_f32,
+                                     c_u64, c_i64, c_int, c_p, c_p]),
+    'se_host_walk_sgns_step': (c_int, [c_p, c_p, c_p, c_i64, c_int, c_p, c_i64, c_int, c_f64, c_f64, c_int, c_int, c_u64,
+                                       c_i64, c_p, c_p, c_i64, c_int, c_int, c_int, c_int, c_p, c_p, c_f32, c_int,
+                                       c_p, c_p, c_p, c_p, c_p, c_p]),
+}
+
+
+def header_symbols():
+    """Function names declared in include/se_b200.h."""
+    text = open(HEADER_PATH).read()
+    text = re.sub(r'/\*.*?\*/', '', text, flags=re.S)
+    return sorted(set(re.findall(r'\b(se_[a-z0-9_]+)\s*\(', text)))
+
+
+def load():
+    """dlopen the native library and bind every symbol of the header.  Does not need a GPU."""
+    global _lib
+    if _lib is not None:
+        return _lib
+    if not os.path.exists(LIB_PATH):
+        raise RuntimeError(
+            f'native library not found at {LIB_PATH}: build it with `python __graft_entry__.py` '
+            f'(nvcc -gencode arch=compute_100a,code=sm_100a). There is no CPU fallback.')
+    lib = ctypes.CDLL(LIB_PATH)
+    declared = header_symbols()
+    missing = [s for s in declared if not hasattr(lib, s)]
+    if missing:
+        raise RuntimeError(f'{LIB_PATH} does not export {missing} declared in {HEADER_PATH}; rebuild it')
+    unbound = [s for s in declared if s not in _SIGNATURES]
+    if unbound:
+        raise RuntimeError(f'_native.py has no ctypes signature for {unbound}')
+    for name, (res, args) in _SIGNATURES.items():
+        fn = getattr(lib, name)
+        fn.restype, fn.argtypes = res, args
+    _lib = lib
+    return lib
+
+
+def launches() -> int:
+    return _launches
+
+
+def _check(rc: int):
+    if rc != SE_OK:
+        msg = load().se_last_error().decode()
+        if rc == -1:
+            raise AssertionError(msg)      # the reference signals bad arguments with `assert`
+        raise RuntimeError(f'se_b200 error {rc}: {msg}')
+
+
+def _ptr(t: Optional[torch.Tensor], dtype=None, name='tensor') -> Optional[int]:
+    if t is None:
+        return None
+    if not t.is_cuda:
+        raise RuntimeError(f'{name} must be a CUDA tensor: the B200 path has no CPU fallback')
+    if dtype is not None and t.dtype != dtype:
+        raise TypeError(f'{name} must be {dtype}, got {t.dtype}')
+    if not t.is_contiguous():
+        raise ValueError(f'{name} must be contiguous')
+    return t.data_ptr()
+
+
+def _on(t: torch.Tensor):
+    """Device guard; refuses CPU tensors before anything else happens."""
+    if not t.is_cuda:
+        raise RuntimeError('expected a CUDA tensor: the B200 path has no CPU fallback')
+    return torch.cuda.device(t.device)
+
+
+def _stream() -> int:
+    return torch.cuda.current_stream().cuda_stream
+
+
+def version() -> str:
+    return load().se_version().decode()
+
+
+def device_info() -> Dict[str, int]:
+    sm, major, minor = ctypes.c_int(), ctypes.c_int(), ctypes.c_int()
+    _check(load().se_device_info(ctypes.byref(sm), ctypes.byref(major), ctypes.byref(minor)))
+    return {'sm_count': sm.value, 'cc_major': major.value, 'cc_minor': minor.value}
+
+
+# ----------------------------------------------------------------------------------------------------------------
+# walks
+# ----------------------------------------------------------------------------------------------------------------
+def walk_exact(csr, starts: torch.Tensor, walk_len: int, p: float, q: float, node2vec: bool, rule: int,
+               uniforms: torch.Tensor) -> torch.Tensor:
+    """Reference-exact walks under supplied uniforms (one per transition) -> int32 [n_walks, walk_len]."""
+    global _launches
+    lib = load()
+    n = starts.numel()
+    out = torch.empty((n, walk_len), dtype=torch.int32, device=starts.device)
+    nbytes = lib.se_walk_exact_scratch_bytes(csr.max_degree, n)
+    scratch = torch.empty(max(int(nbytes), 8), dtype=torch.uint8, device=starts.device)
+    with _on(starts):
+        _check(lib.se_walk_exact(
+            _ptr(csr.rowptr, torch.int64, 'rowptr'), _ptr(csr.col, torch.int32, 'col'),
+            _ptr(csr.col_sorted, torch.int32, 'col_sorted'), _ptr(csr.w, torch.float64, 'w'), int(csr.w_is_int),
+            csr.n_nodes, csr.max_degree, _ptr(starts, torch.int32, 'starts'), n, int(walk_len), float(p), float(q),
+            int(bool(node2vec)), int(rule), _ptr(uniforms, torch.float64, 'uniforms'), scratch.data_ptr(),
+            scratch.numel(), out.data_ptr(), _stream()))
+    _launches += 1
+    return out
+
+
+def walk(csr, starts: torch.Tensor, walk_len: int, p: float, q: float, node2vec: bool, rule: int, seed: int,
+         walk_id_base: int = 0, walk_id_stride: int = 1, out: Optional[torch.Tensor] = None,
+         err_count: Optional[torch.Tensor] = None) -> torch.Tensor:
+    """Philox/rejection walks -> int32 [n_walks, walk_len]."""
+    global _launches
+    lib = load()
+    n = starts.numel()
+    if out is None:
+        out = torch.empty((n, walk_len), dtype=torch.int32, device=starts.device)
+    assert out.numel() >= n * walk_len
+    with _on(starts):
+        _check(lib.se_walk(
+            _ptr(csr.rowptr, torch.int64, 'rowptr'), _ptr(csr.col_sorted, torch.int32, 'col_sorted'),
+            _ptr(csr.wcdf, torch.float32, 'wcdf'), csr.n_nodes, int(csr.symmetric), _ptr(starts, torch.int32, 'starts'),
+            n, int(walk_len), float(p), float(q), int(bool(node2vec)), int(rule), int(seed) & (2 ** 64 - 1),
+            int(walk_id_base), int(walk_id_stride), _ptr(out, torch.int32, 'out'),
+            _ptr(err_count, torch.int32, 'err_count'), _stream()))
+    _launches += 1
+    return out
+
+
+# ----------------------------------------------------------------------------------------------------------------
+# negatives
+# ----------------------------------------------------------------------------------------------------------------
+def alias_build(counts, power: float, device) -> Dict[str, torch.Tensor]:
+    """Vose alias table for weights counts**power (host set-up), uploaded to `device`."""
+    import numpy as np
+    counts = np.ascontiguousarray(counts, dtype=np.float64)
+    prob = np.empty(len(counts), dtype=np.float32)
+    alias = np.empty(len(counts), dtype=np.int32)
+    _check(load().se_alias_build_host(counts.ctypes.data, len(counts), float(power), prob.ctypes.data, alias.ctypes.data))
+    return {'prob': torch.from_numpy(prob).to(device), 'alias': torch.from_numpy(alias).to(device)}
+
+
+def sample_negatives(n: int, vocab: int, seed: int, device, alias: Optional[Dict[str, torch.Tensor]] = None,
+                     draw_id_base: int = 0) -> torch.Tensor:
+    global _launches
+    out = torch.empty(n, dtype=torch.int64, device=device)
+    with _on(out):
+        _check(load().se_sample_negatives(
+            _ptr(alias['prob'], torch.float32) if alias else None, _ptr(alias['alias'], torch.int32) if alias else None,
+            int(vocab), int(seed) & (2 ** 64 - 1), int(draw_id_base), int(n), out.data_ptr(), _stream()))
+    _launches += 1
+    return out
+
+
+# ----------------------------------------------------------------------------------------------------------------
+# SGNS
+# ----------------------------------------------------------------------------------------------------------------
+def _stats_dict(stats: torch.Tensor) -> Dict[str, float]:
+    s = stats.tolist()
+    pairs = max(s[4], 1.0)
+    return {
+        'loss': (s[0] + s[1]) / pairs, 'positive-loss': s[0] / pairs, 'negative-loss': s[1] / pairs,
+        'recall': s[2] / pairs, 'precision': 1.0 - s[3] / max(s[5], 1.0), 'pairs': int(s[4]), 'negatives': int(s[5]),
+    }
+
+
+def skipgram_scores(w_in: torch.Tensor, w_out: torch.Tensor, inputs: torch.Tensor, outputs: torch.Tensor,
+                    proba: bool) -> torch.Tensor:
+    global _launches
+    batch, m = outputs.shape
+    out = torch.empty((batch, m), dtype=torch.float32, device=w_in.device)
+    with _on(w_in):
+        _check(load().se_skipgram_scores(
+            _ptr(w_in, torch.float32, 'w_in'), _ptr(w_out, torch.float32, 'w_out'), w_in.shape[0], w_in.shape[1],
+            _ptr(inputs.reshape(-1), torch.int64, 'inputs'), _ptr(outputs, torch.int64, 'outputs'), batch, m,
+            int(bool(proba)), out.data_ptr(), _stream()))
+    _launches += 1
+    return out
+
+
+def sgns_grad(w_in: torch.Tensor, w_out: torch.Tensor, inputs: torch.Tensor, targets: torch.Tensor,
+              noise: torch.Tensor, want_grads: bool = True, stats: Optional[torch.Tensor] = None) -> Dict:
+    """Loss dict (+ dense grads of the mean loss) for an explicit (inputs (B,1), targets (B,N), noise (B,N,K)) batch."""
+    global _launches
+    batch, n_ctx = targets.shape
+    n_neg = noise.shape[2] if noise is not None and noise.dim() == 3 else 0
+    own_stats = stats is None
+    if own_stats:
+        stats = torch.zeros(STATS_LEN, dtype=torch.float64, device=w_in.device)
+    g_in = torch.zeros_like(w_in) if want_grads else None
+    g_out = torch.zeros_like(w_out) if want_grads else None
+    with _on(w_in):
+        _check(load().se_sgns_grad(
+            _ptr(w_in, torch.float32, 'w_in'), _ptr(w_out, torch.float32, 'w_out'), w_in.shape[0], w_in.shape[1],
+            _ptr(inputs.reshape(-1), torch.int64, 'inputs'), _ptr(targets, torch.int64, 'targets'),
+            _ptr(noise, torch.int64, 'noise') if n_neg else None, batch, n_ctx, n_neg, stats.data_ptr(),
+            _ptr(g_in), _ptr(g_out), _stream()))
+    _launches += 1
+    out = _stats_dict(stats) if own_stats else {}
+    out['grad_in'], out['grad_out'] = g_in, g_out
+    return out
+
+
+def sgns_step(w_in: torch.Tensor, w_out: torch.Tensor, inputs: torch.Tensor, targets: torch.Tensor,
+              noise: Optional[torch.Tensor], n_neg: int, lr: float, seed: int = 0, pair_id_base: int = 0,
+              alias: Optional[Dict[str, torch.Tensor]] = None, flags: int = SCATTER_RED,
+              stats: Optional[torch.Tensor] = None) -> Optional[Dict[str, float]]:
+    """Fused in-place SGD on an explicit batch; `lr` multiplies the un-averaged per-pair gradient."""
+    global _launches
+    batch, n_ctx = targets.shape
+    own_stats = stats is None
+    if own_stats:
+        stats = torch.zeros(STATS_LEN, dtype=torch.float64, device=w_in.device)
+    with _on(w_in):
+        _check(load().se_sgns_step(
+            _ptr(w_in, torch.float32, 'w_in'), _ptr(w_out, torch.float32, 'w_out'), w_in.shape[0], w_in.shape[1],
+            _ptr(inputs.reshape(-1), torch.int64, 'inputs'), _ptr(targets, torch.int64, 'targets'),
+            _ptr(noise, torch.int64, 'noise'), batch, n_ctx, int(n_neg),
+            _ptr(alias['prob'], torch.float32) if alias else None, _ptr(alias['alias'], torch.int32) if alias else None,
+            float(lr), int(seed) & (2 ** 64 - 1), int(pair_id_base), int(flags), stats.data_ptr(), _stream()))
+    _launches += 1
+    return _stats_dict(stats) if own_stats else None
+
+
+def sgns_update_walks(w_in: torch.Tensor, w_out: torch.Tensor, tokens: torch.Tensor, radius: int, n_neg: int,
+                      row_offset: int, lr: float, seed: int, centre_id_base: int = 0,
+                      alias: Optional[Dict[str, torch.Tensor]] = None, flags: int = SCATTER_RED,
+                      stats: Optional[torch.Tensor] = None) -> Optional[Dict[str, float]]:
+    """The fused hot path on tokens int32 [n_seq, L]: windows + negatives + in-place SGNS update."""
+    global _launches
+    n_seq, seq_len = tokens.shape
+    own_stats = stats is None
+    if own_stats:
+        stats = torch.zeros(STATS_LEN, dtype=torch.float64, device=w_in.device)
+    with _on(w_in):
+        _check(load().se_sgns_update_walks(
+            _ptr(w_in, torch.float32, 'w_in'), _ptr(w_out, torch.float32, 'w_out'), w_in.shape[0], w_in.shape[1],
+            _ptr(tokens, torch.int32, 'tokens'), n_seq, seq_len, int(radius), int(n_neg), int(row_offset),
+            _ptr(alias['prob'], torch.float32) if alias else None, _ptr(alias['alias'], torch.int32) if alias else None,
+            float(lr), int(seed) & (2 ** 64 - 1), int(centre_id_base), int(flags), stats.data_ptr(), _stream()))
+    _launches += 1
+    return _stats_dict(stats) if own_stats else None
+
+
+def host_walk_sgns_step(csr, starts_host: torch.Tensor, walk_len: int, p: float, q: float, node2vec: bool, rule: int,
+                        seed: int, walk_id_base: int, w_in: torch.Tensor, w_out: torch.Tensor, radius: int, n_neg: int,
+                        row_offset: int, lr: float, scratch: Dict[str, torch.Tensor], stats_host: torch.Tensor,
+                        alias: Optional[Dict[str, torch.Tensor]] = None, flags: int = SCATTER_RED,
+                        walks_host: Optional[torch.Tensor] = None) -> None:
+    """HOST-buffer pipeline step (H2D starts -> walk -> fused SGNS -> D2H stats [+ walks]); synchronises."""
+    global _launches
+    assert not starts_host.is_cuda and starts_host.dtype == torch.int32 and starts_host.is_contiguous()
+    assert not stats_host.is_cuda and stats_host.dtype == torch.float64 and stats_host.numel() >= STATS_LEN
+    n = starts_host.numel()
+    with _on(w_in):
+        _check(load().se_host_walk_sgns_step(
+            _ptr(csr.rowptr, torch.int64), _ptr(csr.col_sorted, torch.int32), _ptr(csr.wcdf, torch.float32), csr.n_nodes,
+            int(csr.symmetric), starts_host.data_ptr(), n, int(walk_len), float(p), float(q), int(bool(node2vec)),
+            int(rule), int(seed) & (2 ** 64 - 1), int(walk_id_base), _ptr(w_in, torch.float32), _ptr(w_out, torch.float32),
+            w_in.shape[0], w_in.shape[1], int(radius), int(n_neg), int(row_offset),
+            _ptr(alias['prob'], torch.float32) if alias else None, _ptr(alias['alias'], torch.int32) if alias else None,
+            float(lr), int(flags), _ptr(scratch['starts'], torch.int32), _ptr(scratch['walks'], torch.int32),
+            _ptr(scratch['stats'], torch.float64), walks_host.data_ptr() if walks_host is not None else None,
+            stats_host.data_ptr(), _stream()))
+    _launches += 2

@@ -1,0 +1,162 @@
+/*
+ * se_b200.h -- C ABI of the B200-native (sm_100a) random-walk + SGNS hot path.
+ *
+ * The reference (Robotmurlock/Deepwalk-and-Node2vec) is pure Python and has no FFI of its own; every
+ * entry point below names the reference interface (file:line under the reference root) whose arithmetic
+ * it replaces.  INTEGRATION.md shows the ctypes binding a maintainer of the reference would add.
+ *
+ * Conventions
+ *   - plain pointers and sizes only; no torch / C++ types cross the boundary
+ *   - every `*_dev` / unqualified buffer pointer is a DEVICE pointer owned by the caller; the library never
+ *     allocates or frees caller-visible memory, scratch is passed in
+ *   - `stream` is a cudaStream_t passed as void* (NULL = legacy default stream); all work is enqueued on it and the
+ *     call returns without synchronising, except the `se_host_*` entry points, which take HOST buffers, copy them
+ *     and synchronise before returning
+ *   - return value: SE_OK, or a negative SE_ERR_* code; se_last_error() gives a thread-local message.
+ *     Nothing throws across the ABI.  There is no CPU fallback: without a usable sm_100 device every compute
+ *     entry point returns SE_ERR_CUDA.
+ *   - no global mutable state besides the thread-local error string: re-entrant across streams and devices
+ *   - node ids are int32 in [0, n_nodes); embedding-table rows are int64 on the explicit-index API (the reference's
+ *     LongTensors) and id + row_offset on the walk-driven API (row 0 = '<unk>',
+ *     word2vec/dataloader/torch_dataset.py:99-110)
+ */
+#ifndef SE_B200_H
+#define SE_B200_H
+
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define SE_OK 0
+#define SE_ERR_INVALID_ARG (-1)
+#define SE_ERR_CUDA (-2)
+#define SE_ERR_UNSUPPORTED (-3)
+
+/* node2vec multiplier rule */
+#define SE_RULE_REFERENCE 0 /* what the reference CODE does: x==t -> 1/p ; t in N(x) -> 1/q ; else 1
+                               (graph/random_walk_generator.py:101-108) */
+#define SE_RULE_PAPER 1     /* node2vec paper / reference README: distance 1 -> 1 ; distance 2 -> 1/q */
+
+/* flags for the SGNS update kernels */
+#define SE_SGNS_SCATTER_RED 0   /* red.global.add.v4.f32 scatter: concurrent updates of a row all land */
+#define SE_SGNS_SCATTER_STORE 1 /* plain read-modify-write stores: classic racy Hogwild */
+
+/* stats layout written by the SGNS kernels (double[SE_STATS_LEN], ACCUMULATED into, caller zeroes):
+ *   [0] sum over pairs of positive loss   -log clamp(sigmoid(s+), 1e-6)          (word2vec/loss.py:15)
+ *   [1] sum over pairs of negative loss   -sum_k log clamp(sigmoid(-s-), 1e-6)   (word2vec/loss.py:16)
+ *   [2] number of positive pairs with sigmoid(s+) >= 0.5   (recall numerator,     word2vec/trainer.py:145-146)
+ *   [3] number of negatives with sigmoid(s-) >= 0.5        (1 - precision numer., word2vec/trainer.py:148-149)
+ *   [4] number of positive pairs processed
+ *   [5] number of negatives processed
+ */
+#define SE_STATS_LEN 6
+
+const char *se_version(void);
+const char *se_last_error(void);
+/* sm count and compute capability of the current device. */
+int se_device_info(int *sm_count, int *cc_major, int *cc_minor);
+
+/* ------------------------------------------------------------------------------------------------------------
+ * Random walks.  Replaces DeepWalk.walk / Node2Vec.walk (graph/random_walk_generator.py:61-72, 94-119) and the
+ * per-node weight helpers (:41-53) over a CSR graph.  A walk has `walk_len` NODES (walk_len-1 transitions, :64,:98).
+ * out[n_walks * walk_len] int32 node ids, row-major.
+ * ---------------------------------------------------------------------------------------------------------- */
+
+/* Exact mode: fp64 inverse-CDF selection consuming ONE supplied uniform per transition, bit-identical to the
+ * reference under `random.choices` (CPython 3.12 sum()/accumulate/bisect semantics; see oracle/walk_oracle.py).
+ *   rowptr[n_nodes+1], col[nnz] in the reference's CDF order (networkx adjacency order),
+ *   col_sorted[nnz]  each row ascending (may alias col when rows are already sorted) -- membership tests,
+ *   w[nnz] fp64 edge weights or NULL (unweighted); w_is_int != 0 when the weights are python ints,
+ *   uniforms[n_walks * (walk_len-1)] fp64 in [0,1),
+ *   scratch: >= se_walk_exact_scratch_bytes(max_degree, n_walks) bytes. */
+int64_t se_walk_exact_scratch_bytes(int64_t max_degree, int64_t n_walks);
+int se_walk_exact(const int64_t *rowptr, const int32_t *col, const int32_t *col_sorted, const double *w, int w_is_int,
+                  int64_t n_nodes, int64_t max_degree, const int32_t *starts, int64_t n_walks, int walk_len,
+                  double p, double q, int node2vec, int rule, const double *uniforms,
+                  void *scratch, int64_t scratch_bytes, int32_t *out, void *stream);
+
+/* Fast mode: one warp per walk, counter-based Philox4x32-10 keyed by (seed; walk id, step, try), rejection sampling
+ * of the 1/p, 1, 1/q multipliers with binary-search membership tests; neighbour lists up to 128 entries are staged in
+ * shared memory.  Same transition distribution as the reference rule (validated by chi-square), not the same draws.
+ *   col[nnz]: each row ASCENDING;  wcdf[nnz]: per-row inclusive prefix sums of the edge weights (fp32) or NULL,
+ *   walk id of out row i = walk_id_base + i * walk_id_stride  (so any sharding reproduces the 1-GPU walks),
+ *   symmetric != 0 promises x in N(t) <=> t in N(x) (undirected graph) and enables the staged-list membership test,
+ *   err_count (int32[1], may be NULL) counts walks that hit a degree-0 node (the reference raises there; the walk
+ *   stays on that node). */
+int se_walk(const int64_t *rowptr, const int32_t *col, const float *wcdf, int64_t n_nodes, int symmetric,
+            const int32_t *starts, int64_t n_walks, int walk_len, double p, double q, int node2vec, int rule,
+            uint64_t seed, int64_t walk_id_base, int64_t walk_id_stride, int32_t *out, int32_t *err_count,
+            void *stream);
+
+/* ------------------------------------------------------------------------------------------------------------
+ * Negative sampling.  Replaces generate_noise_batch (word2vec/utils/sampling.py:7-21): the reference draws
+ * UNIFORM ids over [0, V); the alias table adds unigram^power (power = 0.75 is word2vec's; power = 0 reproduces
+ * the reference distribution).
+ * ---------------------------------------------------------------------------------------------------------- */
+
+/* Vose alias table on the HOST (one-off set-up, O(V)); counts_host[V] >= 0, prob_host[V] fp32, alias_host[V] int32. */
+int se_alias_build_host(const double *counts_host, int64_t vocab, double power, float *prob_host, int32_t *alias_host);
+
+/* out[n] int64 ids; id i is Philox(seed; draw_id_base + i).  prob/alias NULL -> uniform over [0, vocab). */
+int se_sample_negatives(const float *prob, const int32_t *alias, int64_t vocab, uint64_t seed, int64_t draw_id_base,
+                        int64_t n, int64_t *out, void *stream);
+
+/* ------------------------------------------------------------------------------------------------------------
+ * SkipGram / SGNS on explicit index tensors (the reference's (inputs (B,1), targets (B,N), noise (B,N,K)) int64).
+ * Tables are fp32 row-major [vocab x emb], 16-byte aligned.
+ * ---------------------------------------------------------------------------------------------------------- */
+
+/* SkipGram.forward (word2vec/model.py:79-91): out[b*m + j] = <W_in[inputs[b]], W_out[outputs[b*m + j]]>,
+ * sigmoid applied when proba != 0. */
+int se_skipgram_scores(const float *w_in, const float *w_out, int64_t vocab, int emb, const int64_t *inputs,
+                       const int64_t *outputs, int64_t batch, int m, int proba, float *out, void *stream);
+
+/* Word2VecTrainer.training_step + backward (word2vec/trainer.py:131-152, word2vec/loss.py:14-22): loss sums /
+ * counters into stats (divide by stats[4] for the reference's means) and, when grad_in/grad_out are non-NULL,
+ * ACCUMULATES the dense gradients of the MEAN loss into them (caller zeroes; same values as autograd). */
+int se_sgns_grad(const float *w_in, const float *w_out, int64_t vocab, int emb, const int64_t *inputs,
+                 const int64_t *targets, const int64_t *noise, int64_t batch, int n_ctx, int n_neg,
+                 double *stats, float *grad_in, float *grad_out, void *stream);
+
+/* Fused in-place SGD on an explicit batch: every row touched by pair (b, n) moves by -lr * dL_pair/drow where
+ * L_pair is the un-averaged per-pair loss (pass lr = lr_ref / (batch * n_ctx) for the reference's mean loss).
+ * noise NULL -> K negatives per pair drawn in-kernel (alias or uniform), keyed (seed; pair_id_base + b, n, k). */
+int se_sgns_step(float *w_in, float *w_out, int64_t vocab, int emb, const int64_t *inputs, const int64_t *targets,
+                 const int64_t *noise, int64_t batch, int n_ctx, int n_neg, const float *alias_prob,
+                 const int32_t *alias_idx, float lr, uint64_t seed, int64_t pair_id_base, int flags, double *stats,
+                 void *stream);
+
+/* ------------------------------------------------------------------------------------------------------------
+ * The fused hot path: walks -> skip-gram windows -> negatives -> in-place SGNS update, nothing materialised.
+ * Replaces W2VCollateFunctional sg branch (word2vec/dataloader/torch_dataset.py:293-322: centres i in
+ * [radius, L - radius), 2*radius contexts each), generate_noise_batch, SkipGram.forward x2, NegativeSamplingLoss,
+ * backward and the optimiser step (word2vec/trainer.py:131-152) for tokens[n_seq * seq_len] int32 (node ids or
+ * token ids); table row = token + row_offset.  Negative k of (centre c, context n) is keyed
+ * (seed; centre_id_base + c, n * n_neg + k) so results do not depend on the launch geometry.
+ * ---------------------------------------------------------------------------------------------------------- */
+int se_sgns_update_walks(float *w_in, float *w_out, int64_t vocab, int emb, const int32_t *tokens, int64_t n_seq,
+                         int seq_len, int radius, int n_neg, int row_offset, const float *alias_prob,
+                         const int32_t *alias_idx, float lr, uint64_t seed, int64_t centre_id_base, int flags,
+                         double *stats, void *stream);
+
+/* ------------------------------------------------------------------------------------------------------------
+ * Host-buffer pipeline step (what bench.py's e2e leg and RandomWalkDataset-driven training call): copies
+ * starts_host[n_walks] to the device, runs se_walk + se_sgns_update_walks on `stream`, copies the SE_STATS_LEN
+ * doubles back into stats_host and synchronises.  Device scratch: starts_dev[n_walks] int32,
+ * walks_dev[n_walks*walk_len] int32, stats_dev[SE_STATS_LEN] double.  walks_host may be NULL; when non-NULL the
+ * walks are copied back as well (the reference's RandomWalk.walk returns them to the caller).
+ * ---------------------------------------------------------------------------------------------------------- */
+int se_host_walk_sgns_step(const int64_t *rowptr, const int32_t *col, const float *wcdf, int64_t n_nodes,
+                           int symmetric, const int32_t *starts_host, int64_t n_walks, int walk_len, double p,
+                           double q, int node2vec, int rule, uint64_t seed, int64_t walk_id_base,
+                           float *w_in, float *w_out, int64_t vocab, int emb, int radius, int n_neg, int row_offset,
+                           const float *alias_prob, const int32_t *alias_idx, float lr, int flags,
+                           int32_t *starts_dev, int32_t *walks_dev, double *stats_dev, int32_t *walks_host,
+                           double *stats_host, void *stream);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* SE_B200_H */

@@ -1,0 +1,254 @@
+"""GPU parity tests for the SGNS kernels, through the C ABI.
+
+fp32 tolerance (north star): loss and gradients within 1e-5 relative of the reference (golden vectors from torch
+autograd on the reference's SkipGram + NegativeSamplingLoss).  Gradient error is measured as max-abs error over the
+max-abs gradient of the batch, as in oracle/make_golden.py.
+"""
+import os
+
+import numpy as np
+import pytest
+import torch
+
+import philox_ref
+from helpers import GOLDEN, SGNS_CASES, cuda_device
+from oracle import sgns_oracle
+from shallow_encoders import _native as nat
+
+pytestmark = pytest.mark.gpu
+REL_TOL = 1e-5
+
+
+def _t(a, dev):
+    return torch.from_numpy(np.ascontiguousarray(a)).to(dev)
+
+
+@pytest.mark.parametrize('tag', SGNS_CASES)
+def test_sgns_grad_matches_reference_autograd(tag):
+    dev = cuda_device()
+    z = np.load(os.path.join(GOLDEN, f'sgns_{tag}.npz'))
+    res = nat.sgns_grad(_t(z['w_in_f32'], dev), _t(z['w_out_f32'], dev), _t(z['inputs'], dev), _t(z['targets'], dev), _t(z['noise'], dev))
+    got = np.array([res['loss'], res['positive-loss'], res['negative-loss']])
+    np.testing.assert_allclose(got, z['loss_f32'], rtol=REL_TOL)
+    np.testing.assert_allclose(got, z['loss_f64'], rtol=REL_TOL)
+    np.testing.assert_allclose([res['recall'], res['precision']], z['metrics_f32'], atol=1e-6)
+    for ref in ('f32', 'f64'):
+        den = max(np.abs(z[f'grad_in_{ref}']).max(), np.abs(z[f'grad_out_{ref}']).max())
+        err_in = np.abs(res['grad_in'].cpu().numpy() - z[f'grad_in_{ref}']).max() / den
+        err_out = np.abs(res['grad_out'].cpu().numpy() - z[f'grad_out_{ref}']).max() / den
+        assert err_in <= REL_TOL and err_out <= REL_TOL, (ref, err_in, err_out)
+
+
+@pytest.mark.parametrize('emb', [1, 2, 3, 6, 8, 20, 48, 64, 100, 128, 130, 256, 300, 512, 1024])
+def test_sgns_grad_all_embedding_sizes(emb):
+    dev = cuda_device()
+    rng = np.random.default_rng(emb)
+    vocab, b, n, k = 77, 37, 3, 4
+    w_in = (rng.standard_normal((vocab, emb)) / np.sqrt(emb)).astype(np.float32)
+    w_out = (rng.standard_normal((vocab, emb)) * 2 / np.sqrt(emb)).astype(np.float32)
+    inputs, targets, noise = rng.integers(0, vocab, (b, 1)), rng.integers(0, vocab, (b, n)), rng.integers(0, vocab, (b, n, k))
+    o = sgns_oracle.training_step(w_in.astype(np.float64), w_out.astype(np.float64), inputs, targets, noise)
+    res = nat.sgns_grad(_t(w_in, dev), _t(w_out, dev), _t(inputs, dev), _t(targets, dev), _t(noise, dev))
+    assert abs(res['loss'] - o['loss']) <= REL_TOL * abs(o['loss'])
+    den = max(np.abs(o['grad_in']).max(), np.abs(o['grad_out']).max())
+    assert np.abs(res['grad_in'].cpu().numpy() - o['grad_in']).max() / den <= REL_TOL
+    assert np.abs(res['grad_out'].cpu().numpy() - o['grad_out']).max() / den <= REL_TOL
+    sc = nat.skipgram_scores(_t(w_in, dev), _t(w_out, dev), _t(inputs, dev), _t(targets, dev), proba=False).cpu().numpy()
+    np.testing.assert_allclose(sc, o['pos_logits'], rtol=1e-5, atol=1e-5)
+    pr = nat.skipgram_scores(_t(w_in, dev), _t(w_out, dev), _t(inputs, dev), _t(targets, dev), proba=True).cpu().numpy()
+    np.testing.assert_allclose(pr, sgns_oracle.sigmoid(o['pos_logits']), rtol=1e-5, atol=1e-6)
+
+
+def test_sgns_grad_edge_cases():
+    dev = cuda_device()
+    w = torch.randn(10, 8, device=dev)
+    e_in = torch.empty((0, 1), dtype=torch.int64, device=dev)
+    res = nat.sgns_grad(w, w.clone(), e_in, torch.empty((0, 4), dtype=torch.int64, device=dev),
+                        torch.empty((0, 4, 2), dtype=torch.int64, device=dev))
+    assert res['pairs'] == 0 and float(res['grad_in'].abs().sum()) == 0.0
+    # K = 0 (no negatives): only the positive term
+    rng = np.random.default_rng(0)
+    inputs, targets = rng.integers(0, 10, (5, 1)), rng.integers(0, 10, (5, 2))
+    wi, wo = rng.standard_normal((10, 8)).astype(np.float32), rng.standard_normal((10, 8)).astype(np.float32)
+    o = sgns_oracle.training_step(wi.astype(np.float64), wo.astype(np.float64), inputs, targets, np.zeros((5, 2, 0), dtype=np.int64))
+    res = nat.sgns_grad(_t(wi, dev), _t(wo, dev), _t(inputs, dev), _t(targets, dev), torch.empty((5, 2, 0), dtype=torch.int64, device=dev))
+    assert abs(res['loss'] - o['loss']) <= REL_TOL * abs(o['loss']) and res['negative-loss'] == 0.0
+
+
+def _distinct_batch(rng, vocab, b, n, k):
+    """A batch in which no table row is touched twice -> Hogwild == mini-batch SGD exactly."""
+    perm = rng.permutation(vocab)
+    need = b * (n + n * k)
+    assert vocab >= need and vocab >= b
+    inputs = rng.permutation(vocab)[:b].reshape(b, 1)
+    targets = perm[:b * n].reshape(b, n)
+    noise = perm[b * n:need].reshape(b, n, k)
+    return inputs, targets, noise
+
+
+@pytest.mark.parametrize('flags', [nat.SCATTER_RED, nat.SCATTER_STORE])
+@pytest.mark.parametrize('emb', [2, 48, 128])
+def test_sgns_step_equals_minibatch_sgd_without_collisions(flags, emb):
+    dev = cuda_device()
+    rng = np.random.default_rng(5)
+    vocab, b, n, k = 4000, 32, 4, 5
+    w_in = (rng.standard_normal((vocab, emb)) * 0.5).astype(np.float32)
+    w_out = (rng.standard_normal((vocab, emb)) * 0.5).astype(np.float32)
+    inputs, targets, noise = _distinct_batch(rng, vocab, b, n, k)
+    lr = 0.05
+    want_in, want_out, o = sgns_oracle.sgd_step(w_in.astype(np.float64), w_out.astype(np.float64), inputs, targets, noise, lr * b * n)
+    t_in, t_out = _t(w_in, dev), _t(w_out, dev)
+    stats = nat.sgns_step(t_in, t_out, _t(inputs, dev), _t(targets, dev), _t(noise, dev), k, lr, flags=flags)
+    assert abs(stats['loss'] - o['loss']) <= 1e-4 * abs(o['loss'])       # fast-math sigmoid/log in the update kernels
+    np.testing.assert_allclose(t_in.cpu().numpy(), want_in, rtol=1e-4, atol=1e-5)
+    np.testing.assert_allclose(t_out.cpu().numpy(), want_out, rtol=1e-4, atol=1e-5)
+    assert stats['pairs'] == b * n and stats['negatives'] == b * n * k
+
+
+def test_sgns_step_red_scatter_accumulates_duplicate_rows():
+    """Same centre twice and the same negative for every pair: red.add applies every contribution."""
+    dev = cuda_device()
+    emb = 128
+    w_in = torch.full((8, emb), 0.01, device=dev)
+    w_out = torch.full((8, emb), 0.02, device=dev)
+    inputs = torch.tensor([[1], [2], [3], [4]], device=dev)
+    targets = torch.tensor([[5], [5], [5], [5]], device=dev)     # one context row shared by 4 centres
+    noise = torch.full((4, 1, 1), 6, dtype=torch.int64, device=dev)
+    wi0, wo0 = w_in.cpu().numpy().astype(np.float64), w_out.cpu().numpy().astype(np.float64)
+    lr = 0.1
+    nat.sgns_step(w_in, w_out, inputs, targets, noise, 1, lr, flags=nat.SCATTER_RED)
+    want_in, want_out, _ = sgns_oracle.sgd_step(wi0, wo0, inputs.cpu().numpy(), targets.cpu().numpy(), noise.cpu().numpy(), lr * 4)
+    np.testing.assert_allclose(w_out.cpu().numpy(), want_out, rtol=1e-4, atol=1e-6)
+    np.testing.assert_allclose(w_in.cpu().numpy(), want_in, rtol=1e-4, atol=1e-6)
+
+
+def test_in_kernel_negatives_match_philox_restatement_and_walk_windows():
+    """Fused walk kernel == oracle: windows per torch_dataset.py:300-309, negatives predicted by the numpy Philox,
+    rows made collision-free so the in-place update equals mini-batch SGD."""
+    dev = cuda_device()
+    rng = np.random.default_rng(8)
+    emb, radius, k, length, n_seq, seed, offset = 128, 2, 3, 7, 6, 4242, 1
+    vocab = 200000
+    tokens = rng.permutation(vocab - offset)[:n_seq * length].reshape(n_seq, length).astype(np.int32)   # all distinct
+    n_cen = length - 2 * radius
+    neg = philox_ref.negatives(seed, np.arange(n_seq * n_cen), 2 * radius, k, vocab)
+    inputs, targets = sgns_oracle.windows_from_walks(tokens.astype(np.int64), radius, offset)
+    assert inputs.shape == (n_seq * n_cen, 1) and targets.shape == (n_seq * n_cen, 2 * radius)
+    # negatives collide with nothing else (vocab is large); otherwise pick another seed
+    touched = np.concatenate([targets.ravel(), neg.ravel()])
+    assert len(np.unique(neg.ravel())) == neg.size and not np.isin(neg.ravel(), targets.ravel()).any()
+    # small weights: first-order updates ~1e-3, second-order (stale-row) effects ~5e-6
+    w_in = (rng.standard_normal((vocab, emb)) * 0.05).astype(np.float32)
+    w_out = (rng.standard_normal((vocab, emb)) * 0.05).astype(np.float32)
+    rows = np.unique(np.concatenate([touched, inputs.ravel()]))
+    lr = 0.05
+    # context rows ARE shared between neighbouring centres of a walk, so compare against a sequential oracle:
+    # centres in order, each a mini-batch of its own (that is exactly what one group does)
+    wi, wo = w_in[rows].astype(np.float64), w_out[rows].astype(np.float64)
+    remap = {int(r): i for i, r in enumerate(rows)}
+    rm = np.vectorize(remap.get)
+    loss_sum = 0.0
+    for c in range(len(inputs)):
+        wi, wo, o = sgns_oracle.sgd_step(wi, wo, rm(inputs[c:c + 1]), rm(targets[c:c + 1]), rm(neg[c:c + 1]), lr * 2 * radius)
+        loss_sum += o['loss']
+    t_in, t_out = _t(w_in, dev), _t(w_out, dev)
+    # one group must process the centres of a walk in order: a single sequence per launch keeps it sequential
+    stats_total = 0.0
+    for s in range(n_seq):
+        st = nat.sgns_update_walks(t_in, t_out, _t(tokens[s:s + 1], dev), radius, k, offset, lr, seed, centre_id_base=s * n_cen)
+        stats_total += st['loss'] * st['pairs']
+    got_in, got_out = t_in.cpu().numpy()[rows], t_out.cpu().numpy()[rows]
+    # a launch spreads the n_cen centres of a sequence over groups, so within a walk the order is not sequential;
+    # the shared context rows then see concurrent red.adds computed from slightly stale rows: tolerance, not equality
+    np.testing.assert_allclose(got_in, wi, rtol=0, atol=1e-4)
+    np.testing.assert_allclose(got_out, wo, rtol=0, atol=1e-4)
+    assert np.abs(got_out - w_out[rows]).max() > 5e-4      # the updates themselves are an order of magnitude larger
+    untouched = np.setdiff1d(np.arange(0, 5000), rows)
+    assert np.array_equal(t_in.cpu().numpy()[untouched], w_in[untouched])
+    assert np.array_equal(t_out.cpu().numpy()[untouched], w_out[untouched])
+    assert abs(stats_total / (len(inputs) * 2 * radius) - loss_sum / len(inputs)) < 1e-3
+
+
+def test_fused_walk_update_exact_when_windows_do_not_overlap():
+    """L = 2r+1 -> one centre per sequence, all rows distinct: fused kernel == mini-batch SGD to fp32 accuracy."""
+    dev = cuda_device()
+    rng = np.random.default_rng(9)
+    emb, radius, k, n_seq, seed, offset = 128, 5, 5, 64, 77, 1
+    length = 2 * radius + 1
+    vocab = 500000
+    tokens = rng.permutation(vocab - offset)[:n_seq * length].reshape(n_seq, length).astype(np.int32)
+    neg = philox_ref.negatives(seed, np.arange(n_seq) + 1000, 2 * radius, k, vocab)
+    inputs, targets = sgns_oracle.windows_from_walks(tokens.astype(np.int64), radius, offset)
+    allrows = np.concatenate([targets.ravel(), neg.ravel()])
+    assert len(np.unique(allrows)) == allrows.size
+    w_in = (rng.standard_normal((vocab, emb)) * 0.3).astype(np.float32)
+    w_out = (rng.standard_normal((vocab, emb)) * 0.3).astype(np.float32)
+    lr = 0.025
+    rows = np.unique(np.concatenate([allrows, inputs.ravel()]))
+    remap = {int(r): i for i, r in enumerate(rows)}
+    rm = np.vectorize(remap.get)
+    want_in, want_out, o = sgns_oracle.sgd_step(w_in[rows].astype(np.float64), w_out[rows].astype(np.float64), rm(inputs), rm(targets), rm(neg), lr * n_seq * 2 * radius)
+    for flags in (nat.SCATTER_RED, nat.SCATTER_STORE):
+        t_in, t_out = _t(w_in, dev), _t(w_out, dev)
+        st = nat.sgns_update_walks(t_in, t_out, _t(tokens, dev), radius, k, offset, lr, seed, centre_id_base=1000, flags=flags)
+        np.testing.assert_allclose(t_in.cpu().numpy()[rows], want_in, rtol=1e-4, atol=1e-5)
+        np.testing.assert_allclose(t_out.cpu().numpy()[rows], want_out, rtol=1e-4, atol=1e-5)
+        assert abs(st['loss'] - o['loss']) <= 1e-4 * abs(o['loss'])
+        assert abs(st['recall'] - o['recall']) < 1e-9 and abs(st['precision'] - o['precision']) < 1e-9
+        assert st['pairs'] == n_seq * 2 * radius
+
+
+def test_fused_walk_update_rejects_short_sequences():
+    dev = cuda_device()
+    w = torch.zeros(10, 4, device=dev)
+    with pytest.raises(AssertionError, match='Text is too short'):
+        nat.sgns_update_walks(w, w.clone(), torch.zeros((3, 4), dtype=torch.int32, device=dev), 2, 1, 0, 0.1, 0)
+
+
+def test_negative_sampler_distributions():
+    from scipy.stats import chisquare
+    dev = cuda_device()
+    vocab, n = 1000, 2_000_000
+    # uniform over [0, V): the reference's distribution (sampling.py:21)
+    ids = nat.sample_negatives(n, vocab, seed=3, device=dev).cpu().numpy()
+    assert ids.min() == 0 and ids.max() == vocab - 1
+    assert np.array_equal(ids, philox_ref.draws(3, n, vocab))
+    assert chisquare(np.bincount(ids, minlength=vocab)).pvalue > 1e-6
+    # unigram^0.75 through the alias table
+    counts = (1e6 / np.arange(1, vocab + 1)).astype(np.float64)
+    alias = nat.alias_build(counts, 0.75, dev)
+    ids = nat.sample_negatives(n, vocab, seed=4, device=dev, alias=alias).cpu().numpy()
+    assert np.array_equal(ids, philox_ref.draws(4, n, vocab, alias['prob'].cpu().numpy(), alias['alias'].cpu().numpy()))
+    want = counts ** 0.75
+    want /= want.sum()
+    assert chisquare(np.bincount(ids, minlength=vocab), want * n).pvalue > 1e-6
+    # power 0 alias == uniform
+    alias0 = nat.alias_build(counts, 0.0, dev)
+    ids0 = nat.sample_negatives(n, vocab, seed=5, device=dev, alias=alias0).cpu().numpy()
+    assert chisquare(np.bincount(ids0, minlength=vocab)).pvalue > 1e-6
+
+
+def test_training_reduces_loss_and_separates_clusters():
+    """End-to-end sanity of the fused path on the reference's toy graph (graph_triplets: 3 paths of 3 nodes)."""
+    dev = cuda_device()
+    from shallow_encoders.graph.csr import CSRGraph
+    rowptr = np.array([0, 1, 3, 4, 5, 7, 8, 9, 11, 12], dtype=np.int64)
+    col = np.array([1, 0, 2, 1, 4, 3, 5, 4, 7, 6, 8, 7], dtype=np.int32)
+    csr = CSRGraph.from_arrays(rowptr, col, device=dev)
+    torch.manual_seed(0)
+    emb = 8
+    w_in = (torch.rand(10, emb, device=dev) - 0.5) * 0.5
+    w_out = (torch.rand(10, emb, device=dev) - 0.5) * 0.5
+    starts = torch.arange(9, dtype=torch.int32, device=dev).repeat(64)
+    first = last = None
+    for epoch in range(30):
+        walks = nat.walk(csr, starts, 5, 1.0, 1.0, False, 0, seed=epoch)
+        st = nat.sgns_update_walks(w_in, w_out, walks, 2, 1, 1, 0.05, seed=1000 + epoch, centre_id_base=epoch * 10 ** 6)
+        first = st['loss'] if first is None else first
+        last = st['loss']
+    assert last < first - 0.2, (first, last)
+    x = torch.nn.functional.normalize(w_in[1:], dim=1).cpu().numpy()
+    sim = x @ x.T
+    same = np.mean([sim[i, j] for i in range(9) for j in range(9) if i != j and i // 3 == j // 3])
+    diff = np.mean([sim[i, j] for i in range(9) for j in range(9) if i // 3 != j // 3])
+    assert same > diff + 0.3, (same, diff)
