@@ -342,9 +342,10 @@ extern "C" int se_skipgram_scores(const float *w_in, const float *w_out, int64_t
                                   const int64_t *outputs, int64_t batch, int m, int proba, float *out, void *stream) {
     int rc = se::common_checks("se_skipgram_scores", w_in, w_out, vocab, emb, 0);
     if (rc != SE_OK) return rc;
-    SE_REQUIRE(inputs && outputs && out && batch >= 0 && m >= 1, "se_skipgram_scores: bad arguments");
+    SE_REQUIRE(batch >= 0 && m >= 1, "se_skipgram_scores: bad shape");
     const int64_t total = batch * m;
     if (total == 0) return SE_OK;
+    SE_REQUIRE(inputs && outputs && out, "se_skipgram_scores: null pointer");
     const int sms = se::sm_count();
     if (sms <= 0) return SE_ERR_CUDA;
     if (emb >= 32) {
@@ -362,8 +363,9 @@ extern "C" int se_sgns_grad(const float *w_in, const float *w_out, int64_t vocab
                             double *stats, float *grad_in, float *grad_out, void *stream) {
     int rc = se::common_checks("se_sgns_grad", w_in, w_out, vocab, emb, n_neg);
     if (rc != SE_OK) return rc;
-    SE_REQUIRE(inputs && targets && (noise || n_neg == 0), "se_sgns_grad: null index tensor");
     SE_REQUIRE(batch >= 0 && n_ctx >= 1, "se_sgns_grad: bad batch shape");
+    if (batch == 0) return SE_OK;
+    SE_REQUIRE(inputs && targets && (noise || n_neg == 0), "se_sgns_grad: null index tensor");
     SE_REQUIRE((grad_in == nullptr) == (grad_out == nullptr), "se_sgns_grad: pass both gradient buffers or neither");
     se::SgnsArgs a{};
     a.w_in = const_cast<float *>(w_in); a.w_out = const_cast<float *>(w_out);
@@ -380,8 +382,9 @@ extern "C" int se_sgns_step(float *w_in, float *w_out, int64_t vocab, int emb, c
                             int64_t pair_id_base, int flags, double *stats, void *stream) {
     int rc = se::common_checks("se_sgns_step", w_in, w_out, vocab, emb, n_neg);
     if (rc != SE_OK) return rc;
-    SE_REQUIRE(inputs && targets, "se_sgns_step: null index tensor");
     SE_REQUIRE(batch >= 0 && n_ctx >= 1, "se_sgns_step: bad batch shape");
+    if (batch == 0) return SE_OK;
+    SE_REQUIRE(inputs && targets, "se_sgns_step: null index tensor");
     SE_REQUIRE((alias_prob == nullptr) == (alias_idx == nullptr), "se_sgns_step: pass both alias arrays or neither");
     SE_REQUIRE(flags == SE_SGNS_SCATTER_RED || flags == SE_SGNS_SCATTER_STORE, "se_sgns_step: unknown flags %d", flags);
     se::SgnsArgs a{};
@@ -398,7 +401,7 @@ extern "C" int se_sgns_update_walks(float *w_in, float *w_out, int64_t vocab, in
                                     int64_t centre_id_base, int flags, double *stats, void *stream) {
     int rc = se::common_checks("se_sgns_update_walks", w_in, w_out, vocab, emb, n_neg);
     if (rc != SE_OK) return rc;
-    SE_REQUIRE(tokens && n_seq >= 0, "se_sgns_update_walks: null tokens");
+    SE_REQUIRE(n_seq >= 0 && (tokens || n_seq == 0), "se_sgns_update_walks: null tokens");
     SE_REQUIRE(radius >= 1, "se_sgns_update_walks: context radius must be >= 1");
     // W2VCollateFunctional asserts text_length >= 2r+1 (torch_dataset.py:298)
     SE_REQUIRE(seq_len >= 2 * radius + 1, "Text is too short! [text_length=%d] < [min_text_length=%d]", seq_len, 2 * radius + 1);

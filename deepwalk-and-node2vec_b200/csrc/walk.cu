@@ -249,12 +249,12 @@ extern "C" int se_walk_exact(const int64_t *rowptr, const int32_t *col, const in
                              int64_t n_walks, int walk_len, double p, double q, int node2vec, int rule,
                              const double *uniforms, void *scratch, int64_t scratch_bytes, int32_t *out,
                              void *stream) {
-    SE_REQUIRE(rowptr && col && col_sorted && starts && out, "se_walk_exact: null graph/starts/out pointer");
     SE_REQUIRE(n_nodes > 0 && n_walks >= 0 && walk_len >= 1, "se_walk_exact: bad sizes (walk length must be >= 1)");
-    SE_REQUIRE(walk_len == 1 || uniforms, "se_walk_exact: uniforms required");
     SE_REQUIRE(p > 0 && q > 0, "se_walk_exact: p and q must be positive");
     SE_REQUIRE(rule == SE_RULE_REFERENCE || rule == SE_RULE_PAPER, "se_walk_exact: unknown rule %d", rule);
     if (n_walks == 0) return SE_OK;
+    SE_REQUIRE(rowptr && col && col_sorted && starts && out, "se_walk_exact: null graph/starts/out pointer");
+    SE_REQUIRE(walk_len == 1 || uniforms, "se_walk_exact: uniforms required");
     if (max_degree < 1) max_degree = 1;
     const int64_t fstride = (max_degree + 7) & ~7ll;
     const int64_t per_warp = max_degree * 8 + fstride;
@@ -276,11 +276,11 @@ extern "C" int se_walk(const int64_t *rowptr, const int32_t *col, const float *w
                        const int32_t *starts, int64_t n_walks, int walk_len, double p, double q, int node2vec,
                        int rule, uint64_t seed, int64_t walk_id_base, int64_t walk_id_stride, int32_t *out,
                        int32_t *err_count, void *stream) {
-    SE_REQUIRE(rowptr && col && starts && out, "se_walk: null graph/starts/out pointer");
     SE_REQUIRE(n_nodes > 0 && n_walks >= 0 && walk_len >= 1, "se_walk: bad sizes (walk length must be >= 1)");
     SE_REQUIRE(p > 0 && q > 0, "se_walk: p and q must be positive");
     SE_REQUIRE(rule == SE_RULE_REFERENCE || rule == SE_RULE_PAPER, "se_walk: unknown rule %d", rule);
     if (n_walks == 0) return SE_OK;
+    SE_REQUIRE(rowptr && col && starts && out, "se_walk: null graph/starts/out pointer");
     const int sms = se::sm_count();
     if (sms <= 0) return SE_ERR_CUDA;
     // persistent grid: 8 resident blocks of 8 warps per SM (64 warps/SM), capped by the work available

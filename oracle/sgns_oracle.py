@@ -80,7 +80,7 @@ def training_step(w_in: np.ndarray, w_out: np.ndarray, inputs: np.ndarray, targe
     out = loss_dict(sp, sn)
     sig_p, sig_n, sig_mn = sigmoid(sp), sigmoid(sn), sigmoid(-sn)
     out['recall'] = (sig_p >= 0.5).astype(np.float64).mean()
-    out['precision'] = 1.0 - (sig_n >= 0.5).astype(np.float64).mean()
+    out['precision'] = 1.0 - ((sig_n >= 0.5).astype(np.float64).mean() if sig_n.size else 0.0)
     scale = dt.type(1.0) / dt.type(b * n)
     # clamp(x, min) passes gradient only where x > min
     gp = -(1 - sig_p) * (sig_p > dt.type(CLAMP_MIN)) * scale               # dL/ds+
@@ -90,8 +90,8 @@ def training_step(w_in: np.ndarray, w_out: np.ndarray, inputs: np.ndarray, targe
     g_out = np.zeros_like(w_out)
     gc = np.einsum('bn,bne->be', gp, w_out[targets]) + np.einsum('bnk,bnke->be', gn, w_out[noise])
     np.add.at(g_in, inputs[:, 0], gc)
-    np.add.at(g_out, targets.reshape(-1), (gp[:, :, None] * c[:, None, :]).reshape(b * n, -1))
-    np.add.at(g_out, noise.reshape(-1), (gn[:, :, :, None] * c[:, None, None, :]).reshape(b * n * k, -1))
+    np.add.at(g_out, targets.reshape(-1), (gp[:, :, None] * c[:, None, :]).reshape(b * n, c.shape[1]))
+    np.add.at(g_out, noise.reshape(-1), (gn[:, :, :, None] * c[:, None, None, :]).reshape(b * n * k, c.shape[1]))
     out['grad_in'], out['grad_out'] = g_in, g_out
     out['pos_logits'], out['neg_logits'] = sp, sn
     return out

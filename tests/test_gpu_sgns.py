@@ -141,7 +141,7 @@ def test_in_kernel_negatives_match_philox_restatement_and_walk_windows():
     w_in = (rng.standard_normal((vocab, emb)) * 0.05).astype(np.float32)
     w_out = (rng.standard_normal((vocab, emb)) * 0.05).astype(np.float32)
     rows = np.unique(np.concatenate([touched, inputs.ravel()]))
-    lr = 0.05
+    lr = 0.005     # updates ~1e-4 (first order in lr); staleness between concurrent centres of a walk ~3e-7 (second order)
     # context rows ARE shared between neighbouring centres of a walk, so compare against a sequential oracle:
     # centres in order, each a mini-batch of its own (that is exactly what one group does)
     wi, wo = w_in[rows].astype(np.float64), w_out[rows].astype(np.float64)
@@ -160,27 +160,32 @@ def test_in_kernel_negatives_match_philox_restatement_and_walk_windows():
     got_in, got_out = t_in.cpu().numpy()[rows], t_out.cpu().numpy()[rows]
     # a launch spreads the n_cen centres of a sequence over groups, so within a walk the order is not sequential;
     # the shared context rows then see concurrent red.adds computed from slightly stale rows: tolerance, not equality
-    np.testing.assert_allclose(got_in, wi, rtol=0, atol=1e-4)
-    np.testing.assert_allclose(got_out, wo, rtol=0, atol=1e-4)
-    assert np.abs(got_out - w_out[rows]).max() > 5e-4      # the updates themselves are an order of magnitude larger
+    np.testing.assert_allclose(got_in, wi, rtol=0, atol=1e-5)
+    np.testing.assert_allclose(got_out, wo, rtol=0, atol=1e-5)
+    assert np.abs(got_out - w_out[rows]).max() > 1e-4      # the updates themselves are an order of magnitude larger
     untouched = np.setdiff1d(np.arange(0, 5000), rows)
     assert np.array_equal(t_in.cpu().numpy()[untouched], w_in[untouched])
     assert np.array_equal(t_out.cpu().numpy()[untouched], w_out[untouched])
     assert abs(stats_total / (len(inputs) * 2 * radius) - loss_sum / len(inputs)) < 1e-3
 
 
-def test_fused_walk_update_exact_when_windows_do_not_overlap():
+@pytest.mark.parametrize('emb,radius,k,n_seq', [(128, 5, 5, 4), (128, 2, 3, 8), (48, 2, 5, 6), (2, 1, 1, 16), (256, 3, 2, 5)])
+def test_fused_walk_update_exact_when_windows_do_not_overlap(emb, radius, k, n_seq):
     """L = 2r+1 -> one centre per sequence, all rows distinct: fused kernel == mini-batch SGD to fp32 accuracy."""
     dev = cuda_device()
     rng = np.random.default_rng(9)
-    emb, radius, k, n_seq, seed, offset = 128, 5, 5, 64, 77, 1
+    offset = 1
     length = 2 * radius + 1
-    vocab = 500000
+    vocab = 400000
     tokens = rng.permutation(vocab - offset)[:n_seq * length].reshape(n_seq, length).astype(np.int32)
-    neg = philox_ref.negatives(seed, np.arange(n_seq) + 1000, 2 * radius, k, vocab)
     inputs, targets = sgns_oracle.windows_from_walks(tokens.astype(np.int64), radius, offset)
-    allrows = np.concatenate([targets.ravel(), neg.ravel()])
-    assert len(np.unique(allrows)) == allrows.size
+    for seed in range(77, 400):      # deterministic search for a draw without row collisions
+        neg = philox_ref.negatives(seed, np.arange(n_seq) + 1000, 2 * radius, k, vocab)
+        allrows = np.concatenate([targets.ravel(), neg.ravel()])
+        if len(np.unique(allrows)) == allrows.size:
+            break
+    else:
+        raise AssertionError('no collision-free seed')
     w_in = (rng.standard_normal((vocab, emb)) * 0.3).astype(np.float32)
     w_out = (rng.standard_normal((vocab, emb)) * 0.3).astype(np.float32)
     lr = 0.025
@@ -239,11 +244,13 @@ def test_training_reduces_loss_and_separates_clusters():
     emb = 8
     w_in = (torch.rand(10, emb, device=dev) - 0.5) * 0.5
     w_out = (torch.rand(10, emb, device=dev) - 0.5) * 0.5
-    starts = torch.arange(9, dtype=torch.int32, device=dev).repeat(64)
+    # every launch is one Hogwild mini-batch: 72 walks x 4 pairs all hit the same 10 rows concurrently, so the
+    # per-pair step is the reference-style batch step divided by the pairs per launch (lr mapping)
+    starts = torch.arange(9, dtype=torch.int32, device=dev).repeat(8)
     first = last = None
-    for epoch in range(30):
+    for epoch in range(300):
         walks = nat.walk(csr, starts, 5, 1.0, 1.0, False, 0, seed=epoch)
-        st = nat.sgns_update_walks(w_in, w_out, walks, 2, 1, 1, 0.05, seed=1000 + epoch, centre_id_base=epoch * 10 ** 6)
+        st = nat.sgns_update_walks(w_in, w_out, walks, 2, 1, 1, 0.02, seed=1000 + epoch, centre_id_base=epoch * 10 ** 6)
         first = st['loss'] if first is None else first
         last = st['loss']
     assert last < first - 0.2, (first, last)

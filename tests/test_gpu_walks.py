@@ -171,7 +171,7 @@ def test_philox_walks_chi_square_vs_exact_probabilities(case, p, q):
             ring = np.where((t_ == 1) | (t_ == 400), 1, 2)
             wsum = 1 / p + ring / q + (399 - ring)
             exp += [(1 / p / wsum).sum(), (ring / q / wsum).sum(), ((399 - ring) / wsum).sum()]
-        assert obs.sum() > 50000
+        assert obs.sum() > 20000
         assert float(((obs - exp) ** 2 / exp).sum()) < chi2.ppf(1 - 1e-6, 2), (obs, exp)
     # and the PAPER rule must be rejected by the same statistic when p != q-symmetric
     if case == 'triangle_rich' and q != 1.0:
