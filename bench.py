@@ -1,0 +1,402 @@
+#!/usr/bin/env python
+"""
+bench.py -- the hot path of BASELINE.json on B200: node2vec walks over a CSR graph -> skip-gram windows ->
+negative sampling -> in-place SGNS update of the input and context tables.
+
+    python bench.py [--gpus N] [--steps K] [--warmup W] [--impl reference]
+    python -m torch.distributed.run --nnodes=1 --nproc-per-node N ... bench.py --gpus N ...
+
+Workload (config.workload "S3"): synthetic power-law graph, 10 M nodes / 250 M undirected edges, node2vec p=0.5 q=2
+(reference code rule), walk_len 80, dim 128, r=5, K=5 uniform negatives (the reference's distribution).  One STEP =
+one batch of `--walks-per-step` walks (start nodes follow the reference's schedule: shuffled node list, 10
+consecutive walks per node) pushed through the walk kernel and the fused window/negatives/SGNS kernel.
+value = positive (centre, context) pairs per second over the whole step (walk time included), all GPUs.
+
+N > 1: one process per GPU, weak scaling.  Walks shard by walk id against a replicated CSR with no communication;
+each rank applies its SGNS updates to its own replica of the tables and the replicas are averaged with one NCCL
+all-reduce per step inside the timed region.
+
+--impl reference: the reference's CPU path (oracle/cpu_port.py: python walks on all host cores + torch CPU
+SkipGram/loss/backward/Adam) on a bounded sample of the same workload; rank 0 only.
+"""
+import argparse
+import json
+import os
+import sys
+import threading
+import time
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, os.path.join(ROOT, 'deepwalk-and-node2vec_b200'))
+sys.path.insert(0, ROOT)
+
+METRIC = 'sgns_pairs_per_s'
+UNIT = 'pairs/s'
+
+
+def parse_args():
+    ap = argparse.ArgumentParser()
+    ap.add_argument('--gpus', type=int, default=1)
+    ap.add_argument('--steps', type=int, default=10)
+    ap.add_argument('--warmup', type=int, default=3)
+    ap.add_argument('--impl', default='b200', choices=['b200', 'reference'])
+    ap.add_argument('--nodes', type=int, default=10_000_000)
+    ap.add_argument('--edges', type=int, default=250_000_000)
+    ap.add_argument('--walks-per-step', type=int, default=262_144)
+    ap.add_argument('--walks-per-node', type=int, default=10)
+    ap.add_argument('--walk-len', type=int, default=80)
+    ap.add_argument('--emb', type=int, default=128)
+    ap.add_argument('--radius', type=int, default=5)
+    ap.add_argument('--neg', type=int, default=5)
+    ap.add_argument('--p', type=float, default=0.5)
+    ap.add_argument('--q', type=float, default=2.0)
+    ap.add_argument('--lr', type=float, default=0.025)
+    ap.add_argument('--scatter', default='red', choices=['red', 'store'])
+    ap.add_argument('--seed', type=int, default=0)
+    ap.add_argument('--no-cpu-baseline', action='store_true')
+    ap.add_argument('--cpu-nodes', type=int, default=100_000, help='node count of the CPU sample graph (same mean degree)')
+    ap.add_argument('--cpu-walks-per-step', type=int, default=64, help='reference batch_size (walks per step)')
+    ap.add_argument('--cpu-seconds', type=float, default=15.0, help='target CPU time of the cpu_baseline sample')
+    return ap.parse_args()
+
+
+def workload_config(a, n_gpus):
+    return {
+        'workload': 'S3 synthetic power-law graph: node2vec walks -> windows -> negatives -> SGNS update',
+        'nodes': a.nodes, 'edges': a.edges, 'method': 'node2vec', 'p': a.p, 'q': a.q, 'rule': 'reference-code',
+        'walk_len': a.walk_len, 'walks_per_node': a.walks_per_node, 'walks_per_step_per_gpu': a.walks_per_step,
+        'emb': a.emb, 'context_radius': a.radius, 'negatives': a.neg, 'negative_sampling': 'uniform (reference)',
+        'optimizer': 'in-place SGD (Hogwild, red.global.add.v4.f32)' if a.scatter == 'red' else 'in-place SGD (Hogwild, plain stores)',
+        'parallelism': 'single GPU' if n_gpus == 1 else f'dp{n_gpus}: walks sharded by id, table replicas averaged by NCCL all-reduce every step',
+        'l2': 'inputs exceed L2 (tables 2 x %.2f GB, CSR ~%.1f GB); no flush' % ((a.nodes + 1) * a.emb * 4 / 1e9, (2 * a.edges * 4 + a.nodes * 8) / 1e9),
+    }
+
+
+def bytes_per_pair(emb, neg, radius):
+    """Algorithmic HBM bytes per positive pair: fp32 rows read + written once per use, the centre row
+    amortised over its 2r contexts: 2 * 4E * (1 + K + 1/N)."""
+    return 2.0 * 4.0 * emb * (1.0 + neg + 1.0 / (2 * radius))
+
+
+# --------------------------------------------------------------------------------------------------------------
+class ClockSampler(threading.Thread):
+    """Samples SM clock and clock-event reasons through NVML while the timed region runs."""
+    REASONS = {0x1: 'gpu_idle', 0x2: 'applications_clocks_setting', 0x4: 'sw_power_cap', 0x8: 'hw_slowdown',
+               0x10: 'sync_boost', 0x20: 'sw_thermal_slowdown', 0x40: 'hw_thermal_slowdown', 0x80: 'hw_power_brake_slowdown',
+               0x100: 'display_clock_setting'}
+
+    def __init__(self, index, period=0.1):
+        super().__init__(daemon=True)
+        self.index, self.period = index, period
+        self.samples, self.reasons, self.max_mhz, self.power = [], set(), None, []
+        self._stop_evt = threading.Event()
+        self.ok = False
+        try:
+            import pynvml
+            pynvml.nvmlInit()
+            self.nv = pynvml
+            self.h = pynvml.nvmlDeviceGetHandleByIndex(index)
+            self.max_mhz = pynvml.nvmlDeviceGetMaxClockInfo(self.h, pynvml.NVML_CLOCK_SM)
+            self.ok = True
+        except Exception as e:   # noqa: BLE001
+            self.err = repr(e)
+
+    def run(self):
+        if not self.ok:
+            return
+        while not self._stop_evt.is_set():
+            try:
+                self.samples.append(self.nv.nvmlDeviceGetClockInfo(self.h, self.nv.NVML_CLOCK_SM))
+                try:
+                    mask = self.nv.nvmlDeviceGetCurrentClocksEventReasons(self.h)
+                except Exception:   # noqa: BLE001
+                    mask = self.nv.nvmlDeviceGetCurrentClocksThrottleReasons(self.h)
+                for bit, name in self.REASONS.items():
+                    if mask & bit:
+                        self.reasons.add(name)
+                self.power.append(self.nv.nvmlDeviceGetPowerUsage(self.h) / 1000.0)
+            except Exception:   # noqa: BLE001
+                pass
+            self._stop_evt.wait(self.period)
+
+    def stop(self):
+        self._stop_evt.set()
+        if self.is_alive():
+            self.join(timeout=2)
+        if not self.samples:
+            return {'sm_mhz': None, 'sm_max_mhz': self.max_mhz, 'reasons': sorted(self.reasons), 'samples': 0}
+        s = sorted(self.samples)
+        return {'sm_mhz': s[len(s) // 2], 'sm_max_mhz': self.max_mhz, 'reasons': sorted(self.reasons - {'gpu_idle'}),
+                'samples': len(s), 'power_w_max': max(self.power) if self.power else None}
+
+
+def nvml_index(local_rank):
+    vis = os.environ.get('CUDA_VISIBLE_DEVICES')
+    if vis:
+        parts = [p.strip() for p in vis.split(',') if p.strip()]
+        if local_rank < len(parts) and parts[local_rank].isdigit():
+            return int(parts[local_rank])
+    return local_rank
+
+
+def measured_peak():
+    path = os.path.join(ROOT, 'MEASURED_PEAKS.json')
+    if os.path.exists(path):
+        try:
+            return float(json.load(open(path))['hbm_gbs']), 'measured (MEASURED_PEAKS.json hbm_gbs)'
+        except Exception:   # noqa: BLE001
+            pass
+    return 6650.0, 'fallback (B200_PROFILING.md)'
+
+
+def recorded_traffic():
+    """DRAM bytes per launch of the dominant kernel from the committed `ncu --set full` capture, or None."""
+    path = os.path.join(ROOT, 'profiles', 'sgns_traffic.json')
+    if os.path.exists(path):
+        try:
+            return json.load(open(path))
+        except Exception:   # noqa: BLE001
+            return None
+    return None
+
+
+# --------------------------------------------------------------------------------------------------------------
+def run_reference(a, rank, world):
+    """CPU arm: the reference's path (oracle port) on all host cores, bounded sample of the same workload."""
+    if rank != 0:
+        return
+    from oracle import cpu_port
+    cores = os.cpu_count() or 1
+    nodes = min(a.cpu_nodes, a.nodes)
+    edges = int(round(a.edges * (nodes / a.nodes)))
+    g = cpu_port.powerlaw_graph_host(nodes, edges, a.seed)
+    r = cpu_port.run_reference_pipeline(g, a.cpu_walks_per_step, a.steps, a.warmup, a.walk_len, a.p, a.q, True, a.radius,
+                                        a.emb, a.neg, cores, optimizer='adam', seed=a.seed)
+    sample = (f'{a.steps} steps x {a.cpu_walks_per_step} walks (reference batch_size) on a {nodes}-node / {edges}-edge power-law '
+              f'sample of S3 (same generator, same mean degree); python walks on {cores} processes + torch CPU '
+              f'SkipGram/loss/backward/dense Adam with {cores} threads; walk {r["walk_steps_per_s"]:.3g} steps/s, '
+              f'sgns {r["sgns_pairs_per_s"]:.3g} pairs/s')
+    cfg = workload_config(a, 1)
+    cfg['parallelism'] = f'{cores} host cores'
+    cfg['optimizer'] = 'torch.optim.Adam on dense tables (as every shipped YAML, e.g. configs/sge_sg_cora.yaml:32-34)'
+    line = {
+        'impl': 'reference', 'metric': METRIC, 'value': r['pairs_per_s'], 'unit': UNIT, 'n_gpus': a.gpus, 'steps': a.steps,
+        'warmup': a.warmup, 'ms_per_step': r['ms_per_step'], 'higher_is_better': True, 'scaling': 'weak', 'vs_baseline': None,
+        'dtype': 'f32', 'data': 'synthetic', 'config': cfg,
+        'cpu_baseline': {'value': r['pairs_per_s'], 'unit': UNIT, 'cores': cores, 'kind': 'port', 'sample': sample},
+        'e2e': {'value': r['pairs_per_s'], 'unit': UNIT, 'h2d_bytes_per_step': 0, 'd2h_bytes_per_step': 0},
+        'walk_steps_per_s': r['walk_steps_per_s'], 'gpu_launches': 0,
+    }
+    print(json.dumps(line), flush=True)
+
+
+def cpu_baseline(a):
+    from oracle import cpu_port
+    cores = os.cpu_count() or 1
+    nodes = min(a.cpu_nodes, a.nodes)
+    edges = int(round(a.edges * (nodes / a.nodes)))
+    g = cpu_port.powerlaw_graph_host(nodes, edges, a.seed)
+    probe = cpu_port.run_reference_pipeline(g, a.cpu_walks_per_step, 2, 1, a.walk_len, a.p, a.q, True, a.radius, a.emb, a.neg,
+                                            cores, optimizer='adam', seed=a.seed)
+    steps = max(3, min(200, int(a.cpu_seconds / max(probe['seconds'] / 2, 1e-3))))
+    r = cpu_port.run_reference_pipeline(g, a.cpu_walks_per_step, steps, 1, a.walk_len, a.p, a.q, True, a.radius, a.emb, a.neg,
+                                        cores, optimizer='adam', seed=a.seed + 1)
+    return {
+        'value': r['pairs_per_s'], 'unit': UNIT, 'cores': cores, 'kind': 'port',
+        'sample': (f'{steps} steps x {a.cpu_walks_per_step} walks ({r["seconds"]:.1f} s CPU) on a {nodes}-node / {edges}-edge '
+                   f'power-law sample of S3; oracle/cpu_port.py = reference pattern: python node2vec walks on {cores} '
+                   f'processes, python collate, torch CPU SkipGram + loss + backward + dense Adam ({cores} threads)'),
+        'walk_steps_per_s': r['walk_steps_per_s'], 'sgns_pairs_per_s': r['sgns_pairs_per_s'],
+    }
+
+
+# --------------------------------------------------------------------------------------------------------------
+def run_b200(a, rank, local_rank, world):
+    import torch
+    import torch.distributed as dist
+    from shallow_encoders import _native as nat
+    from shallow_encoders.graph.synthetic import powerlaw_graph_device
+
+    assert torch.cuda.is_available(), 'bench.py needs a CUDA device (no CPU fallback); use --impl reference for the CPU arm'
+    dev = torch.device('cuda', local_rank)
+    torch.cuda.set_device(dev)
+    if world > 1:
+        dist.init_process_group('nccl', device_id=dev)
+    nat.load()
+
+    # ---- resident state: replicated CSR, tables ----------------------------------------------------------------
+    csr = powerlaw_graph_device(a.nodes, a.edges, a.seed, dev)
+    vocab = a.nodes + 1                                   # row 0 = '<unk>' (torch_dataset.py:99-110)
+    gen = torch.Generator(device=dev)
+    gen.manual_seed(a.seed)                               # same init on every rank
+    bound = (6.0 / (vocab + a.emb)) ** 0.5                # xavier_uniform_ (model.py:26-27)
+    w_in = (torch.rand(vocab, a.emb, device=dev, generator=gen) * 2 - 1) * bound
+    w_out = (torch.rand(vocab, a.emb, device=dev, generator=gen) * 2 - 1) * bound
+    flags = nat.SCATTER_RED if a.scatter == 'red' else nat.SCATTER_STORE
+
+    # ---- schedule: shuffled node list, walks_per_node consecutive walks per node (graph/datasets.py:45,76) -----
+    total_steps = a.warmup + 2 * a.steps + 2
+    n_walks = a.walks_per_step
+    g_cpu = torch.Generator()
+    g_cpu.manual_seed(a.seed)
+    order = torch.randperm(a.nodes, generator=g_cpu, dtype=torch.int64)
+    n_cen = a.walk_len - 2 * a.radius
+
+    def starts_for(step):
+        # global walk index of this rank's j-th walk in `step`: ((step * world + rank) * n_walks + j)
+        base = (step * world + rank) * n_walks
+        idx = (torch.arange(base, base + n_walks, dtype=torch.int64) // a.walks_per_node) % a.nodes
+        return order[idx].to(torch.int32), base
+
+    host_starts = [starts_for(s) for s in range(total_steps)]
+    pinned = [(st.pin_memory(), base) for st, base in host_starts]
+    dev_starts = [(st.to(dev), base) for st, base in host_starts]
+    walks = torch.empty((n_walks, a.walk_len), dtype=torch.int32, device=dev)
+    stats = torch.zeros(nat.STATS_LEN, dtype=torch.float64, device=dev)
+    scratch = {'starts': torch.empty(n_walks, dtype=torch.int32, device=dev), 'walks': walks, 'stats': stats}
+    stats_host = torch.zeros(nat.STATS_LEN, dtype=torch.float64).pin_memory()
+
+    def sync_tables():
+        if world > 1:
+            dist.all_reduce(w_in, op=dist.ReduceOp.AVG)
+            dist.all_reduce(w_out, op=dist.ReduceOp.AVG)
+
+    ev = lambda: torch.cuda.Event(enable_timing=True)   # noqa: E731
+    sgns_events, walk_events = [], []
+
+    def device_step(step, record=False):
+        st, base = dev_starts[step]
+        if record:
+            e0, e1, e2 = ev(), ev(), ev()
+            e0.record()
+        nat.walk(csr, st, a.walk_len, a.p, a.q, True, nat.RULE_REFERENCE, a.seed, walk_id_base=base, out=walks)
+        if record:
+            e1.record()
+        nat.sgns_update_walks(w_in, w_out, walks, a.radius, a.neg, 1, a.lr, a.seed + 1, centre_id_base=base * n_cen,
+                              flags=flags, stats=stats)
+        if record:
+            e2.record()
+            walk_events.append((e0, e1))
+            sgns_events.append((e1, e2))
+        sync_tables()
+
+    def host_step(step):
+        st, base = pinned[step]
+        nat.host_walk_sgns_step(csr, st, a.walk_len, a.p, a.q, True, nat.RULE_REFERENCE, a.seed, base, w_in, w_out, a.radius,
+                                a.neg, 1, a.lr, scratch, stats_host, flags=flags)
+        sync_tables()
+
+    def barrier():
+        torch.cuda.synchronize()
+        if world > 1:
+            dist.barrier()
+            torch.cuda.synchronize()
+
+    def max_over_ranks(ms):
+        if world == 1:
+            return ms
+        t = torch.tensor([ms], dtype=torch.float64, device=dev)
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        return float(t.item())
+
+    # ---- device-resident timing (`value`) ---------------------------------------------------------------------
+    for s in range(a.warmup):
+        device_step(s)
+    sampler = ClockSampler(nvml_index(local_rank))
+    barrier()
+    launches0 = nat.launches()
+    sampler.start()
+    torch.cuda.profiler.start()          # `ncu --profile-from-start off` captures exactly the timed region
+    t0, t1 = ev(), ev()
+    t0.record()
+    for s in range(a.warmup, a.warmup + a.steps):
+        device_step(s, record=True)
+    t1.record()
+    barrier()
+    torch.cuda.profiler.stop()
+    clocks = sampler.stop()
+    launches = nat.launches() - launches0
+    ms_total = max_over_ranks(t0.elapsed_time(t1))
+    pairs_per_step = n_walks * n_cen * 2 * a.radius
+    walk_steps_per_step = n_walks * (a.walk_len - 1)
+    value = world * pairs_per_step * a.steps / (ms_total / 1e3)
+    sgns_ms = sum(x.elapsed_time(y) for x, y in sgns_events) / len(sgns_events)
+    walk_ms = sum(x.elapsed_time(y) for x, y in walk_events) / len(walk_events)
+    stat_vals = stats.tolist()
+
+    # ---- end-to-end through the host-buffer C-ABI entry (`e2e`) -------------------------------------------------
+    host_step(a.warmup + a.steps)       # warm
+    barrier()
+    w0 = time.perf_counter()
+    e0, e1 = ev(), ev()
+    e0.record()
+    for s in range(a.warmup + a.steps + 1, a.warmup + 2 * a.steps + 1):
+        host_step(s)
+    e1.record()
+    barrier()
+    e2e_wall = time.perf_counter() - w0
+    e2e_ms = max_over_ranks(max(e0.elapsed_time(e1), 0.0))
+    e2e_ms = max(e2e_ms, max_over_ranks(e2e_wall * 1e3) if world > 1 else e2e_wall * 1e3)   # host copies + sync are on the clock
+    e2e_value = world * pairs_per_step * a.steps / (e2e_ms / 1e3)
+
+    if rank != 0:
+        if world > 1:
+            dist.destroy_process_group()
+        return
+
+    peak, peak_src = measured_peak()
+    bpp = bytes_per_pair(a.emb, a.neg, a.radius)
+    achieved = pairs_per_step * bpp / (sgns_ms / 1e3) / 1e9
+    traffic = recorded_traffic()
+    line = {
+        'metric': METRIC, 'value': value, 'unit': UNIT, 'n_gpus': world, 'steps': a.steps, 'warmup': a.warmup,
+        'ms_per_step': ms_total / a.steps, 'higher_is_better': True, 'scaling': 'weak', 'vs_baseline': None, 'dtype': 'f32',
+        'data': 'synthetic', 'config': workload_config(a, world),
+        'walk_steps_per_s': world * walk_steps_per_step / (walk_ms / 1e3),
+        'sgns_kernel_pairs_per_s': world * pairs_per_step / (sgns_ms / 1e3),
+        'kernel_ms': {'walk_kernel': walk_ms, 'sgns_kernel': sgns_ms},
+        'roofline': {
+            'bound': 'hbm', 'kernel': 'sgns_kernel<MODE_WALK,4,32,1> (se_sgns_update_walks)', 'achieved': achieved, 'peak': peak,
+            'unit': 'GB/s', 'frac': achieved / peak, 'peak_source': peak_src,
+            'algorithmic_bytes_per_pair': bpp, 'pairs_per_launch': pairs_per_step,
+            'traffic': (traffic or {}).get('dram_bytes_per_launch'), 'traffic_source': (traffic or {}).get('source'),
+        },
+        'e2e': {'value': e2e_value, 'unit': UNIT, 'h2d_bytes_per_step': n_walks * 4, 'd2h_bytes_per_step': nat.STATS_LEN * 8,
+                'ms_per_step': e2e_ms / a.steps, 'api': 'se_host_walk_sgns_step (pinned host start nodes in, loss statistics out)'},
+        'gpu_launches': launches,
+        'clocks': clocks,
+        'train_stats': {'loss': (stat_vals[0] + stat_vals[1]) / max(stat_vals[4], 1), 'pairs': stat_vals[4]},
+        'graph': {'n_nodes': csr.n_nodes, 'nnz': csr.nnz, 'max_degree': csr.max_degree},
+        'library': nat.version(),
+    }
+    if world == 1 and not a.no_cpu_baseline:
+        del w_in, w_out, csr
+        torch.cuda.empty_cache()
+        try:
+            line['cpu_baseline'] = cpu_baseline(a)
+        except Exception as e:   # noqa: BLE001
+            line['cpu_baseline'] = {'value': None, 'unit': UNIT, 'cores': os.cpu_count(), 'kind': 'port', 'sample': f'failed: {e!r}'}
+    print(json.dumps(line), flush=True)
+    if world > 1:
+        dist.destroy_process_group()
+
+
+def main():
+    a = parse_args()
+    rank = int(os.environ.get('RANK', '0'))
+    local_rank = int(os.environ.get('LOCAL_RANK', '0'))
+    world = int(os.environ.get('WORLD_SIZE', '1'))
+    if a.impl == 'reference':
+        run_reference(a, rank, world)
+        return
+    if world == 1 and a.gpus > 1:
+        # launched without torchrun: re-exec under it
+        import subprocess
+        cmd = [sys.executable, '-m', 'torch.distributed.run', '--nnodes=1', f'--nproc-per-node={a.gpus}',
+               '--master-addr', '127.0.0.1', '--master-port', os.environ.get('MASTER_PORT', '29517'), *sys.argv]
+        sys.exit(subprocess.call(cmd))
+    run_b200(a, rank, local_rank, world)
+
+
+if __name__ == '__main__':
+    main()
