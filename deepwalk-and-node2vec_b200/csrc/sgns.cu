@@ -327,6 +327,66 @@ scores_kernel(const float *__restrict__ w_in, const float *__restrict__ w_out, i
     }
 }
 
+// Backward of scores_kernel (proba = 0), dense accumulate: one warp per batch row.
+__global__ void __launch_bounds__(256)
+scores_backward_kernel(const float *__restrict__ w_in, const float *__restrict__ w_out, int emb,
+                       const int64_t *__restrict__ inputs, const int64_t *__restrict__ outputs, int64_t batch, int m,
+                       const float *__restrict__ grad_scores, float *__restrict__ grad_in, float *__restrict__ grad_out) {
+    const int lane = threadIdx.x & 31;
+    const int64_t warp = ((int64_t)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+    const int64_t n_warps = ((int64_t)gridDim.x * blockDim.x) >> 5;
+    for (int64_t b = warp; b < batch; b += n_warps) {
+        const int64_t crow = __ldg(inputs + b);
+        for (int e0 = 0; e0 < emb; e0 += 32) {
+            const int e = e0 + lane;
+            const float c = e < emb ? __ldcg(w_in + crow * emb + e) : 0.f;
+            float acc = 0.f;
+            for (int j = 0; j < m; ++j) {
+                const int64_t orow = __ldg(outputs + b * m + j);
+                const float g = __ldg(grad_scores + b * m + j);
+                if (e < emb) {
+                    acc = fmaf(g, __ldcg(w_out + orow * emb + e), acc);
+                    atomicAdd(grad_out + orow * emb + e, g * c);
+                }
+            }
+            if (e < emb) atomicAdd(grad_in + crow * emb + e, acc);
+        }
+    }
+}
+
+// NegativeSamplingLoss.forward on logits (loss.py:14-22) + d(mean loss)/d(logits); one thread per (b, n).
+__global__ void __launch_bounds__(256)
+ns_loss_kernel(const float *__restrict__ pos, const float *__restrict__ neg, int64_t pairs, int n_neg, float scale,
+               double *__restrict__ stats, float *__restrict__ grad_pos, float *__restrict__ grad_neg) {
+    float lp = 0.f, ln = 0.f;
+    unsigned rec = 0, fp = 0, cnt = 0;
+    for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < pairs; i += (int64_t)gridDim.x * blockDim.x) {
+        const float s = pos[i];
+        const float sig = 1.0f / (1.0f + expf(-s));
+        lp -= logf(fmaxf(sig, CLAMP_MIN));
+        if (grad_pos) grad_pos[i] = (sig > CLAMP_MIN) ? -scale / (1.0f + expf(s)) : 0.f;
+        rec += sig >= 0.5f;
+        cnt += 1;
+        for (int k = 0; k < n_neg; ++k) {
+            const float z = neg[i * n_neg + k];
+            const float sm = 1.0f / (1.0f + expf(z)), sg = 1.0f / (1.0f + expf(-z));
+            ln -= logf(fmaxf(sm, CLAMP_MIN));
+            if (grad_neg) grad_neg[i * n_neg + k] = (sm > CLAMP_MIN) ? scale * sg : 0.f;
+            fp += sg >= 0.5f;
+        }
+    }
+    __shared__ double sred[SE_STATS_LEN];
+    if (threadIdx.x < SE_STATS_LEN) sred[threadIdx.x] = 0.0;
+    __syncthreads();
+    if (cnt) {
+        atomicAdd(&sred[0], (double)lp); atomicAdd(&sred[1], (double)ln);
+        atomicAdd(&sred[2], (double)rec); atomicAdd(&sred[3], (double)fp);
+        atomicAdd(&sred[4], (double)cnt); atomicAdd(&sred[5], (double)cnt * n_neg);
+    }
+    __syncthreads();
+    if (threadIdx.x < SE_STATS_LEN && stats && sred[threadIdx.x] != 0.0) atomicAdd(stats + threadIdx.x, sred[threadIdx.x]);
+}
+
 int common_checks(const char *fn, const void *w_in, const void *w_out, int64_t vocab, int emb, int n_neg) {
     if (!w_in || !w_out) { set_error("%s: null embedding table", fn); return SE_ERR_INVALID_ARG; }
     if (vocab < 1 || vocab > 0x7fffffffll) { set_error("%s: vocab %lld out of range", fn, (long long)vocab); return SE_ERR_INVALID_ARG; }
@@ -414,4 +474,34 @@ extern "C" int se_sgns_update_walks(float *w_in, float *w_out, int64_t vocab, in
     a.n_units = n_seq * a.n_cen;
     a.lr = lr; a.seed = seed; a.id_base = centre_id_base; a.scatter_store = flags == SE_SGNS_SCATTER_STORE;
     return se::launch<se::MODE_WALK>(a, (cudaStream_t)stream);
+}
+
+extern "C" int se_skipgram_scores_backward(const float *w_in, const float *w_out, int64_t vocab, int emb,
+                                           const int64_t *inputs, const int64_t *outputs, int64_t batch, int m,
+                                           const float *grad_scores, float *grad_in, float *grad_out, void *stream) {
+    int rc = se::common_checks("se_skipgram_scores_backward", w_in, w_out, vocab, emb, 0);
+    if (rc != SE_OK) return rc;
+    SE_REQUIRE(batch >= 0 && m >= 1, "se_skipgram_scores_backward: bad shape");
+    if (batch == 0) return SE_OK;
+    SE_REQUIRE(inputs && outputs && grad_scores && grad_in && grad_out, "se_skipgram_scores_backward: null pointer");
+    const int sms = se::sm_count();
+    if (sms <= 0) return SE_ERR_CUDA;
+    int64_t blocks = (batch + 7) / 8; if (blocks > (int64_t)sms * 8) blocks = (int64_t)sms * 8;
+    se::scores_backward_kernel<<<(int)blocks, 256, 0, (cudaStream_t)stream>>>(w_in, w_out, emb, inputs, outputs, batch, m,
+                                                                             grad_scores, grad_in, grad_out);
+    return se::check_cuda(cudaGetLastError(), "scores_backward_kernel launch");
+}
+
+extern "C" int se_ns_loss(const float *pos_logits, const float *neg_logits, int64_t batch, int n_ctx, int n_neg,
+                          double *stats, float *grad_pos, float *grad_neg, void *stream) {
+    SE_REQUIRE(batch >= 0 && n_ctx >= 1 && n_neg >= 0, "se_ns_loss: bad shape");
+    const int64_t pairs = batch * n_ctx;
+    if (pairs == 0) return SE_OK;
+    SE_REQUIRE(pos_logits && (neg_logits || n_neg == 0) && stats, "se_ns_loss: null pointer");
+    const int sms = se::sm_count();
+    if (sms <= 0) return SE_ERR_CUDA;
+    int64_t blocks = (pairs + 255) / 256; if (blocks > (int64_t)sms * 8) blocks = (int64_t)sms * 8;
+    se::ns_loss_kernel<<<(int)blocks, 256, 0, (cudaStream_t)stream>>>(pos_logits, neg_logits, pairs, n_neg,
+                                                                     1.0f / (float)pairs, stats, grad_pos, grad_neg);
+    return se::check_cuda(cudaGetLastError(), "ns_loss_kernel launch");
 }

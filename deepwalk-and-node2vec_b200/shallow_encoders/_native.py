@@ -42,6 +42,8 @@ _SIGNATURES = {
     'se_alias_build_host': (c_int, [c_p, c_i64, c_f64, c_p, c_p]),
     'se_sample_negatives': (c_int, [c_p, c_p, c_i64, c_u64, c_i64, c_i64, c_p, c_p]),
     'se_skipgram_scores': (c_int, [c_p, c_p, c_i64, c_int, c_p, c_p, c_i64, c_int, c_int, c_p, c_p]),
+    'se_skipgram_scores_backward': (c_int, [c_p, c_p, c_i64, c_int, c_p, c_p, c_i64, c_int, c_p, c_p, c_p, c_p]),
+    'se_ns_loss': (c_int, [c_p, c_p, c_i64, c_int, c_int, c_p, c_p, c_p, c_p]),
     'se_sgns_grad': (c_int, [c_p, c_p, c_i64, c_int, c_p, c_p, c_p, c_i64, c_int, c_int, c_p, c_p, c_p, c_p]),
     'se_sgns_step': (c_int, [c_p, c_p, c_i64, c_int, c_p, c_p, c_p, c_i64, c_int, c_int, c_p, c_p, c_f32, c_u64, c_i64,
                              c_int, c_p, c_p]),
@@ -222,6 +224,36 @@ def skipgram_scores(w_in: torch.Tensor, w_out: torch.Tensor, inputs: torch.Tenso
             int(bool(proba)), out.data_ptr(), _stream()))
     _launches += 1
     return out
+
+
+def skipgram_scores_backward(w_in: torch.Tensor, w_out: torch.Tensor, inputs: torch.Tensor, outputs: torch.Tensor,
+                             grad_scores: torch.Tensor, grad_in: torch.Tensor, grad_out: torch.Tensor) -> None:
+    """Accumulate the dense gradients of the raw scores into grad_in / grad_out."""
+    global _launches
+    batch, m = outputs.shape
+    with _on(w_in):
+        _check(load().se_skipgram_scores_backward(
+            _ptr(w_in, torch.float32, 'w_in'), _ptr(w_out, torch.float32, 'w_out'), w_in.shape[0], w_in.shape[1],
+            _ptr(inputs.reshape(-1), torch.int64, 'inputs'), _ptr(outputs, torch.int64, 'outputs'), batch, m,
+            _ptr(grad_scores, torch.float32, 'grad_scores'), _ptr(grad_in, torch.float32, 'grad_in'),
+            _ptr(grad_out, torch.float32, 'grad_out'), _stream()))
+    _launches += 1
+
+
+def ns_loss(pos_logits: torch.Tensor, neg_logits: torch.Tensor, want_grads: bool = True):
+    """(stats double[6] on device, grad_pos, grad_neg) for logits (B,N) / (B,N,K)."""
+    global _launches
+    batch, n_ctx = pos_logits.shape
+    n_neg = neg_logits.shape[2] if neg_logits.dim() == 3 else 0
+    stats = torch.zeros(STATS_LEN, dtype=torch.float64, device=pos_logits.device)
+    g_pos = torch.empty_like(pos_logits) if want_grads else None
+    g_neg = torch.empty_like(neg_logits) if want_grads else None
+    with _on(pos_logits):
+        _check(load().se_ns_loss(
+            _ptr(pos_logits, torch.float32, 'pos_logits'), _ptr(neg_logits, torch.float32, 'neg_logits') if n_neg else None,
+            batch, n_ctx, n_neg, stats.data_ptr(), _ptr(g_pos), _ptr(g_neg) if n_neg else None, _stream()))
+    _launches += 1
+    return stats, g_pos, g_neg
 
 
 def sgns_grad(w_in: torch.Tensor, w_out: torch.Tensor, inputs: torch.Tensor, targets: torch.Tensor,

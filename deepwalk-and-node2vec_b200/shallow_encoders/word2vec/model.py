@@ -1,0 +1,81 @@
+"""
+Word2vec models with the reference's interface (shallow_encoders/word2vec/model.py:10-91: W2VBase, SkipGram).
+
+The two tables are ordinary `nn.Embedding` parameters (state-dict keys `_input_embedding.weight`,
+`_output_embedding.weight`, Xavier-uniform init) living in HBM; scoring and its backward run in the sm_100a kernels
+(`se_skipgram_scores`, `se_skipgram_scores_backward`) through a `torch.autograd.Function`, so the reference's training
+loop (loss.backward() + any torch optimizer) works unchanged.  The fast path does not go through here at all: see
+`Word2VecTrainer.fused_step`, which updates the tables in place from walks.
+"""
+from typing import Optional
+
+import torch
+from torch import nn
+
+from shallow_encoders import _native as nat
+
+
+class _SkipGramScores(torch.autograd.Function):
+    """scores[b, j] = <W_in[inputs[b]], W_out[outputs[b, j]]> with dense gradients, as autograd gives for model.py:85-88."""
+
+    @staticmethod
+    def forward(ctx, w_in, w_out, inputs, outputs):
+        inputs, outputs = inputs.contiguous(), outputs.contiguous()
+        ctx.save_for_backward(w_in, w_out, inputs, outputs)
+        return nat.skipgram_scores(w_in.detach(), w_out.detach(), inputs, outputs, proba=False)
+
+    @staticmethod
+    def backward(ctx, grad_scores):
+        w_in, w_out, inputs, outputs = ctx.saved_tensors
+        g_in, g_out = torch.zeros_like(w_in), torch.zeros_like(w_out)
+        nat.skipgram_scores_backward(w_in.detach(), w_out.detach(), inputs, outputs, grad_scores.contiguous(), g_in, g_out)
+        return g_in, g_out, None, None
+
+
+class W2VBase(nn.Module):
+    """Input and context embedding tables."""
+
+    def __init__(self, vocab_size: int, embedding_size: int, max_norm: Optional[float] = None, device=None):
+        super().__init__()
+        if max_norm is not None:
+            raise NotImplementedError('max_norm renormalisation is not implemented on the B200 path (only the abcde toy '
+                                      'configs of the reference set it)')
+        device = torch.device('cuda' if device is None else device)
+        self._input_embedding = nn.Embedding(vocab_size, embedding_size, device=device)
+        self._output_embedding = nn.Embedding(vocab_size, embedding_size, device=device)
+        torch.nn.init.xavier_uniform_(self._input_embedding.weight)
+        torch.nn.init.xavier_uniform_(self._output_embedding.weight)
+
+    @property
+    def input_embedding(self) -> torch.Tensor:
+        """Input embedding weights as a CPU tensor (reference :29-37)."""
+        return self._input_embedding.weight.to('cpu').data
+
+    @property
+    def output_embedding(self) -> torch.Tensor:
+        """Context embedding weights as a CPU tensor (reference :39-47)."""
+        return self._output_embedding.weight.to('cpu').data
+
+    @property
+    def tables(self):
+        """(W_in, W_out) device tensors the fused kernels update in place."""
+        return self._input_embedding.weight.data, self._output_embedding.weight.data
+
+    def embed_inputs(self, inputs: torch.Tensor) -> torch.Tensor:
+        return self._input_embedding(inputs)
+
+    def embed_outs(self, outputs: torch.Tensor) -> torch.Tensor:
+        return self._output_embedding(outputs)
+
+
+class SkipGram(W2VBase):
+    """inputs (B, 1), outputs (B, N) -> scores (B, N); sigmoid applied when `proba` (reference :79-91)."""
+
+    def forward(self, inputs: torch.Tensor, outputs: torch.Tensor, proba: bool = True) -> torch.Tensor:
+        w_in, w_out = self._input_embedding.weight, self._output_embedding.weight
+        inputs = inputs.to(w_in.device).reshape(-1)
+        outputs = outputs.to(w_in.device)
+        if not (torch.is_grad_enabled() and (w_in.requires_grad or w_out.requires_grad)):
+            return nat.skipgram_scores(w_in.detach(), w_out.detach(), inputs.contiguous(), outputs.contiguous(), proba=proba)
+        scores = _SkipGramScores.apply(w_in, w_out, inputs, outputs)
+        return torch.sigmoid(scores) if proba else scores

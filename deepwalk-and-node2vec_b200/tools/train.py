@@ -1,0 +1,124 @@
+#!/usr/bin/env python
+"""
+Trains a SkipGram model from a YAML config -- the reference's entry point (tools/train.py:46-83):
+
+    python tools/train.py --config-name=sge_sg_karate_club [train.max_epochs=5 train.engine=fused ...]
+
+Outputs follow the reference's conventions (tools/conventions.py:1-27):
+    runs/<dataset>/<experiment>/checkpoints/{checkpoint_epoch=..._step=....ckpt, last.ckpt}
+    runs/<dataset>/<experiment>/run_history/train_<timestamp>.yaml
+    runs/tb_logs/<dataset>/<experiment>/scalars.jsonl            (scalar log; TensorBoard itself is out of scope)
+Checkpoints hold {'state_dict': {'_model._input_embedding.weight', '_model._output_embedding.weight'}, ...}.
+
+Engines (`train.engine`):
+    reference   Lightning's loop restated: DataLoader batches of `batch_size` walks -> collate -> training_step ->
+                backward -> YAML optimizer -> per-epoch scheduler.  Same arithmetic as the reference, kernels on the B200.
+    fused       per epoch: one walk-kernel launch + one fused window/negatives/SGNS launch per `batch_size` walks,
+                in-place SGD with lr = train.fused_lr / (pairs per launch) decayed by the YAML's StepLR schedule.
+An existing experiment directory is replaced without the reference's interactive prompt (train.py:36-42) unless --keep.
+"""
+import argparse
+import json
+import os
+import shutil
+import sys
+import time
+from datetime import datetime
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+if ROOT not in sys.path:
+    sys.path.insert(0, ROOT)
+
+import torch  # noqa: E402
+import yaml  # noqa: E402
+
+from shallow_encoders.config_parser import load_config  # noqa: E402
+
+
+def experiment_dirs(output_dir: str, dataset: str, experiment: str):
+    base = os.path.join(output_dir, dataset, experiment)
+    return {'checkpoints': os.path.join(base, 'checkpoints'), 'run_history': os.path.join(base, 'run_history'),
+            'tb_logs': os.path.join(output_dir, 'tb_logs', dataset, experiment)}
+
+
+def train(cfg, keep: bool = False, quiet: bool = False):
+    dirs = experiment_dirs(cfg.path.output_dir, cfg.datamodule.dataset_name, cfg.train.experiment)
+    for key in ('checkpoints', 'tb_logs'):
+        if os.path.exists(dirs[key]) and not keep:
+            shutil.rmtree(dirs[key])
+    for d in dirs.values():
+        os.makedirs(d, exist_ok=True)
+
+    dataset = cfg.datamodule.instantiate_dataset()
+    trainer = cfg.instantiate_trainer(dataset=dataset)
+    scalars = open(os.path.join(dirs['tb_logs'], 'scalars.jsonl'), 'a')
+
+    def end_of_epoch(tr, epoch, means):
+        name = f'checkpoint_epoch={epoch:06d}_step={tr.global_step:09d}.ckpt'
+        tr.save_checkpoint(os.path.join(dirs['checkpoints'], name))
+        tr.save_checkpoint(os.path.join(dirs['checkpoints'], 'last.ckpt'))
+        scalars.write(json.dumps({'epoch': epoch, 'step': tr.global_step, **means}) + '\n')
+        scalars.flush()
+        if not quiet:
+            print(f'epoch {epoch:3d} step {tr.global_step:7d} ' + ' '.join(f'{k}={v:.4f}' for k, v in means.items()), flush=True)
+
+    t0 = time.time()
+    if cfg.train.engine == 'reference':
+        trainer.fit(cfg.datamodule.instantiate_dataloader(dataset=dataset), cfg.train.max_epochs, on_epoch_end=end_of_epoch)
+    elif cfg.train.engine == 'fused':
+        fit_fused(cfg, dataset, trainer, end_of_epoch)
+    else:
+        raise ValueError(f'unknown train.engine "{cfg.train.engine}"')
+    torch.cuda.synchronize()
+    if not quiet:
+        print(f'trained {cfg.train.max_epochs} epochs in {time.time() - t0:.1f}s; checkpoints in {dirs["checkpoints"]}')
+    return trainer, dataset
+
+
+def fit_fused(cfg, dataset, trainer, end_of_epoch):
+    """Walk kernel + fused SGNS kernel; one launch per `batch_size` walks so that a launch is the reference's mini-batch."""
+    r = cfg.datamodule.context_radius
+    sched = cfg.train.scheduler.get('scheduler', cfg.train.scheduler)
+    step_size, gamma = int(sched.get('step_size', 10 ** 9)), float(sched.get('gamma', 1.0))
+    from shallow_encoders import _native as nat
+    stats = torch.zeros(nat.STATS_LEN, dtype=torch.float64, device='cuda')
+    for epoch in range(cfg.train.max_epochs):
+        trainer.current_epoch = epoch
+        lr_batch = cfg.train.fused_lr * gamma ** (epoch // step_size)
+        tokens = dataset.epoch_tokens()[:, :cfg.datamodule.max_length]
+        stats.zero_()
+        for lo in range(0, tokens.shape[0], cfg.datamodule.batch_size):
+            chunk = tokens[lo:lo + cfg.datamodule.batch_size].contiguous()
+            pairs = chunk.shape[0] * (chunk.shape[1] - 2 * r) * 2 * r
+            trainer.fused_step(chunk, r, lr_batch / pairs, row_offset=dataset.row_offset,
+                               seed=epoch * 1_000_003 + lo, stats=stats)
+            trainer.global_step += 1
+        s = stats.tolist()
+        p = max(s[4], 1.0)
+        means = {'train-epoch/loss': (s[0] + s[1]) / p, 'train-epoch/positive-loss': s[0] / p,
+                 'train-epoch/negative-loss': s[1] / p, 'train-metrics/recall': s[2] / p,
+                 'train-metrics/precision': 1 - s[3] / max(s[5], 1.0), 'epoch/lr': lr_batch}
+        for name, value in means.items():
+            trainer.log(name, value)
+        end_of_epoch(trainer, epoch, means)
+
+
+def main(argv=None):
+    ap = argparse.ArgumentParser(description=__doc__, formatter_class=argparse.RawDescriptionHelpFormatter)
+    ap.add_argument('--config-name', required=True)
+    ap.add_argument('--config-path', default=None)
+    ap.add_argument('--keep', action='store_true', help='do not delete an existing experiment directory')
+    ap.add_argument('overrides', nargs='*', help='hydra-style a.b.c=value overrides')
+    a = ap.parse_args(argv)
+    kwargs = {'config_path': a.config_path} if a.config_path else {}
+    cfg = load_config(a.config_name, a.overrides, **kwargs)
+    dirs = experiment_dirs(cfg.path.output_dir, cfg.datamodule.dataset_name, cfg.train.experiment)
+    os.makedirs(dirs['run_history'], exist_ok=True)
+    stamp = datetime.now().strftime('%Y-%m-%d_%H-%M-%S.%f')
+    with open(os.path.join(dirs['run_history'], f'train_{stamp}.yaml'), 'w') as fh:
+        yaml.safe_dump({'config_name': a.config_name, 'overrides': a.overrides}, fh)
+    train(cfg, keep=a.keep)
+
+
+if __name__ == '__main__':
+    main()

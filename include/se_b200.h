@@ -113,6 +113,19 @@ int se_sample_negatives(const float *prob, const int32_t *alias, int64_t vocab, 
 int se_skipgram_scores(const float *w_in, const float *w_out, int64_t vocab, int emb, const int64_t *inputs,
                        const int64_t *outputs, int64_t batch, int m, int proba, float *out, void *stream);
 
+/* Backward of se_skipgram_scores with proba = 0 (what autograd does for model.py:85-88): ACCUMULATES
+ * grad_in[inputs[b]] += sum_j g[b,j] * W_out[outputs[b,j]] and grad_out[outputs[b,j]] += g[b,j] * W_in[inputs[b]]
+ * into dense [vocab x emb] buffers. */
+int se_skipgram_scores_backward(const float *w_in, const float *w_out, int64_t vocab, int emb, const int64_t *inputs,
+                                const int64_t *outputs, int64_t batch, int m, const float *grad_scores, float *grad_in,
+                                float *grad_out, void *stream);
+
+/* NegativeSamplingLoss.forward on logits (word2vec/loss.py:14-22): pos_logits (B,N), neg_logits (B,N,K) -> stats
+ * (same layout as above) and, when non-NULL, grad_pos (B,N) = d mean(positive-loss)/d pos_logits and
+ * grad_neg (B,N,K) = d mean(negative-loss)/d neg_logits. */
+int se_ns_loss(const float *pos_logits, const float *neg_logits, int64_t batch, int n_ctx, int n_neg, double *stats,
+               float *grad_pos, float *grad_neg, void *stream);
+
 /* Word2VecTrainer.training_step + backward (word2vec/trainer.py:131-152, word2vec/loss.py:14-22): loss sums /
  * counters into stats (divide by stats[4] for the reference's means) and, when grad_in/grad_out are non-NULL,
  * ACCUMULATES the dense gradients of the MEAN loss into them (caller zeroes; same values as autograd). */

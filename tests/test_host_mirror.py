@@ -1,0 +1,98 @@
+"""CPU: host-side mirror of the reference API (registry, vocabulary order, window collate, schedule, config loader).
+Nothing here launches a kernel."""
+import os
+
+import numpy as np
+import pytest
+import torch
+
+from helpers import GOLDEN
+from shallow_encoders.config_parser import load_config
+from shallow_encoders.graph.datasets import GraphTriplets, KarateClubDataset, RandomWalkDataset
+from shallow_encoders.graph.random_walk_generator import DeepWalk, Node2Vec, random_walk_factory
+from shallow_encoders.word2vec.dataloader.registry import DATASET_REGISTRY, register_dataset
+from shallow_encoders.word2vec.dataloader.torch_dataset import GraphDataset, W2VCollateFunctional
+
+
+def test_registry_has_reference_names_and_rejects_duplicates():
+    for name in ('graph_triplets', 'graph_karate_club', 'graph_cora'):
+        assert name in DATASET_REGISTRY
+    with pytest.raises(AssertionError, match='Already registered'):
+        register_dataset('graph_triplets')(object)
+
+
+def test_vocab_order_matches_reference_golden():
+    z = np.load(os.path.join(GOLDEN, 'vocab.npz'))
+    ds = GraphDataset('graph_karate_club', context_radius=2,
+                      additional_parameters={'walks_per_node': 2, 'walk_length': 10, 'method': 'deepwalk'})
+    assert ds.vocab.get_itos() == [str(s) for s in z['karate_itos']]
+    assert len(ds.vocab) == 35 and ds.vocab['<unk>'] == 0 and ds.vocab['n01'] == 1 and ds.vocab['nope'] == 0
+    assert ds.vocab(['n34', 'zzz']) == [34, 0] and 'n05' in ds.vocab and ds.has_labels and not ds.has_features
+    assert len(ds) == 68 and ds.labels['n10'] == '2' and ds.labels['n09'] == '1'
+    tri = GraphDataset('graph_triplets', additional_parameters={'walks_per_node': 4, 'walk_length': 5})
+    assert tri.vocab.get_itos() == [str(s) for s in z['triplets_itos']]
+    assert tri.graph.number_of_edges() == 6          # the code adds x1-x2, x2-x3 only (datasets.py:140-141)
+    with pytest.raises(AssertionError, match='not supported'):
+        GraphDataset('no_such_dataset')
+
+
+def test_collate_matches_reference_golden():
+    z = np.load(os.path.join(GOLDEN, 'collate.npz'))
+    inp, tgt = W2VCollateFunctional('sg', 3, 256)([torch.arange(10, 18)])
+    assert inp.tolist() == z['worked_inputs'].tolist() and tgt.tolist() == z['worked_targets'].tolist()
+    for tag in ('karate', 'clip', 'tri'):
+        texts = [torch.from_numpy(t) for t in z[f'{tag}_texts']]
+        inp, tgt = W2VCollateFunctional('sg', int(z[f'{tag}_r']), int(z[f'{tag}_max_length']))(texts)
+        assert inp.dtype == torch.int64 and np.array_equal(inp.numpy(), z[f'{tag}_inputs'])
+        assert np.array_equal(tgt.numpy(), z[f'{tag}_targets'])
+        # a dense [n, L] tensor is accepted as well (device path)
+        inp2, tgt2 = W2VCollateFunctional('sg', int(z[f'{tag}_r']), int(z[f'{tag}_max_length']))(torch.stack(texts))
+        assert torch.equal(inp, inp2) and torch.equal(tgt, tgt2)
+    # ragged batch == oracle
+    from oracle import sgns_oracle
+    rng = np.random.default_rng(0)
+    ragged = [rng.integers(0, 50, size=(n,)) for n in (5, 9, 6, 12)]
+    inp, tgt = W2VCollateFunctional('sg', 2, 10)([torch.from_numpy(t) for t in ragged])
+    oi, ot = sgns_oracle.collate_sg(ragged, 2, 10)
+    assert np.array_equal(inp.numpy(), oi) and np.array_equal(tgt.numpy(), ot)
+    # cbow is the mirrored pair
+    ci, ct = W2VCollateFunctional('cbow', 2, 10)([torch.from_numpy(t) for t in ragged])
+    assert torch.equal(ci, tgt) and torch.equal(ct, inp)
+    with pytest.raises(AssertionError, match='Text is too short'):
+        W2VCollateFunctional('sg', 2, 256)([torch.arange(4)])
+    with pytest.raises(AssertionError, match='Invalid collate mode'):
+        W2VCollateFunctional('xx', 2, 256)
+
+
+def test_walk_factory_and_schedule():
+    ds = KarateClubDataset(walks_per_node=3, walk_length=10, method='node2vec', method_params={'p': 1, 'q': 0.5})
+    assert isinstance(ds.walk_generator, Node2Vec) and len(ds) == 102
+    starts = ds.epoch_starts()
+    assert starts.shape == (102,) and sorted(starts[::3].tolist()) == list(range(34))
+    assert torch.equal(starts[0::3], starts[1::3]) and torch.equal(starts[0::3], starts[2::3])   # nodes[index // wpn]
+    g = GraphTriplets(walks_per_node=1, walk_length=5).graph
+    assert isinstance(random_walk_factory('DFS', g, 5), DeepWalk)
+    assert isinstance(random_walk_factory('node2vec', g, 5, {'p': 2.0, 'q': 0.5}), Node2Vec)
+    with pytest.raises(AssertionError, match='Unknown method'):
+        random_walk_factory('bfs', g, 5)
+    with pytest.raises(AssertionError, match='Minimum walk length'):
+        DeepWalk(g, 0)
+    assert issubclass(KarateClubDataset, RandomWalkDataset)
+
+
+def test_config_loader_schema_and_overrides():
+    cfg = load_config('sge_sg_karate_club', ['train.max_epochs=3', 'datamodule.additional_parameters.method_params.q=2.0'])
+    assert cfg.train.max_epochs == 3 and cfg.train.loss.negative_samples == 1 and cfg.train.engine == 'reference'
+    assert cfg.datamodule.additional_parameters['method_params'] == {'p': 1, 'q': 2.0}
+    assert cfg.model['_target_'] == 'shallow_encoders.word2vec.model.SkipGram'
+    assert cfg.train.optimizer['_target_'] == 'torch.optim.Adam' and cfg.datamodule.batch_size == 64
+    for name in ('sge_sg_cora', 'sge_sg_graph_triplets'):
+        c = load_config(name)
+        assert c.datamodule.is_graph and c.datamodule.mode == 'sg'
+    p = torch.nn.Parameter(torch.zeros(2))
+    opt = cfg.train.instantiate_optimizer([p])
+    sched = cfg.train.instantiate_scheduler(opt)
+    assert isinstance(opt, torch.optim.Adam) and isinstance(sched, torch.optim.lr_scheduler.StepLR)
+    from shallow_encoders.split import TrainTestRatioSplit
+    from shallow_encoders.config_parser.core import instantiate
+    assert isinstance(instantiate(cfg.downstream['node_classification']['split_algorithm']), TrainTestRatioSplit)
