@@ -176,3 +176,33 @@ def run_reference_pipeline(graph: walk_oracle.OracleGraph, walks_per_step: int, 
             'walk_steps_per_s': n_steps / max(t_walk, 1e-9), 'sgns_pairs_per_s': pairs / max(t_sgns, 1e-9),
             't_walk': t_walk, 't_collate': t_collate, 't_sgns': t_sgns, 'ms_per_step': 1e3 * total / max(steps, 1),
             'cores': workers, 'cpu_count': os.cpu_count()}
+
+
+def train_reference_cpu(nx_graph, walks_per_node: int, walk_length: int, method: str, p: float, q: float, radius: int,
+                        emb: int, n_neg: int, batch_size: int, lr: float, max_epochs: int, step_size: int, gamma: float,
+                        workers: int = 1, seed: int = 0):
+    """The reference's training run on the CPU (walk -> collate -> training_step -> backward -> Adam; StepLR per epoch,
+    tools/train.py:67-83 + configs/*.yaml).  Returns the input embedding table [V, E] (row 0 = '<unk>')."""
+    import torch
+    torch.manual_seed(seed)
+    g = walk_oracle.OracleGraph.from_networkx(nx_graph)
+    pool = WalkPool(g, workers)
+    model = TorchCpuSgns(g.n_nodes + 1, emb, n_neg, lr=lr, optimizer='adam', seed=seed)
+    sched = torch.optim.lr_scheduler.StepLR(model.opt, step_size=step_size, gamma=gamma)
+    rnd = random.Random(seed)
+    nodes = list(range(g.n_nodes))
+    losses = []
+    try:
+        for epoch in range(max_epochs):
+            rnd.shuffle(nodes)
+            starts = [n for n in nodes for _ in range(walks_per_node)]
+            walks = pool.walks(starts, walk_length, p, q, method == 'node2vec', seed * 100003 + epoch)
+            tot = 0.0
+            for lo in range(0, len(walks), batch_size):
+                inputs, targets = collate(walks[lo:lo + batch_size], radius, 1 << 30, 1)
+                tot += model.step(inputs, targets)
+            losses.append(tot / max(1, (len(walks) + batch_size - 1) // batch_size))
+            sched.step()
+    finally:
+        pool.close()
+    return model.w_in.weight.detach().numpy().copy(), g.names, losses
