@@ -39,6 +39,7 @@ constexpr uint32_t PHILOX_W0 = 0x9E3779B9u, PHILOX_W1 = 0xBB67AE85u;
 constexpr uint32_t STREAM_WALK = 0x10000000u;
 constexpr uint32_t STREAM_NEG = 0x20000000u;
 constexpr uint32_t STREAM_DRAW = 0x30000000u;
+constexpr uint32_t STREAM_NEG_COIN = 0x40000000u;
 
 __host__ __device__ __forceinline__ uint32_t mulhi32(uint32_t a, uint32_t b) {
 #ifdef __CUDA_ARCH__
@@ -76,6 +77,18 @@ __device__ __forceinline__ int64_t draw_row(const float *__restrict__ prob, cons
         if (u01(r1) >= __ldg(prob + j)) j = (uint32_t)__ldg(alias + j);
     }
     return (int64_t)j;
+}
+
+__device__ __forceinline__ uint32_t pick_word(const uint4 &r, int i) {
+    return i == 0 ? r.x : i == 1 ? r.y : i == 2 ? r.z : r.w;
+}
+
+// Negative k of context n of centre `centre` is keyed independently of launch geometry and embedding size:
+//   bucket word = word (n & 3) of Philox(seed; centre, n >> 2, STREAM_NEG | k)
+//   coin word   = word (n & 3) of Philox(seed; centre, n >> 2, STREAM_NEG_COIN | k)      (alias tables only)
+// so one Philox call serves four consecutive contexts.  tests/philox_ref.py restates this.
+__device__ __forceinline__ uint4 neg_words(uint64_t seed, uint64_t centre, int n, int k, uint32_t stream) {
+    return philox(seed, centre, (uint32_t)(n >> 2), stream | (uint32_t)k);
 }
 
 constexpr unsigned FULL = 0xffffffffu;

@@ -72,6 +72,7 @@ struct SgnsArgs {
     float lr, grad_scale;
     uint64_t seed; int64_t id_base;
     int scatter_store;
+    int force_generic;                   // SE_SGNS_GENERIC_KERNEL: skip the fast path (testing / comparison)
 };
 
 template <bool FAST> __device__ __forceinline__ float sigmoidf_(float x) {
@@ -147,8 +148,10 @@ sgns_kernel(const SgnsArgs a) {
                     } else if (MODE != MODE_WALK && a.noise != nullptr) {
                         my = (int)__ldg(a.noise + (u * N + n) * K + (tj - 1));
                     } else {
-                        const uint4 r = philox(a.seed, (uint64_t)(a.id_base + u), (uint32_t)(n * K + (tj - 1)), STREAM_NEG);
-                        my = (int)draw_row(a.alias_prob, a.alias_idx, (uint32_t)a.vocab, r.x, r.y);
+                        const uint64_t cid = (uint64_t)(a.id_base + u);
+                        const uint32_t r0 = pick_word(neg_words(a.seed, cid, n, tj - 1, STREAM_NEG), n & 3);
+                        const uint32_t r1 = a.alias_prob ? pick_word(neg_words(a.seed, cid, n, tj - 1, STREAM_NEG_COIN), n & 3) : 0u;
+                        my = (int)draw_row(a.alias_prob, a.alias_idx, (uint32_t)a.vocab, r0, r1);
                     }
                 }
                 int tid[CH];
@@ -265,6 +268,282 @@ sgns_kernel(const SgnsArgs a) {
     if (threadIdx.x < SE_STATS_LEN && a.stats && sred[threadIdx.x] != 0.0) atomicAdd(a.stats + threadIdx.x, sred[threadIdx.x]);
 }
 
+
+// ------------------------------------------------------------------------------------------------------------------
+// Fast path for the in-place kernels (MODE_STEP / MODE_WALK) when a row is at least 64 floats: one WARP per centre,
+// R float4 per lane per row, CH = 8/R target rows per chunk.  Versus sgns_kernel it
+//   * issues an L2 bulk prefetch (cp.async.bulk.prefetch.L2) for every row of the NEXT chunk (and the next centre row)
+//     before working on the current one, so the register loads mostly hit L2 and twice the bytes are in flight,
+//   * reduces the CH dot products with a transposed butterfly (CH-1 + log2(32/CH) shuffles instead of 5*CH) that leaves
+//     dot c in lane group c, where sigmoid / clamp / log are evaluated ONCE per chunk instead of once per row,
+//   * draws negatives from one Philox call per four contexts (see neg_words),
+//   * knows the row length at compile time when E == 128*R (no predication, shift addressing).
+// ------------------------------------------------------------------------------------------------------------------
+__device__ __forceinline__ void prefetch_row_l2(const float *p, int bytes) {
+    asm volatile("cp.async.bulk.prefetch.L2.global [%0], %1;" ::"l"(p), "r"(bytes) : "memory");
+}
+
+template <int CH> __device__ __forceinline__ float transposed_reduce(float (&v)[CH], int lane) {
+    int off = 16;
+#pragma unroll
+    for (int n = CH; n > 1; n >>= 1, off >>= 1) {
+        const bool hi = (lane & off) != 0;
+#pragma unroll
+        for (int i = 0; i < n / 2; ++i) {
+            const float send = hi ? v[i] : v[i + n / 2];
+            const float keep = hi ? v[i + n / 2] : v[i];
+            v[i] = keep + __shfl_xor_sync(FULL, send, off);
+        }
+    }
+    float r = v[0];
+    for (; off > 0; off >>= 1) r += __shfl_xor_sync(FULL, r, off);
+    return r;      // lane l holds the dot of row (l >> (5 - log2 CH))
+}
+
+template <int MODE, int R, bool EXACT>
+__global__ void __launch_bounds__(SGNS_THREADS, (R == 1) ? 3 : 2)
+sgns_fast_kernel(const SgnsArgs a) {
+    constexpr int VEC = 4;
+    constexpr int CH = 8 / R;
+    constexpr int SHIFT = (CH == 8) ? 2 : (CH == 4) ? 3 : (CH == 2) ? 4 : 5;   // lanes per owner group = 1 << SHIFT
+    const int lane = threadIdx.x & 31;
+    const int64_t gid = (int64_t)blockIdx.x * (SGNS_THREADS / 32) + (threadIdx.x >> 5);
+    const int64_t n_groups = (int64_t)gridDim.x * (SGNS_THREADS / 32);
+    const int E = EXACT ? 128 * R : a.emb;
+    const int row_bytes = E * 4;
+    const int N = a.n_ctx, K = a.n_neg, T = 1 + a.n_neg;
+    const int n_chunks = (T + CH - 1) / CH;
+    const int Q = N * n_chunks;                     // chunks per centre
+    const bool cache_words = n_chunks == 1;         // one Philox call then serves 4 consecutive contexts
+    const bool explicit_noise = (MODE != MODE_WALK) && a.noise != nullptr;
+    const int owner_c = lane >> SHIFT;              // the row whose dot this lane holds after the reduction
+    const bool owner_rep = (lane & ((1 << SHIFT) - 1)) == 0;
+
+    int eoff[R]; bool ok[R];
+#pragma unroll
+    for (int j = 0; j < R; ++j) { eoff[j] = (lane + j * 32) * VEC; ok[j] = EXACT || eoff[j] < E; }
+
+    float loss_pos = 0.f, loss_neg = 0.f;
+    unsigned cnt_recall = 0, cnt_fp = 0, cnt_pairs = 0;
+
+    int64_t u_begin, u_end, u_step;
+    if constexpr (MODE == MODE_WALK) {
+        const int64_t span = (a.n_units + n_groups - 1) / n_groups;
+        u_begin = gid * span; u_end = min(a.n_units, u_begin + span); u_step = 1;
+    } else {
+        u_begin = gid; u_end = a.n_units; u_step = n_groups;
+    }
+
+    uint4 w_bucket = make_uint4(0, 0, 0, 0), w_coin = make_uint4(0, 0, 0, 0);
+
+    // row id owned by this lane (lane < cnt) in chunk (n, t0) of centre u; refreshes the cached Philox words
+    auto resolve = [&](int64_t u, int n, int t0) -> int {
+        const int cnt = min(CH, T - t0);
+        int my = -1;
+        const int tj = t0 + lane;
+        const bool negative_lane = lane < cnt && tj > 0 && !explicit_noise;
+        if (K > 0 && !explicit_noise && (!cache_words || (n & 3) == 0 || n == 0)) {
+            if (!cache_words || negative_lane || true) {
+                const uint64_t cid = (uint64_t)(a.id_base + u);
+                w_bucket = neg_words(a.seed, cid, n, max(tj - 1, 0), STREAM_NEG);
+                if (a.alias_prob) w_coin = neg_words(a.seed, cid, n, max(tj - 1, 0), STREAM_NEG_COIN);
+            }
+        }
+        if (lane < cnt) {
+            if (tj == 0) {
+                if constexpr (MODE == MODE_WALK) {
+                    const int64_t s = u / a.n_cen;
+                    const int pos = a.radius + (int)(u - s * a.n_cen);
+                    const int off = (n < a.radius) ? (pos - a.radius + n) : (pos + 1 + n - a.radius);
+                    my = __ldg(a.tokens + s * a.seq_len + off) + a.row_offset;
+                } else {
+                    my = (int)__ldg(a.targets + u * N + n);
+                }
+            } else if (explicit_noise) {
+                my = (int)__ldg(a.noise + (u * N + n) * K + (tj - 1));
+            } else {
+                my = (int)draw_row(a.alias_prob, a.alias_idx, (uint32_t)a.vocab, pick_word(w_bucket, n & 3), pick_word(w_coin, n & 3));
+            }
+        }
+        return my;
+    };
+    auto centre_row = [&](int64_t u) -> int64_t {
+        if constexpr (MODE == MODE_WALK) {
+            const int64_t s = u / a.n_cen;
+            return (int64_t)__ldg(a.tokens + s * a.seq_len + a.radius + (int)(u - s * a.n_cen)) + a.row_offset;
+        } else {
+            return __ldg(a.inputs + u);
+        }
+    };
+
+    int my_next = -1;
+    if (u_begin < u_end) {
+        my_next = resolve(u_begin, 0, 0);
+        if (my_next >= 0) prefetch_row_l2(a.w_out + (int64_t)my_next * E, row_bytes);
+    }
+
+    for (int64_t u = u_begin; u < u_end; u += u_step) {
+        const int64_t crow = centre_row(u);
+        float cen[R][VEC], acc[R][VEC];
+        const float *cptr = a.w_in + crow * E;
+#pragma unroll
+        for (int j = 0; j < R; ++j) {
+#pragma unroll
+            for (int e = 0; e < VEC; ++e) { cen[j][e] = 0.f; acc[j][e] = 0.f; }
+            if (ok[j]) load_vec<VEC>(cptr + eoff[j], cen[j]);
+        }
+
+        int n = 0, t0 = 0;
+        for (int q = 0; q < Q; ++q) {
+            const int my = my_next;
+            const int cnt = min(CH, T - t0);
+            const bool positive_chunk = t0 == 0;
+            // ---- look ahead one chunk: resolve its rows and start pulling them into L2 --------------------------
+            int n2 = n, t2 = t0 + CH;
+            if (t2 >= T) { t2 = 0; n2 = n + 1; }
+            if (n2 < N) {
+                my_next = resolve(u, n2, t2);
+                if (my_next >= 0) prefetch_row_l2(a.w_out + (int64_t)my_next * E, row_bytes);
+            } else if (u + u_step < u_end) {
+                my_next = resolve(u + u_step, 0, 0);
+                if (my_next >= 0) prefetch_row_l2(a.w_out + (int64_t)my_next * E, row_bytes);
+                if (lane == 31) prefetch_row_l2(a.w_in + centre_row(u + u_step) * E, row_bytes);
+            } else {
+                my_next = -1;
+            }
+            // ---- gather the chunk -----------------------------------------------------------------------------
+            int tid[CH];
+            float row[CH][R][VEC];
+            float dot[CH];
+#pragma unroll
+            for (int c = 0; c < CH; ++c) tid[c] = __shfl_sync(FULL, my, c);
+#pragma unroll
+            for (int c = 0; c < CH; ++c) {
+                const float *rp = a.w_out + (int64_t)tid[c] * E;
+#pragma unroll
+                for (int j = 0; j < R; ++j) {
+#pragma unroll
+                    for (int e = 0; e < VEC; ++e) row[c][j][e] = 0.f;
+                    if (c < cnt && ok[j]) load_vec<VEC>(rp + eoff[j], row[c][j]);
+                }
+            }
+#pragma unroll
+            for (int c = 0; c < CH; ++c) {
+                float d = 0.f;
+#pragma unroll
+                for (int j = 0; j < R; ++j)
+#pragma unroll
+                    for (int e = 0; e < VEC; ++e) d = fmaf(row[c][j][e], cen[j][e], d);
+                dot[c] = d;
+            }
+            const float s = transposed_reduce<CH>(dot, lane);
+            // ---- sigmoid / clamp / log once per chunk, in the lane group that owns the row (loss.py:15-16) ---------
+            float step_mine = 0.f;
+            if (owner_c < cnt) {
+                const bool positive = positive_chunk && owner_c == 0;
+                const float x = positive ? s : -s;                       // loss = -log clamp(sigmoid(x), 1e-6)
+                const float e = __expf(-x);
+                const float sig = __fdividef(1.0f, 1.0f + e);
+                const bool live = sig > CLAMP_MIN;
+                const float g = live ? (positive ? -(e * sig) : (e * sig)) : 0.f;   // dL/ds: -sigmoid(-s) | sigmoid(s)
+                step_mine = -a.lr * g;
+                if (owner_rep) {
+                    const float l = -__logf(fmaxf(sig, CLAMP_MIN));
+                    if (positive) { loss_pos += l; cnt_recall += x >= 0.f; cnt_pairs += 1; }
+                    else { loss_neg += l; cnt_fp += x <= 0.f; }
+                }
+            }
+            // ---- scatter ----------------------------------------------------------------------------------------
+#pragma unroll
+            for (int c = 0; c < CH; ++c) {
+                const float step = __shfl_sync(FULL, step_mine, c << SHIFT);
+                if (c < cnt) {
+                    float *rp = a.w_out + (int64_t)tid[c] * E;
+#pragma unroll
+                    for (int j = 0; j < R; ++j) {
+                        float d[VEC];
+#pragma unroll
+                        for (int e = 0; e < VEC; ++e) {
+                            acc[j][e] = fmaf(step, row[c][j][e], acc[j][e]);
+                            d[e] = step * cen[j][e];
+                        }
+                        if (ok[j]) {
+                            if (a.scatter_store) {
+#pragma unroll
+                                for (int e = 0; e < VEC; ++e) d[e] += row[c][j][e];
+                                store_vec<VEC>(rp + eoff[j], d);
+                            } else {
+                                red_vec<VEC>(rp + eoff[j], d);
+                            }
+                        }
+                    }
+                }
+            }
+            t0 = t2; n = n2;
+        }
+#pragma unroll
+        for (int j = 0; j < R; ++j) {
+            if (!ok[j]) continue;
+            float *cp = a.w_in + crow * E + eoff[j];
+            if (a.scatter_store) {
+                float d[VEC];
+#pragma unroll
+                for (int e = 0; e < VEC; ++e) d[e] = cen[j][e] + acc[j][e];
+                store_vec<VEC>(cp, d);
+            } else {
+                red_vec<VEC>(cp, acc[j]);
+            }
+        }
+    }
+
+    __shared__ double sred[SE_STATS_LEN];
+    if (threadIdx.x < SE_STATS_LEN) sred[threadIdx.x] = 0.0;
+    __syncthreads();
+    if (loss_pos != 0.f || loss_neg != 0.f || cnt_pairs != 0 || cnt_fp != 0 || cnt_recall != 0) {
+        atomicAdd(&sred[0], (double)loss_pos);
+        atomicAdd(&sred[1], (double)loss_neg);
+        atomicAdd(&sred[2], (double)cnt_recall);
+        atomicAdd(&sred[3], (double)cnt_fp);
+        atomicAdd(&sred[4], (double)cnt_pairs);
+        atomicAdd(&sred[5], (double)cnt_pairs * (double)K);
+    }
+    __syncthreads();
+    if (threadIdx.x < SE_STATS_LEN && a.stats && sred[threadIdx.x] != 0.0) atomicAdd(a.stats + threadIdx.x, sred[threadIdx.x]);
+}
+
+template <int MODE, int R, bool EXACT>
+int launch_fast_one(const SgnsArgs &a, cudaStream_t stream) {
+    auto kern = sgns_fast_kernel<MODE, R, EXACT>;
+    int occ = 0;
+    if (check_cuda(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, kern, SGNS_THREADS, 0), "occupancy") != SE_OK) return SE_ERR_CUDA;
+    if (occ < 1) occ = 1;
+    const int sms = sm_count();
+    if (sms <= 0) return SE_ERR_CUDA;
+    constexpr int GPB = SGNS_THREADS / 32;
+    int64_t blocks = (a.n_units + GPB - 1) / GPB;
+    const int64_t cap = (int64_t)sms * occ;
+    if (blocks > cap) blocks = cap;
+    if (blocks < 1) blocks = 1;
+    kern<<<(int)blocks, SGNS_THREADS, 0, stream>>>(a);
+    return check_cuda(cudaGetLastError(), "sgns_fast_kernel launch");
+}
+
+// Returns SE_ERR_UNSUPPORTED when the shape is not covered (caller falls back to sgns_kernel).
+template <int MODE>
+int launch_fast(const SgnsArgs &a, cudaStream_t stream) {
+    if (a.emb % 4 != 0 || a.emb <= 64 || a.emb > 1024 || a.n_neg > 64) return SE_ERR_UNSUPPORTED;
+    if (((uintptr_t)a.w_in % 16) || ((uintptr_t)a.w_out % 16)) return SE_ERR_UNSUPPORTED;
+    const int nvec = a.emb / 4;
+    if (a.emb == 128) return launch_fast_one<MODE, 1, true>(a, stream);
+    if (a.emb == 256) return launch_fast_one<MODE, 2, true>(a, stream);
+    if (a.emb == 512) return launch_fast_one<MODE, 4, true>(a, stream);
+    if (a.emb == 1024) return launch_fast_one<MODE, 8, true>(a, stream);
+    if (nvec <= 32) return launch_fast_one<MODE, 1, false>(a, stream);
+    if (nvec <= 64) return launch_fast_one<MODE, 2, false>(a, stream);
+    if (nvec <= 128) return launch_fast_one<MODE, 4, false>(a, stream);
+    return launch_fast_one<MODE, 8, false>(a, stream);
+}
+
 template <int MODE, int VEC, int G, int R>
 int launch_one(const SgnsArgs &a, cudaStream_t stream) {
     auto kern = sgns_kernel<MODE, VEC, G, R>;
@@ -300,6 +579,12 @@ int launch_vec(const SgnsArgs &a, int nvec, cudaStream_t stream) {
 template <int MODE>
 int launch(const SgnsArgs &a, cudaStream_t stream) {
     if (a.n_units <= 0) return SE_OK;
+    if constexpr (MODE != MODE_GRAD) {
+        if (!a.force_generic) {
+            const int rc = launch_fast<MODE>(a, stream);
+            if (rc != SE_ERR_UNSUPPORTED) return rc;
+        }
+    }
     const bool al16 = ((uintptr_t)a.w_in % 16 == 0) && ((uintptr_t)a.w_out % 16 == 0) &&
                       (MODE != MODE_GRAD || (((uintptr_t)a.grad_in % 16 == 0) && ((uintptr_t)a.grad_out % 16 == 0)));
     const bool al8 = ((uintptr_t)a.w_in % 8 == 0) && ((uintptr_t)a.w_out % 8 == 0) &&
@@ -446,12 +731,13 @@ extern "C" int se_sgns_step(float *w_in, float *w_out, int64_t vocab, int emb, c
     if (batch == 0) return SE_OK;
     SE_REQUIRE(inputs && targets, "se_sgns_step: null index tensor");
     SE_REQUIRE((alias_prob == nullptr) == (alias_idx == nullptr), "se_sgns_step: pass both alias arrays or neither");
-    SE_REQUIRE(flags == SE_SGNS_SCATTER_RED || flags == SE_SGNS_SCATTER_STORE, "se_sgns_step: unknown flags %d", flags);
+    SE_REQUIRE((flags & ~(SE_SGNS_SCATTER_STORE | SE_SGNS_GENERIC_KERNEL)) == 0, "se_sgns_step: unknown flags %d", flags);
     se::SgnsArgs a{};
     a.w_in = w_in; a.w_out = w_out; a.inputs = inputs; a.targets = targets; a.noise = noise;
     a.alias_prob = alias_prob; a.alias_idx = alias_idx;
     a.stats = stats; a.n_units = batch; a.vocab = vocab; a.emb = emb; a.n_ctx = n_ctx; a.n_neg = n_neg;
-    a.lr = lr; a.seed = seed; a.id_base = pair_id_base; a.scatter_store = flags == SE_SGNS_SCATTER_STORE;
+    a.lr = lr; a.seed = seed; a.id_base = pair_id_base; a.scatter_store = (flags & SE_SGNS_SCATTER_STORE) != 0;
+    a.force_generic = (flags & SE_SGNS_GENERIC_KERNEL) != 0;
     return se::launch<se::MODE_STEP>(a, (cudaStream_t)stream);
 }
 
@@ -466,13 +752,14 @@ extern "C" int se_sgns_update_walks(float *w_in, float *w_out, int64_t vocab, in
     // W2VCollateFunctional asserts text_length >= 2r+1 (torch_dataset.py:298)
     SE_REQUIRE(seq_len >= 2 * radius + 1, "Text is too short! [text_length=%d] < [min_text_length=%d]", seq_len, 2 * radius + 1);
     SE_REQUIRE((alias_prob == nullptr) == (alias_idx == nullptr), "se_sgns_update_walks: pass both alias arrays or neither");
-    SE_REQUIRE(flags == SE_SGNS_SCATTER_RED || flags == SE_SGNS_SCATTER_STORE, "se_sgns_update_walks: unknown flags %d", flags);
+    SE_REQUIRE((flags & ~(SE_SGNS_SCATTER_STORE | SE_SGNS_GENERIC_KERNEL)) == 0, "se_sgns_update_walks: unknown flags %d", flags);
     se::SgnsArgs a{};
     a.w_in = w_in; a.w_out = w_out; a.tokens = tokens; a.alias_prob = alias_prob; a.alias_idx = alias_idx;
     a.stats = stats; a.vocab = vocab; a.emb = emb; a.n_ctx = 2 * radius; a.n_neg = n_neg;
     a.seq_len = seq_len; a.radius = radius; a.n_cen = seq_len - 2 * radius; a.row_offset = row_offset;
     a.n_units = n_seq * a.n_cen;
-    a.lr = lr; a.seed = seed; a.id_base = centre_id_base; a.scatter_store = flags == SE_SGNS_SCATTER_STORE;
+    a.lr = lr; a.seed = seed; a.id_base = centre_id_base; a.scatter_store = (flags & SE_SGNS_SCATTER_STORE) != 0;
+    a.force_generic = (flags & SE_SGNS_GENERIC_KERNEL) != 0;
     return se::launch<se::MODE_WALK>(a, (cudaStream_t)stream);
 }
 

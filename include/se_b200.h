@@ -42,6 +42,8 @@ extern "C" {
 /* flags for the SGNS update kernels */
 #define SE_SGNS_SCATTER_RED 0   /* red.global.add.v4.f32 scatter: concurrent updates of a row all land */
 #define SE_SGNS_SCATTER_STORE 1 /* plain read-modify-write stores: classic racy Hogwild */
+#define SE_SGNS_GENERIC_KERNEL 2 /* bit flag: use the generic group-per-centre kernel even where the warp-per-centre
+                                    fast kernel applies (same results; for testing and A/B timing) */
 
 /* stats layout written by the SGNS kernels (double[SE_STATS_LEN], ACCUMULATED into, caller zeroes):
  *   [0] sum over pairs of positive loss   -log clamp(sigmoid(s+), 1e-6)          (word2vec/loss.py:15)

@@ -3,7 +3,7 @@ import numpy as np
 
 M0, M1 = np.uint64(0xD2511F53), np.uint64(0xCD9E8D57)
 W0, W1 = 0x9E3779B9, 0xBB67AE85
-STREAM_WALK, STREAM_NEG, STREAM_DRAW = 0x10000000, 0x20000000, 0x30000000
+STREAM_WALK, STREAM_NEG, STREAM_DRAW, STREAM_NEG_COIN = 0x10000000, 0x20000000, 0x30000000, 0x40000000
 MASK = np.uint64(0xFFFFFFFF)
 
 
@@ -38,11 +38,21 @@ def draw_row(r0, r1, vocab, prob=None, alias=None):
 
 
 def negatives(seed, centre_ids, n_ctx, n_neg, vocab, prob=None, alias=None):
-    """(len(centre_ids), n_ctx, n_neg) int64: negative k of (centre, context n) = Philox(seed; centre, n*K+k)."""
-    c = np.asarray(centre_ids, dtype=np.uint64)[:, None, None]
-    sub = (np.arange(n_ctx)[:, None] * n_neg + np.arange(n_neg)[None, :])[None]
-    ids = np.broadcast_to(c, (len(centre_ids), n_ctx, n_neg))
-    r0, r1, _, _ = philox(seed, ids, np.broadcast_to(sub, ids.shape), STREAM_NEG)
+    """(len(centre_ids), n_ctx, n_neg) int64, keyed as csrc/common.cuh `neg_words`: negative k of context n of centre c
+    uses word (n & 3) of Philox(seed; c, n >> 2, STREAM_NEG | k) (and STREAM_NEG_COIN | k for the alias coin)."""
+    c = np.asarray(centre_ids, dtype=np.uint64)
+    shape = (len(c), n_ctx, n_neg)
+    ids = np.broadcast_to(c[:, None, None], shape)
+    n = np.broadcast_to(np.arange(n_ctx)[None, :, None], shape)
+    k = np.broadcast_to(np.arange(n_neg)[None, None, :], shape)
+
+    def word(stream):
+        w = philox4x32_10(ids & MASK, ids >> np.uint64(32), (n >> 2).astype(np.uint64), (stream | k).astype(np.uint64),
+                          seed & 0xFFFFFFFF, (seed >> 32) & 0xFFFFFFFF)
+        return np.choose(n & 3, w)
+
+    r0 = word(STREAM_NEG)
+    r1 = word(STREAM_NEG_COIN) if prob is not None else r0
     return draw_row(r0, r1, vocab, prob, alias)
 
 
