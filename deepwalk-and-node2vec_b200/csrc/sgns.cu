@@ -270,19 +270,14 @@ sgns_kernel(const SgnsArgs a) {
 
 
 // ------------------------------------------------------------------------------------------------------------------
-// Fast path for the in-place kernels (MODE_STEP / MODE_WALK) when a row is at least 64 floats: one WARP per centre,
-// R float4 per lane per row, CH = 8/R target rows per chunk.  Versus sgns_kernel it
-//   * issues an L2 bulk prefetch (cp.async.bulk.prefetch.L2) for every row of the NEXT chunk (and the next centre row)
-//     before working on the current one, so the register loads mostly hit L2 and twice the bytes are in flight,
+// Fast path for the in-place kernels (MODE_STEP / MODE_WALK) for rows longer than 128 floats or more than 7 negatives:
+// one WARP per centre, R float4 per lane per row, CH = 8/R target rows per chunk.  Versus sgns_kernel it
+//   * resolves the row ids of the NEXT chunk before working on the current one,
 //   * reduces the CH dot products with a transposed butterfly (CH-1 + log2(32/CH) shuffles instead of 5*CH) that leaves
 //     dot c in lane group c, where sigmoid / clamp / log are evaluated ONCE per chunk instead of once per row,
 //   * draws negatives from one Philox call per four contexts (see neg_words),
 //   * knows the row length at compile time when E == 128*R (no predication, shift addressing).
 // ------------------------------------------------------------------------------------------------------------------
-__device__ __forceinline__ void prefetch_row_l2(const float *p, int bytes) {
-    asm volatile("cp.async.bulk.prefetch.L2.global [%0], %1;" ::"l"(p), "r"(bytes) : "memory");
-}
-
 template <int CH> __device__ __forceinline__ float transposed_reduce(float (&v)[CH], int lane) {
     int off = 16;
 #pragma unroll
@@ -301,7 +296,7 @@ template <int CH> __device__ __forceinline__ float transposed_reduce(float (&v)[
 }
 
 template <int MODE, int R, bool EXACT>
-__global__ void __launch_bounds__(SGNS_THREADS, (R == 1) ? 3 : 2)
+__global__ void __launch_bounds__(SGNS_THREADS, 2)
 sgns_fast_kernel(const SgnsArgs a) {
     constexpr int VEC = 4;
     constexpr int CH = 8 / R;
@@ -310,7 +305,6 @@ sgns_fast_kernel(const SgnsArgs a) {
     const int64_t gid = (int64_t)blockIdx.x * (SGNS_THREADS / 32) + (threadIdx.x >> 5);
     const int64_t n_groups = (int64_t)gridDim.x * (SGNS_THREADS / 32);
     const int E = EXACT ? 128 * R : a.emb;
-    const int row_bytes = E * 4;
     const int N = a.n_ctx, K = a.n_neg, T = 1 + a.n_neg;
     const int n_chunks = (T + CH - 1) / CH;
     const int Q = N * n_chunks;                     // chunks per centre
@@ -379,7 +373,6 @@ sgns_fast_kernel(const SgnsArgs a) {
     int my_next = -1;
     if (u_begin < u_end) {
         my_next = resolve(u_begin, 0, 0);
-        if (my_next >= 0) prefetch_row_l2(a.w_out + (int64_t)my_next * E, row_bytes);
     }
 
     for (int64_t u = u_begin; u < u_end; u += u_step) {
@@ -398,16 +391,13 @@ sgns_fast_kernel(const SgnsArgs a) {
             const int my = my_next;
             const int cnt = min(CH, T - t0);
             const bool positive_chunk = t0 == 0;
-            // ---- look ahead one chunk: resolve its rows and start pulling them into L2 --------------------------
+            // ---- look ahead one chunk: resolve its row ids (Philox / index loads) off the critical path --------------
             int n2 = n, t2 = t0 + CH;
             if (t2 >= T) { t2 = 0; n2 = n + 1; }
             if (n2 < N) {
                 my_next = resolve(u, n2, t2);
-                if (my_next >= 0) prefetch_row_l2(a.w_out + (int64_t)my_next * E, row_bytes);
             } else if (u + u_step < u_end) {
                 my_next = resolve(u + u_step, 0, 0);
-                if (my_next >= 0) prefetch_row_l2(a.w_out + (int64_t)my_next * E, row_bytes);
-                if (lane == 31) prefetch_row_l2(a.w_in + centre_row(u + u_step) * E, row_bytes);
             } else {
                 my_next = -1;
             }
@@ -511,6 +501,226 @@ sgns_fast_kernel(const SgnsArgs a) {
     if (threadIdx.x < SE_STATS_LEN && a.stats && sred[threadIdx.x] != 0.0) atomicAdd(a.stats + threadIdx.x, sred[threadIdx.x]);
 }
 
+
+// ------------------------------------------------------------------------------------------------------------------
+// Specialised hot kernel: rows of at most 128 floats (one float4 per lane), T = 1 + K <= 8 target rows per context
+// known at compile time (lane t < T owns target t: 0 = context, 1.. = negatives), contexts processed in groups of
+// four that share one Philox call.  All T row gathers of a context are issued back to back, the T dots are reduced
+// with one transposed butterfly, sigmoid / clamp / log run once per context in the owner lanes.
+// Measured on S3 (B200): explicit L2 prefetching of upcoming rows (prefetch.global.L2 / cp.async.bulk.prefetch.L2, one
+// context or one group ahead) LOWERS throughput by 20-25 % -- the prefetched lines thrash the L2 that the scatter's
+// dirty lines and the context-row reuse live in -- so the kernel relies on occupancy (24 warps/SM x T rows in flight).
+// The prefetch path is kept behind a developer flag (flags bit 0x200) for re-measurement on other shapes.
+// ------------------------------------------------------------------------------------------------------------------
+template <int MODE, int T, bool EXACT>
+__global__ void __launch_bounds__(SGNS_THREADS, 2)
+sgns_ctx_kernel(const SgnsArgs a) {
+    constexpr int K = T - 1;
+    constexpr int P = (T <= 1) ? 1 : (T <= 2) ? 2 : (T <= 4) ? 4 : 8;                 // dots padded to a power of two
+    constexpr int SHIFT = (P == 8) ? 2 : (P == 4) ? 3 : (P == 2) ? 4 : 5;             // lanes per owner group = 1 << SHIFT
+    const int lane = threadIdx.x & 31;
+    const int64_t gid = (int64_t)blockIdx.x * (SGNS_THREADS / 32) + (threadIdx.x >> 5);
+    const int64_t n_groups = (int64_t)gridDim.x * (SGNS_THREADS / 32);
+    const int E = EXACT ? 128 : a.emb;
+    const int eoff = lane * 4;
+    const bool ok = EXACT || eoff < E;
+    const int N = a.n_ctx, NG = (a.n_ctx + 3) >> 2;
+    const bool explicit_noise = (MODE != MODE_WALK) && a.noise != nullptr;
+    const int owner_t = lane >> SHIFT;
+    const bool owner_rep = (lane & ((1 << SHIFT) - 1)) == 0;
+
+    float loss_pos = 0.f, loss_neg = 0.f;
+    unsigned cnt_recall = 0, cnt_fp = 0, cnt_pairs = 0;
+
+    int64_t u_begin, u_end, u_step;
+    if constexpr (MODE == MODE_WALK) {
+        const int64_t span = (a.n_units + n_groups - 1) / n_groups;
+        u_begin = gid * span; u_end = min(a.n_units, u_begin + span); u_step = 1;
+    } else {
+        u_begin = gid; u_end = a.n_units; u_step = n_groups;
+    }
+
+    auto centre_row = [&](int64_t u) -> int64_t {
+        if constexpr (MODE == MODE_WALK) {
+            const int64_t s = u / a.n_cen;
+            return (int64_t)__ldg(a.tokens + s * a.seq_len + a.radius + (int)(u - s * a.n_cen)) + a.row_offset;
+        } else {
+            return __ldg(a.inputs + u);
+        }
+    };
+    // ids of the rows this lane owns in contexts 4g .. 4g+3 of centre u
+    auto resolve_group = [&](int64_t u, int g, int (&ids)[4]) {
+        uint4 wb = make_uint4(0, 0, 0, 0), wc = make_uint4(0, 0, 0, 0);
+        if (K > 0 && !explicit_noise) {
+            const uint64_t cid = (uint64_t)(a.id_base + u);
+            const int k = lane >= 1 ? lane - 1 : 0;
+            wb = neg_words(a.seed, cid, g * 4, k, STREAM_NEG);
+            if (a.alias_prob) wc = neg_words(a.seed, cid, g * 4, k, STREAM_NEG_COIN);
+        }
+        const int32_t *seq = nullptr; int pos = 0;
+        if constexpr (MODE == MODE_WALK) {
+            const int64_t s = u / a.n_cen;
+            pos = a.radius + (int)(u - s * a.n_cen);
+            seq = a.tokens + s * a.seq_len;
+        }
+#pragma unroll
+        for (int j = 0; j < 4; ++j) {
+            const int n = g * 4 + j;
+            int id = 0;
+            if (n < N) {
+                if (lane == 0) {
+                    if constexpr (MODE == MODE_WALK) {
+                        const int off = (n < a.radius) ? (pos - a.radius + n) : (pos + 1 + n - a.radius);
+                        id = __ldg(seq + off) + a.row_offset;
+                    } else {
+                        id = (int)__ldg(a.targets + u * N + n);
+                    }
+                } else if (lane < T) {
+                    if (explicit_noise) id = (int)__ldg(a.noise + (u * N + n) * K + (lane - 1));
+                    else id = (int)draw_row(a.alias_prob, a.alias_idx, (uint32_t)a.vocab, pick_word(wb, j), pick_word(wc, j));
+                }
+            }
+            ids[j] = id;
+        }
+    };
+
+    int cur[4] = {0, 0, 0, 0};
+
+    for (int64_t u = u_begin; u < u_end; u += u_step) {
+        const int64_t crow = centre_row(u);
+        float cen[4] = {0.f, 0.f, 0.f, 0.f}, acc[4] = {0.f, 0.f, 0.f, 0.f};
+        if (ok) load_vec<4>(a.w_in + crow * E + eoff, cen);
+
+        for (int g = 0; g < NG; ++g) {
+            resolve_group(u, g, cur);
+#pragma unroll
+            for (int j = 0; j < 4; ++j) {
+                if (g * 4 + j < N) {
+                    int tid[T];
+                    float row[T][4];
+                    float dot[P];
+#pragma unroll
+                    for (int t = 0; t < T; ++t) tid[t] = __shfl_sync(FULL, cur[j], t);
+#pragma unroll
+                    for (int t = 0; t < T; ++t) {
+                        row[t][0] = row[t][1] = row[t][2] = row[t][3] = 0.f;
+                        if (ok) load_vec<4>(a.w_out + (int64_t)tid[t] * E + eoff, row[t]);
+                    }
+#pragma unroll
+                    for (int t = 0; t < P; ++t) {
+                        float d = 0.f;
+                        if (t < T) {
+#pragma unroll
+                            for (int e = 0; e < 4; ++e) d = fmaf(row[t][e], cen[e], d);
+                        }
+                        dot[t] = d;
+                    }
+                    const float s = transposed_reduce<P>(dot, lane);
+                    float step_mine = 0.f;
+                    if (owner_t < T) {
+                        const bool positive = owner_t == 0;
+                        const float x = positive ? s : -s;                        // loss = -log clamp(sigmoid(x), 1e-6)
+                        const float ex = __expf(-x);
+                        const float sig = __fdividef(1.0f, 1.0f + ex);
+                        const bool live = sig > CLAMP_MIN;
+                        const float gmag = live ? ex * sig : 0.f;                 // |dL/ds| = sigmoid(-x)
+                        step_mine = positive ? a.lr * gmag : -a.lr * gmag;        // -lr * dL/ds
+                        if (owner_rep) {
+                            const float l = -__logf(fmaxf(sig, CLAMP_MIN));
+                            if (positive) { loss_pos += l; cnt_recall += x >= 0.f; cnt_pairs += 1; }
+                            else { loss_neg += l; cnt_fp += x <= 0.f; }
+                        }
+                    }
+#pragma unroll
+                    for (int t = 0; t < T; ++t) {
+                        const float step = __shfl_sync(FULL, step_mine, t << SHIFT);
+                        float d[4];
+#pragma unroll
+                        for (int e = 0; e < 4; ++e) acc[e] = fmaf(step, row[t][e], acc[e]);
+                        if (ok) {
+                            float *rp = a.w_out + (int64_t)tid[t] * E + eoff;
+                            if (a.scatter_store) {
+#pragma unroll
+                                for (int e = 0; e < 4; ++e) d[e] = fmaf(step, cen[e], row[t][e]);
+                                store_vec<4>(rp, d);
+                            } else {
+#pragma unroll
+                                for (int e = 0; e < 4; ++e) d[e] = step * cen[e];
+                                red_vec<4>(rp, d);
+                            }
+                        }
+                    }
+                }
+            }
+        }
+        if (ok) {
+            float *cp = a.w_in + crow * E + eoff;
+            if (a.scatter_store) {
+                float d[4];
+#pragma unroll
+                for (int e = 0; e < 4; ++e) d[e] = cen[e] + acc[e];
+                store_vec<4>(cp, d);
+            } else {
+                red_vec<4>(cp, acc);
+            }
+        }
+    }
+
+    __shared__ double sred[SE_STATS_LEN];
+    if (threadIdx.x < SE_STATS_LEN) sred[threadIdx.x] = 0.0;
+    __syncthreads();
+    if (loss_pos != 0.f || loss_neg != 0.f || cnt_pairs != 0 || cnt_fp != 0 || cnt_recall != 0) {
+        atomicAdd(&sred[0], (double)loss_pos);
+        atomicAdd(&sred[1], (double)loss_neg);
+        atomicAdd(&sred[2], (double)cnt_recall);
+        atomicAdd(&sred[3], (double)cnt_fp);
+        atomicAdd(&sred[4], (double)cnt_pairs);
+        atomicAdd(&sred[5], (double)cnt_pairs * (double)K);
+    }
+    __syncthreads();
+    if (threadIdx.x < SE_STATS_LEN && a.stats && sred[threadIdx.x] != 0.0) atomicAdd(a.stats + threadIdx.x, sred[threadIdx.x]);
+}
+
+template <int MODE, int T, bool EXACT>
+int launch_ctx_one(const SgnsArgs &a, cudaStream_t stream) {
+    auto kern = sgns_ctx_kernel<MODE, T, EXACT>;
+    int occ = 0;
+    if (check_cuda(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, kern, SGNS_THREADS, 0), "occupancy") != SE_OK) return SE_ERR_CUDA;
+    if (occ < 1) occ = 1;
+    const int sms = sm_count();
+    if (sms <= 0) return SE_ERR_CUDA;
+    constexpr int GPB = SGNS_THREADS / 32;
+    int64_t blocks = (a.n_units + GPB - 1) / GPB;
+    const int64_t cap = (int64_t)sms * occ;
+    if (blocks > cap) blocks = cap;
+    if (blocks < 1) blocks = 1;
+    kern<<<(int)blocks, SGNS_THREADS, 0, stream>>>(a);
+    return check_cuda(cudaGetLastError(), "sgns_ctx_kernel launch");
+}
+
+template <int MODE, bool EXACT>
+int launch_ctx_t(const SgnsArgs &a, cudaStream_t stream) {
+    switch (1 + a.n_neg) {
+        case 1: return launch_ctx_one<MODE, 1, EXACT>(a, stream);
+        case 2: return launch_ctx_one<MODE, 2, EXACT>(a, stream);
+        case 3: return launch_ctx_one<MODE, 3, EXACT>(a, stream);
+        case 4: return launch_ctx_one<MODE, 4, EXACT>(a, stream);
+        case 5: return launch_ctx_one<MODE, 5, EXACT>(a, stream);
+        case 6: return launch_ctx_one<MODE, 6, EXACT>(a, stream);
+        case 7: return launch_ctx_one<MODE, 7, EXACT>(a, stream);
+        case 8: return launch_ctx_one<MODE, 8, EXACT>(a, stream);
+        default: return SE_ERR_UNSUPPORTED;
+    }
+}
+
+// Returns SE_ERR_UNSUPPORTED when the shape is not covered (caller tries the next kernel).
+template <int MODE>
+int launch_ctx(const SgnsArgs &a, cudaStream_t stream) {
+    if (a.emb % 4 != 0 || a.emb <= 64 || a.emb > 128 || a.n_neg > 7) return SE_ERR_UNSUPPORTED;
+    if (((uintptr_t)a.w_in % 16) || ((uintptr_t)a.w_out % 16)) return SE_ERR_UNSUPPORTED;
+    return a.emb == 128 ? launch_ctx_t<MODE, true>(a, stream) : launch_ctx_t<MODE, false>(a, stream);
+}
+
 template <int MODE, int R, bool EXACT>
 int launch_fast_one(const SgnsArgs &a, cudaStream_t stream) {
     auto kern = sgns_fast_kernel<MODE, R, EXACT>;
@@ -581,7 +791,9 @@ int launch(const SgnsArgs &a, cudaStream_t stream) {
     if (a.n_units <= 0) return SE_OK;
     if constexpr (MODE != MODE_GRAD) {
         if (!a.force_generic) {
-            const int rc = launch_fast<MODE>(a, stream);
+            int rc = launch_ctx<MODE>(a, stream);
+            if (rc != SE_ERR_UNSUPPORTED) return rc;
+            rc = launch_fast<MODE>(a, stream);
             if (rc != SE_ERR_UNSUPPORTED) return rc;
         }
     }

@@ -55,8 +55,8 @@ w_out = (torch.rand(vocab, args.emb, device=dev) - 0.5) * 0.1
 pairs = args.walks * (args.len - 2 * args.radius) * 2 * args.radius
 bpp = 2 * 4 * args.emb * (1 + args.neg + 1 / (2 * args.radius))
 stats = torch.zeros(6, dtype=torch.float64, device=dev)
-for name, flags in [('red', nat.SCATTER_RED), ('store', nat.SCATTER_STORE)]:
+for name, flags in [('red', nat.SCATTER_RED), ('store', nat.SCATTER_STORE), ('generic red', 2), ('generic store', 3)]:
     ms = timed(lambda i: nat.sgns_update_walks(w_in, w_out, walks, args.radius, args.neg, 1, 0.025, seed=i, flags=flags, stats=stats), args.iters)
-    print(f'sgns {name:6s}: {ms:8.3f} ms  {pairs / ms / 1e6:8.2f} M pairs/s  {pairs * bpp / ms / 1e6:8.1f} GB/s algorithmic '
+    print(f'sgns {name:14s}: {ms:8.3f} ms  {pairs / ms / 1e6:8.2f} M pairs/s  {pairs * bpp / ms / 1e6:8.1f} GB/s algorithmic '
           f'({pairs * bpp / ms / 1e6 / 6450.6 * 100:.1f}% of 6450.6)', flush=True)
 print('tables GB', 2 * vocab * args.emb * 4 / 1e9)
