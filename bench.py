@@ -356,7 +356,7 @@ def run_b200(a, rank, local_rank, world):
         'sgns_kernel_pairs_per_s': world * pairs_per_step / (sgns_ms / 1e3),
         'kernel_ms': {'walk_kernel': walk_ms, 'sgns_kernel': sgns_ms},
         'roofline': {
-            'bound': 'hbm', 'kernel': 'sgns_kernel<MODE_WALK,4,32,1> (se_sgns_update_walks)', 'achieved': achieved, 'peak': peak,
+            'bound': 'hbm', 'kernel': 'sgns_ctx_kernel<MODE_WALK, T=1+K, E=128> (se_sgns_update_walks)', 'achieved': achieved, 'peak': peak,
             'unit': 'GB/s', 'frac': achieved / peak, 'peak_source': peak_src,
             'algorithmic_bytes_per_pair': bpp, 'pairs_per_launch': pairs_per_step,
             'traffic': (traffic or {}).get('dram_bytes_per_launch'), 'traffic_source': (traffic or {}).get('source'),

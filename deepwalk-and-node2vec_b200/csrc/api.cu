@@ -113,7 +113,7 @@ extern "C" int se_host_walk_sgns_step(const int64_t *rowptr, const int32_t *col,
     SE_CUDA(cudaMemcpyAsync(starts_dev, starts_host, sizeof(int32_t) * (size_t)n_walks, cudaMemcpyHostToDevice, st));
     SE_CUDA(cudaMemsetAsync(stats_dev, 0, sizeof(double) * SE_STATS_LEN, st));
     int rc = se_walk(rowptr, col, wcdf, n_nodes, symmetric, starts_dev, n_walks, walk_len, p, q, node2vec, rule, seed,
-                     walk_id_base, 1, walks_dev, nullptr, stream);
+                     walk_id_base, 1, walks_dev, nullptr, SE_WALK_AUTO, stream);
     if (rc != SE_OK) return rc;
     rc = se_sgns_update_walks(w_in, w_out, vocab, emb, walks_dev, n_walks, walk_len, radius, n_neg, row_offset,
                               alias_prob, alias_idx, lr, seed ^ 0x9E3779B97F4A7C15ull,

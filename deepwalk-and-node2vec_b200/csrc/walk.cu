@@ -125,7 +125,7 @@ __device__ __forceinline__ int64_t pick_index(const float *__restrict__ wcdf, in
                                               uint32_t r1) {
     if (!WEIGHTED) {
         return (deg <= 0xffffffffll) ? (int64_t)mulhi32(r0, (uint32_t)deg)
-                                     : (int64_t)(((unsigned __int128)(((uint64_t)r0 << 32) | r1) * (uint64_t)deg) >> 64);
+                                     : (int64_t)__umul64hi(((uint64_t)r0 << 32) | r1, (uint64_t)deg);
     }
     const double total = (double)__ldg(wcdf + base + deg - 1);
     const double target = (double)(((uint64_t)r0 << 32) | r1) * (1.0 / 18446744073709551616.0) * total;
@@ -207,7 +207,7 @@ walk_kernel(const int64_t *__restrict__ rowptr, const int32_t *__restrict__ col,
                             }
                             mult = ((rule == SE_RULE_REFERENCE) ? m : !m) ? inv_q : 1.0f;
                         }
-                        const bool acc = u01(r.z) * wmax < mult || round >= (1u << 20);
+                        const bool acc = u01(r.z) * wmax < mult || (round * 32u + (uint32_t)lane) >= (1u << 25) - 1;
                         const unsigned ballot = __ballot_sync(FULL, acc);
                         if (ballot) {
                             x = __shfl_sync(FULL, cand, __ffs(ballot) - 1);
@@ -230,6 +230,118 @@ walk_kernel(const int64_t *__restrict__ rowptr, const int32_t *__restrict__ col,
             if (first + lane < walk_len) o[first + lane] = keep;
         }
         if (dead && lane == 0 && err_count) atomicAdd(err_count, 1);
+    }
+}
+
+
+// ------------------------------------------------------------------------------------------------------------
+// walk_thread_kernel: one THREAD per walk, for large batches.  Pointer chasing is latency-bound, so the kernel buys
+// parallelism instead: 32 independent dependency chains per warp (2048 walks per SM).  Rejection tries are sequential
+// per walk and consume the SAME Philox counters in the same order as walk_kernel's lane-parallel rounds
+// (try = round * 32 + lane, first accepted try wins), so both kernels produce bit-identical walks and the choice
+// between them is a pure scheduling decision.  The loop is flattened into "one try per iteration" so a lane that
+// accepts early moves on to its next step instead of idling while its neighbours retry.  Membership of the candidate in
+// N(t) uses interpolation search (node ids in an adjacency row are close to uniformly spread), falling back to binary
+// search, which cuts the dependent loads on hub rows (degree 10^3..10^5) from 10-17 to ~4.  Outputs are written as
+// 16-byte vectors (4 steps) when the walk rows are 16-byte aligned.
+// ------------------------------------------------------------------------------------------------------------
+__device__ __forceinline__ bool member_interp(const int32_t *__restrict__ col, int64_t lo, int64_t n, int32_t vfirst,
+                                              int32_t vlast, int32_t key) {
+    if (n <= 0 || key < vfirst || key > vlast) return false;
+    if (key == vfirst || key == vlast) return true;
+    int64_t l = lo, r = lo + n - 1;          // col[l] = vl < key < vr = col[r]
+    int32_t vl = vfirst, vr = vlast;
+#pragma unroll 1
+    for (int it = 0; it < 4 && r - l > 8; ++it) {
+        const float frac = (float)(key - vl) / (float)(vr - vl);
+        int64_t m = l + (int64_t)(frac * (float)(r - l));
+        m = max(l + 1, min(r - 1, m));
+        const int32_t vm = __ldg(col + m);
+        if (vm == key) return true;
+        if (vm < key) { l = m; vl = vm; } else { r = m; vr = vm; }
+    }
+    ++l;                                     // remaining candidates: (l, r) exclusive -> [l, r)
+    while (l < r) {
+        const int64_t m = l + ((r - l) >> 1);
+        const int32_t vm = __ldg(col + m);
+        if (vm == key) return true;
+        if (vm < key) l = m + 1; else r = m;
+    }
+    return false;
+}
+
+template <bool WEIGHTED>
+__global__ void __launch_bounds__(256)
+walk_thread_kernel(const int64_t *__restrict__ rowptr, const int32_t *__restrict__ col, const float *__restrict__ wcdf,
+                   int symmetric, const int32_t *__restrict__ starts, int64_t n_walks, int walk_len, float inv_p,
+                   float inv_q, int node2vec, int rule, uint64_t seed, int64_t walk_id_base, int64_t walk_id_stride,
+                   int32_t *__restrict__ out, int32_t *__restrict__ err_count) {
+    const float wmax = fmaxf(1.0f, fmaxf(inv_p, inv_q));
+    const bool any_bias = node2vec && !(inv_p == 1.0f && inv_q == 1.0f);
+    const bool vec_out = ((walk_len & 3) == 0) && ((reinterpret_cast<uintptr_t>(out) & 15) == 0);
+
+    for (int64_t wk = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; wk < n_walks; wk += (int64_t)gridDim.x * blockDim.x) {
+        const uint64_t walk_id = (uint64_t)(walk_id_base + wk * walk_id_stride);
+        int32_t *o = out + wk * (int64_t)walk_len;
+        int32_t v = __ldg(starts + wk), t = -1;
+        int64_t base = 0, deg = 0, tbase = 0, tdeg = 0;
+        int32_t tfirst = 0, tlast = 0, vfirst = 0, vlast = 0;
+        int32_t pend[4];
+        pend[0] = v;
+        if (!vec_out && walk_len > 0) o[0] = v;
+        bool dead = false, need_row = true;
+        int s = 1;
+        uint32_t attempt = 0;
+        while (s < walk_len) {
+            if (need_row) {
+                base = __ldg(rowptr + v);
+                deg = __ldg(rowptr + v + 1) - base;
+                if (deg > 0 && any_bias && symmetric) {     // ends of N(v): the interpolation anchors of the NEXT step
+                    vfirst = __ldg(col + base);
+                    vlast = __ldg(col + base + deg - 1);
+                }
+                need_row = false;
+                attempt = 0;
+            }
+            int32_t x = v;
+            bool commit = true;
+            if (deg <= 0) {
+                dead = true;                    // the reference raises on an isolated node; stay and count
+            } else {
+                const uint4 r = philox(seed, walk_id, (uint32_t)s, STREAM_WALK | attempt);
+                const int64_t k = pick_index<WEIGHTED>(wcdf, base, deg, r.x, r.y);
+                const int32_t cand = __ldg(col + base + k);
+                x = cand;
+                if (any_bias && t >= 0) {
+                    float mult;
+                    if (cand == t) {
+                        mult = inv_p;
+                    } else {
+                        bool m;
+                        if (symmetric) {
+                            m = member_interp(col, tbase, tdeg, tfirst, tlast, cand);
+                        } else {
+                            const int64_t xb = __ldg(rowptr + cand);
+                            m = member_sorted(col, xb, __ldg(rowptr + cand + 1), t);
+                        }
+                        mult = ((rule == SE_RULE_REFERENCE) ? m : !m) ? inv_q : 1.0f;
+                    }
+                    commit = (u01(r.z) * wmax < mult) || attempt >= (1u << 25) - 1;
+                    ++attempt;
+                }
+            }
+            if (commit) {
+                if (vec_out) {
+                    pend[s & 3] = x;
+                    if ((s & 3) == 3) *reinterpret_cast<int4 *>(o + s - 3) = make_int4(pend[0], pend[1], pend[2], pend[3]);
+                } else {
+                    o[s] = x;
+                }
+                if (deg > 0) { t = v; tbase = base; tdeg = deg; tfirst = vfirst; tlast = vlast; v = x; need_row = true; }
+                ++s;
+            }
+        }
+        if (dead && err_count) atomicAdd(err_count, 1);
     }
 }
 
@@ -275,7 +387,7 @@ extern "C" int se_walk_exact(const int64_t *rowptr, const int32_t *col, const in
 extern "C" int se_walk(const int64_t *rowptr, const int32_t *col, const float *wcdf, int64_t n_nodes, int symmetric,
                        const int32_t *starts, int64_t n_walks, int walk_len, double p, double q, int node2vec,
                        int rule, uint64_t seed, int64_t walk_id_base, int64_t walk_id_stride, int32_t *out,
-                       int32_t *err_count, void *stream) {
+                       int32_t *err_count, int flags, void *stream) {
     SE_REQUIRE(n_nodes > 0 && n_walks >= 0 && walk_len >= 1, "se_walk: bad sizes (walk length must be >= 1)");
     SE_REQUIRE(p > 0 && q > 0, "se_walk: p and q must be positive");
     SE_REQUIRE(rule == SE_RULE_REFERENCE || rule == SE_RULE_PAPER, "se_walk: unknown rule %d", rule);
@@ -283,17 +395,33 @@ extern "C" int se_walk(const int64_t *rowptr, const int32_t *col, const float *w
     SE_REQUIRE(rowptr && col && starts && out, "se_walk: null graph/starts/out pointer");
     const int sms = se::sm_count();
     if (sms <= 0) return SE_ERR_CUDA;
+    SE_REQUIRE(flags == SE_WALK_AUTO || flags == SE_WALK_WARP || flags == SE_WALK_THREAD, "se_walk: unknown flags %d", flags);
+    const float inv_p = (float)(1.0 / p), inv_q = (float)(1.0 / q);
+    cudaStream_t st = (cudaStream_t)stream;
+    // both kernels generate identical walks; one thread per walk needs ~a full machine of walks to pay off
+    const bool per_thread = flags == SE_WALK_THREAD || (flags == SE_WALK_AUTO && n_walks >= (int64_t)sms * 1024);
+    if (per_thread) {
+        int64_t blocks = (n_walks + 255) / 256;
+        const int64_t cap = (int64_t)sms * 8;
+        if (blocks > cap) blocks = cap;
+        if (wcdf)
+            se::walk_thread_kernel<true><<<(int)blocks, 256, 0, st>>>(rowptr, col, wcdf, symmetric, starts, n_walks, walk_len, inv_p,
+                                                                      inv_q, node2vec, rule, seed, walk_id_base, walk_id_stride, out, err_count);
+        else
+            se::walk_thread_kernel<false><<<(int)blocks, 256, 0, st>>>(rowptr, col, wcdf, symmetric, starts, n_walks, walk_len, inv_p,
+                                                                       inv_q, node2vec, rule, seed, walk_id_base, walk_id_stride, out, err_count);
+        return se::check_cuda(cudaGetLastError(), "walk_thread_kernel launch");
+    }
     // persistent grid: 8 resident blocks of 8 warps per SM (64 warps/SM), capped by the work available
     int64_t blocks = (n_walks + se::WALK_WPB - 1) / se::WALK_WPB;
     const int64_t cap = (int64_t)sms * 8;
     if (blocks > cap) blocks = cap;
-    const float inv_p = (float)(1.0 / p), inv_q = (float)(1.0 / q);
     if (wcdf)
-        se::walk_kernel<true><<<(int)blocks, se::WALK_WPB * 32, 0, (cudaStream_t)stream>>>(
+        se::walk_kernel<true><<<(int)blocks, se::WALK_WPB * 32, 0, st>>>(
             rowptr, col, wcdf, symmetric, starts, n_walks, walk_len, inv_p, inv_q, node2vec, rule, seed, walk_id_base,
             walk_id_stride, out, err_count);
     else
-        se::walk_kernel<false><<<(int)blocks, se::WALK_WPB * 32, 0, (cudaStream_t)stream>>>(
+        se::walk_kernel<false><<<(int)blocks, se::WALK_WPB * 32, 0, st>>>(
             rowptr, col, wcdf, symmetric, starts, n_walks, walk_len, inv_p, inv_q, node2vec, rule, seed, walk_id_base,
             walk_id_stride, out, err_count);
     return se::check_cuda(cudaGetLastError(), "walk_kernel launch");

@@ -23,6 +23,7 @@ RULE_PAPER = 1
 SCATTER_RED = 0
 SCATTER_STORE = 1
 STATS_LEN = 6
+WALK_AUTO, WALK_WARP, WALK_THREAD = 0, 1, 2
 
 _lib = None
 _launches = 0    # kernels launched through this module (bench.py reports it as gpu_launches)
@@ -38,7 +39,7 @@ _SIGNATURES = {
     'se_walk_exact': (c_int, [c_p, c_p, c_p, c_p, c_int, c_i64, c_i64, c_p, c_i64, c_int, c_f64, c_f64, c_int, c_int,
                               c_p, c_p, c_i64, c_p, c_p]),
     'se_walk': (c_int, [c_p, c_p, c_p, c_i64, c_int, c_p, c_i64, c_int, c_f64, c_f64, c_int, c_int, c_u64, c_i64, c_i64,
-                        c_p, c_p, c_p]),
+                        c_p, c_p, c_int, c_p]),
     'se_alias_build_host': (c_int, [c_p, c_i64, c_f64, c_p, c_p]),
     'se_sample_negatives': (c_int, [c_p, c_p, c_i64, c_u64, c_i64, c_i64, c_p, c_p]),
     'se_skipgram_scores': (c_int, [c_p, c_p, c_i64, c_int, c_p, c_p, c_i64, c_int, c_int, c_p, c_p]),
@@ -156,7 +157,7 @@ def walk_exact(csr, starts: torch.Tensor, walk_len: int, p: float, q: float, nod
 
 def walk(csr, starts: torch.Tensor, walk_len: int, p: float, q: float, node2vec: bool, rule: int, seed: int,
          walk_id_base: int = 0, walk_id_stride: int = 1, out: Optional[torch.Tensor] = None,
-         err_count: Optional[torch.Tensor] = None) -> torch.Tensor:
+         err_count: Optional[torch.Tensor] = None, kernel: int = WALK_AUTO) -> torch.Tensor:
     """Philox/rejection walks -> int32 [n_walks, walk_len]."""
     global _launches
     lib = load()
@@ -170,7 +171,7 @@ def walk(csr, starts: torch.Tensor, walk_len: int, p: float, q: float, node2vec:
             _ptr(csr.wcdf, torch.float32, 'wcdf'), csr.n_nodes, int(csr.symmetric), _ptr(starts, torch.int32, 'starts'),
             n, int(walk_len), float(p), float(q), int(bool(node2vec)), int(rule), int(seed) & (2 ** 64 - 1),
             int(walk_id_base), int(walk_id_stride), _ptr(out, torch.int32, 'out'),
-            _ptr(err_count, torch.int32, 'err_count'), _stream()))
+            _ptr(err_count, torch.int32, 'err_count'), int(kernel), _stream()))
     _launches += 1
     return out
 

@@ -79,18 +79,22 @@ int se_walk_exact(const int64_t *rowptr, const int32_t *col, const int32_t *col_
                   double p, double q, int node2vec, int rule, const double *uniforms,
                   void *scratch, int64_t scratch_bytes, int32_t *out, void *stream);
 
-/* Fast mode: one warp per walk, counter-based Philox4x32-10 keyed by (seed; walk id, step, try), rejection sampling
- * of the 1/p, 1, 1/q multipliers with binary-search membership tests; neighbour lists up to 128 entries are staged in
- * shared memory.  Same transition distribution as the reference rule (validated by chi-square), not the same draws.
+/* Fast mode: counter-based Philox4x32-10 keyed by (seed; walk id, step, try), rejection sampling of the 1/p, 1, 1/q
+ * multipliers with sorted-row membership tests.  Two kernels generate bit-identical walks: one warp per walk (32 tries
+ * per round in parallel, neighbour lists up to 128 entries staged in shared memory) and one thread per walk
+ * (interpolation search, vector stores) -- see `flags`.  Same transition distribution as the reference rule (validated by chi-square), not the same draws.
  *   col[nnz]: each row ASCENDING;  wcdf[nnz]: per-row inclusive prefix sums of the edge weights (fp32) or NULL,
  *   walk id of out row i = walk_id_base + i * walk_id_stride  (so any sharding reproduces the 1-GPU walks),
  *   symmetric != 0 promises x in N(t) <=> t in N(x) (undirected graph) and enables the staged-list membership test,
  *   err_count (int32[1], may be NULL) counts walks that hit a degree-0 node (the reference raises there; the walk
  *   stays on that node). */
+#define SE_WALK_AUTO 0   /* pick the kernel from the batch size (results are identical either way) */
+#define SE_WALK_WARP 1   /* one warp per walk: lowest latency for small batches */
+#define SE_WALK_THREAD 2 /* one thread per walk: highest throughput for large batches */
 int se_walk(const int64_t *rowptr, const int32_t *col, const float *wcdf, int64_t n_nodes, int symmetric,
             const int32_t *starts, int64_t n_walks, int walk_len, double p, double q, int node2vec, int rule,
             uint64_t seed, int64_t walk_id_base, int64_t walk_id_stride, int32_t *out, int32_t *err_count,
-            void *stream);
+            int flags, void *stream);
 
 /* ------------------------------------------------------------------------------------------------------------
  * Negative sampling.  Replaces generate_noise_batch (word2vec/utils/sampling.py:7-21): the reference draws

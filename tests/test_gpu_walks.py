@@ -240,3 +240,48 @@ def test_philox_walk_lengths_and_dead_ends():
         assert w[1].tolist() == [(i + 1) % 2 for i in range(length)]
         assert w[2].tolist() == [2] * length
         assert int(err.item()) == (1 if length > 1 else 0)
+
+
+@pytest.mark.parametrize('weights', [None, 'int'])
+def test_warp_and_thread_kernels_generate_identical_walks(weights):
+    """One warp per walk (parallel tries, staged lists) and one thread per walk (sequential tries, interpolation search)
+    consume the same Philox counters in the same order: bit-identical output, so kernel selection is only scheduling."""
+    dev = cuda_device()
+    for n, m, length in ((3000, 40000, 80), (500, 900, 13), (401, None, 16)):
+        if m is None:
+            z = np.load(os.path.join(GOLDEN, 'walks_star_hub.npz'))
+            rowptr, col = z['rowptr'], z['col']
+        else:
+            rowptr, col = random_csr(n, m, seed=n)
+        w = None
+        if weights:
+            src = np.repeat(np.arange(len(rowptr) - 1), np.diff(rowptr))
+            lo, hi = np.minimum(src, col).astype(np.int64), np.maximum(src, col).astype(np.int64)
+            w = (1 + (lo * 1000003 + hi * 7919) % 9).astype(np.float64)
+        csr = CSRGraph.from_arrays(rowptr, col, w, True, device=dev)
+        starts = torch.from_numpy(np.random.default_rng(1).integers(0, len(rowptr) - 1, 6000).astype(np.int32)).to(dev)
+        for p, q, node2vec, rule in ((0.5, 2.0, True, 0), (4.0, 0.25, True, 1), (1.0, 1.0, False, 0), (1.0, 1.0, True, 0)):
+            a = nat.walk(csr, starts, length, p, q, node2vec, rule, seed=31, kernel=nat.WALK_WARP)
+            b = nat.walk(csr, starts, length, p, q, node2vec, rule, seed=31, kernel=nat.WALK_THREAD)
+            assert torch.equal(a, b), (n, p, q, node2vec, rule)
+    # asymmetric (directed) CSR: membership is tested in N(candidate)
+    rowptr = np.array([0, 2, 4, 6, 7], dtype=np.int64)
+    col = np.array([1, 2, 2, 3, 0, 3, 0], dtype=np.int32)
+    csr = CSRGraph.from_arrays(rowptr, col, symmetric=False, device=dev)
+    starts = torch.arange(4, dtype=torch.int32, device=dev).repeat(500)
+    a = nat.walk(csr, starts, 20, 0.5, 2.0, True, 0, seed=3, kernel=nat.WALK_WARP)
+    b = nat.walk(csr, starts, 20, 0.5, 2.0, True, 0, seed=3, kernel=nat.WALK_THREAD)
+    assert torch.equal(a, b)
+
+
+def test_thread_kernel_chi_square_on_hub_graph():
+    from scipy.stats import chi2
+    dev = cuda_device()
+    z = np.load(os.path.join(GOLDEN, 'walks_star_hub.npz'))
+    rowptr, col = z['rowptr'], z['col']
+    og = oracle_graph_from_csr(rowptr, col)
+    csr = CSRGraph.from_arrays(rowptr, col, device=dev)
+    starts = torch.arange(401, dtype=torch.int32, device=dev).repeat(40)
+    walks = nat.walk(csr, starts, 12, 0.5, 2.0, True, 0, seed=77, kernel=nat.WALK_THREAD).cpu().numpy()
+    stat, dof = _chi_square_transitions(walks, og, 0.5, 2.0, True)
+    assert dof > 20 and stat < chi2.ppf(1 - 1e-6, dof), (stat, dof)

@@ -44,9 +44,9 @@ def test_argument_validation_without_gpu():
     rc = lib.se_sgns_update_walks(one, one, 10, 4, one, 1, 4, 2, 1, 0, None, None, 0.1, 0, 0, 0, None, None)
     assert rc == -1 and b'Text is too short' in lib.se_last_error()
     # walk length must be >= 1 (random_walk_generator.py:21 assert)
-    rc = lib.se_walk(one, one, None, 5, 1, one, 1, 0, 1.0, 1.0, 0, 0, 0, 0, 1, one, None, None)
+    rc = lib.se_walk(one, one, None, 5, 1, one, 1, 0, 1.0, 1.0, 0, 0, 0, 0, 1, one, None, 0, None)
     assert rc == -1 and b'walk length' in lib.se_last_error()
-    rc = lib.se_walk(one, one, None, 5, 1, one, 1, 5, 0.0, 1.0, 1, 0, 0, 0, 1, one, None, None)
+    rc = lib.se_walk(one, one, None, 5, 1, one, 1, 5, 0.0, 1.0, 1, 0, 0, 0, 1, one, None, 0, None)
     assert rc == -1 and b'positive' in lib.se_last_error()
     rc = lib.se_sgns_grad(None, one, 10, 4, one, one, one, 1, 1, 1, None, None, None, None)
     assert rc == -1

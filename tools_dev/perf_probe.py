@@ -46,8 +46,9 @@ walks = torch.empty((args.walks, args.len), dtype=torch.int32, device=dev)
 steps = args.walks * (args.len - 1)
 for name, kw in [('deepwalk', dict(p=1.0, q=1.0, node2vec=False)), ('node2vec p=.5 q=2', dict(p=0.5, q=2.0, node2vec=True)),
                  ('node2vec p=1 q=.5', dict(p=1.0, q=0.5, node2vec=True))]:
-    ms = timed(lambda i: nat.walk(csr, starts, args.len, kw['p'], kw['q'], kw['node2vec'], 0, seed=i, out=walks), args.iters)
-    print(f'walk {name:20s}: {ms:8.3f} ms  {steps / ms / 1e6:8.2f} M steps/s', flush=True)
+    for kname, kern in (('warp', nat.WALK_WARP), ('thread', nat.WALK_THREAD)):
+        ms = timed(lambda i: nat.walk(csr, starts, args.len, kw['p'], kw['q'], kw['node2vec'], 0, seed=i, out=walks, kernel=kern), args.iters)
+        print(f'walk {name:20s} {kname:6s}: {ms:8.3f} ms  {steps / ms / 1e6:8.3f} G steps/s', flush=True)
 
 vocab = args.nodes + 1
 w_in = (torch.rand(vocab, args.emb, device=dev) - 0.5) * 0.1
