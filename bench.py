@@ -12,9 +12,13 @@ one batch of `--walks-per-step` walks (start nodes follow the reference's schedu
 consecutive walks per node) pushed through the walk kernel and the fused window/negatives/SGNS kernel.
 value = positive (centre, context) pairs per second over the whole step (walk time included), all GPUs.
 
-N > 1: one process per GPU, weak scaling.  Walks shard by walk id against a replicated CSR with no communication;
-each rank applies its SGNS updates to its own replica of the tables and the replicas are averaged with one NCCL
-all-reduce per step inside the timed region.
+N > 1: one process per GPU, weak scaling (every GPU processes `--walks-per-step` walks per step).  Walks shard by walk id
+against a replicated CSR with no communication.  SGNS (`--multi sharded`, default): ONE pair of tables, rows striped over
+the HBM of the N GPUs and mapped into every process (shallow_encoders/word2vec/sharded.py); the same fused kernel gathers
+rows and scatters red.global.add.v4.f32 updates straight into peer HBM over NVLink -- no staging, no separate all-to-all,
+no inter-GPU barrier inside a step.  `--negatives local` (default when sharded) draws the K negatives of a pair among the
+rows the GPU owns; `--negatives global` keeps the reference's uniform draw over the whole table (5/6 of the rows then
+cross NVLink) and is reported beside it.  `--multi replicas`: per-GPU replicas averaged by an NCCL all-reduce each step.
 
 --impl reference: the reference's CPU path (oracle/cpu_port.py: python walks on all host cores + torch CPU
 SkipGram/loss/backward/Adam) on a bounded sample of the same workload; rank 0 only.
@@ -53,6 +57,11 @@ def parse_args():
     ap.add_argument('--lr', type=float, default=0.025)
     ap.add_argument('--scatter', default='red', choices=['red', 'store'])
     ap.add_argument('--seed', type=int, default=0)
+    ap.add_argument('--multi', default='sharded', choices=['sharded', 'replicas'], help='N > 1: how the tables are held')
+    ap.add_argument('--negatives', default='auto', choices=['auto', 'local', 'global'],
+                    help='sharded tables: draw negatives among the rows the GPU owns (auto = local) or over the whole table')
+    ap.add_argument('--tables', default='torch', choices=['torch', 'vmm'], help='N = 1: torch tensor or a 1-shard VMM table')
+    ap.add_argument('--extra-steps', type=int, default=5, help='sharded: steps of the other negative mode timed after the main run')
     ap.add_argument('--no-cpu-baseline', action='store_true')
     ap.add_argument('--cpu-nodes', type=int, default=100_000, help='node count of the CPU sample graph (same mean degree)')
     ap.add_argument('--cpu-walks-per-step', type=int, default=64, help='reference batch_size (walks per step)')
@@ -60,14 +69,27 @@ def parse_args():
     return ap.parse_args()
 
 
+def parallelism(a, n_gpus):
+    if n_gpus == 1:
+        return 'single GPU' + (' (tables in a 1-shard VMM mapping)' if a.tables == 'vmm' else '')
+    if a.multi == 'replicas':
+        return f'dp{n_gpus}: walks sharded by id, table replicas averaged by NCCL all-reduce every step'
+    neg = 'global' if a.negatives == 'global' else 'local'
+    return (f'dp{n_gpus}: walks sharded by id (replicated CSR, no communication); ONE pair of tables row-striped (2 MiB stripes) over '
+            f'{n_gpus} HBMs, fused kernel gathers / red.adds peer rows over NVLink; negatives drawn '
+            + ('among the rows each GPU owns' if neg == 'local' else 'uniformly over the whole table (reference)'))
+
+
 def workload_config(a, n_gpus):
     return {
         'workload': 'S3 synthetic power-law graph: node2vec walks -> windows -> negatives -> SGNS update',
         'nodes': a.nodes, 'edges': a.edges, 'method': 'node2vec', 'p': a.p, 'q': a.q, 'rule': 'reference-code',
         'walk_len': a.walk_len, 'walks_per_node': a.walks_per_node, 'walks_per_step_per_gpu': a.walks_per_step,
-        'emb': a.emb, 'context_radius': a.radius, 'negatives': a.neg, 'negative_sampling': 'uniform (reference)',
+        'emb': a.emb, 'context_radius': a.radius, 'negatives': a.neg,
+        'negative_sampling': ('uniform over the rows owned by the GPU (walks are dealt to GPUs by id)'
+                              if (n_gpus > 1 and a.multi == 'sharded' and a.negatives != 'global') else 'uniform (reference)'),
         'optimizer': 'in-place SGD (Hogwild, red.global.add.v4.f32)' if a.scatter == 'red' else 'in-place SGD (Hogwild, plain stores)',
-        'parallelism': 'single GPU' if n_gpus == 1 else f'dp{n_gpus}: walks sharded by id, table replicas averaged by NCCL all-reduce every step',
+        'parallelism': parallelism(a, n_gpus),
         'l2': 'inputs exceed L2 (tables 2 x %.2f GB, CSR ~%.1f GB); no flush' % ((a.nodes + 1) * a.emb * 4 / 1e9, (2 * a.edges * 4 + a.nodes * 8) / 1e9),
     }
 
@@ -227,15 +249,23 @@ def run_b200(a, rank, local_rank, world):
     # ---- resident state: replicated CSR, tables ----------------------------------------------------------------
     csr = powerlaw_graph_device(a.nodes, a.edges, a.seed, dev)
     vocab = a.nodes + 1                                   # row 0 = '<unk>' (torch_dataset.py:99-110)
-    gen = torch.Generator(device=dev)
-    gen.manual_seed(a.seed)                               # same init on every rank
     bound = (6.0 / (vocab + a.emb)) ** 0.5                # xavier_uniform_ (model.py:26-27)
-    w_in = (torch.rand(vocab, a.emb, device=dev, generator=gen) * 2 - 1) * bound
-    w_out = (torch.rand(vocab, a.emb, device=dev, generator=gen) * 2 - 1) * bound
+    sharded = (world > 1 and a.multi == 'sharded') or (world == 1 and a.tables == 'vmm')
+    local_neg = sharded and world > 1 and a.negatives != 'global'
+    if sharded:
+        from shallow_encoders.word2vec.sharded import ShardedTable, make_exchange
+        ex = make_exchange(rank, world)
+        w_in = ShardedTable(vocab, a.emb, dev, rank, world, ex)
+        w_out = ShardedTable(vocab, a.emb, dev, rank, world, ex)
+    else:
+        w_in = torch.empty((vocab, a.emb), dtype=torch.float32, device=dev)
+        w_out = torch.empty((vocab, a.emb), dtype=torch.float32, device=dev)
+    nat.table_fill_uniform(w_in, bound, a.seed + 101)     # same content on every rank / for every sharding
+    nat.table_fill_uniform(w_out, bound, a.seed + 102)
     flags = nat.SCATTER_RED if a.scatter == 'red' else nat.SCATTER_STORE
 
     # ---- schedule: shuffled node list, walks_per_node consecutive walks per node (graph/datasets.py:45,76) -----
-    total_steps = a.warmup + 2 * a.steps + 2
+    total_steps = a.warmup + 2 * a.steps + 2 + a.extra_steps + 1
     n_walks = a.walks_per_step
     g_cpu = torch.Generator()
     g_cpu.manual_seed(a.seed)
@@ -257,14 +287,14 @@ def run_b200(a, rank, local_rank, world):
     stats_host = torch.zeros(nat.STATS_LEN, dtype=torch.float64).pin_memory()
 
     def sync_tables():
-        if world > 1:
+        if world > 1 and not sharded:
             dist.all_reduce(w_in, op=dist.ReduceOp.AVG)
             dist.all_reduce(w_out, op=dist.ReduceOp.AVG)
 
     ev = lambda: torch.cuda.Event(enable_timing=True)   # noqa: E731
     sgns_events, walk_events = [], []
 
-    def device_step(step, record=False):
+    def device_step(step, record=False, local=local_neg):
         st, base = dev_starts[step]
         if record:
             e0, e1, e2 = ev(), ev(), ev()
@@ -273,7 +303,7 @@ def run_b200(a, rank, local_rank, world):
         if record:
             e1.record()
         nat.sgns_update_walks(w_in, w_out, walks, a.radius, a.neg, 1, a.lr, a.seed + 1, centre_id_base=base * n_cen,
-                              flags=flags, stats=stats)
+                              flags=flags, stats=stats, local_negatives=local)
         if record:
             e2.record()
             walk_events.append((e0, e1))
@@ -283,7 +313,7 @@ def run_b200(a, rank, local_rank, world):
     def host_step(step):
         st, base = pinned[step]
         nat.host_walk_sgns_step(csr, st, a.walk_len, a.p, a.q, True, nat.RULE_REFERENCE, a.seed, base, w_in, w_out, a.radius,
-                                a.neg, 1, a.lr, scratch, stats_host, flags=flags)
+                                a.neg, 1, a.lr, scratch, stats_host, flags=flags, local_negatives=local_neg)
         sync_tables()
 
     def barrier():
@@ -320,8 +350,8 @@ def run_b200(a, rank, local_rank, world):
     pairs_per_step = n_walks * n_cen * 2 * a.radius
     walk_steps_per_step = n_walks * (a.walk_len - 1)
     value = world * pairs_per_step * a.steps / (ms_total / 1e3)
-    sgns_ms = sum(x.elapsed_time(y) for x, y in sgns_events) / len(sgns_events)
-    walk_ms = sum(x.elapsed_time(y) for x, y in walk_events) / len(walk_events)
+    sgns_ms = max_over_ranks(sum(x.elapsed_time(y) for x, y in sgns_events) / len(sgns_events))
+    walk_ms = max_over_ranks(sum(x.elapsed_time(y) for x, y in walk_events) / len(walk_events))
     stat_vals = stats.tolist()
 
     # ---- end-to-end through the host-buffer C-ABI entry (`e2e`) -------------------------------------------------
@@ -339,8 +369,28 @@ def run_b200(a, rank, local_rank, world):
     e2e_ms = max(e2e_ms, max_over_ranks(e2e_wall * 1e3) if world > 1 else e2e_wall * 1e3)   # host copies + sync are on the clock
     e2e_value = world * pairs_per_step * a.steps / (e2e_ms / 1e3)
 
+    # ---- sharded tables: the other negative-sampling mode, a few steps, reported beside the headline -------------
+    other = None
+    if sharded and world > 1 and a.extra_steps > 0:
+        first = a.warmup + 2 * a.steps + 1
+        device_step(first, local=not local_neg)
+        barrier()
+        x0, x1 = ev(), ev()
+        x0.record()
+        for s in range(first + 1, first + 1 + a.extra_steps):
+            device_step(s, local=not local_neg)
+        x1.record()
+        barrier()
+        other_ms = max_over_ranks(x0.elapsed_time(x1))
+        other = {'negatives': 'global (uniform over the whole table, reference)' if local_neg else 'local',
+                 'value': world * pairs_per_step * a.extra_steps / (other_ms / 1e3), 'unit': UNIT, 'steps': a.extra_steps,
+                 'ms_per_step': other_ms / a.extra_steps}
+
     if rank != 0:
         if world > 1:
+            barrier()
+            if sharded:
+                w_in.close(); w_out.close(); ex.close()
             dist.destroy_process_group()
         return
 
@@ -369,7 +419,14 @@ def run_b200(a, rank, local_rank, world):
         'graph': {'n_nodes': csr.n_nodes, 'nnz': csr.nnz, 'max_degree': csr.max_degree},
         'library': nat.version(),
     }
+    if other is not None:
+        line['sharded_other_negative_mode'] = other
+    if sharded:
+        line['tables'] = {'kind': 'vmm-striped', 'stripe_bytes': w_in.stripe_bytes, 'stripes_per_table': w_in.n_stripes,
+                          'bytes_per_gpu': 2 * w_in.n_stripes * w_in.stripe_bytes // world}
     if world == 1 and not a.no_cpu_baseline:
+        if sharded:
+            w_in.close(); w_out.close()
         del w_in, w_out, csr
         torch.cuda.empty_cache()
         try:
@@ -378,6 +435,9 @@ def run_b200(a, rank, local_rank, world):
             line['cpu_baseline'] = {'value': None, 'unit': UNIT, 'cores': os.cpu_count(), 'kind': 'port', 'sample': f'failed: {e!r}'}
     print(json.dumps(line), flush=True)
     if world > 1:
+        barrier()
+        if sharded:
+            w_in.close(); w_out.close(); ex.close()
         dist.destroy_process_group()
 
 

@@ -101,13 +101,13 @@ extern "C" int se_sample_negatives(const float *prob, const int32_t *alias, int6
     return se::check_cuda(cudaGetLastError(), "sample_negatives_kernel launch");
 }
 
-extern "C" int se_host_walk_sgns_step(const int64_t *rowptr, const int32_t *col, const float *wcdf, int64_t n_nodes,
-                                      int symmetric, const int32_t *starts_host, int64_t n_walks, int walk_len,
-                                      double p, double q, int node2vec, int rule, uint64_t seed, int64_t walk_id_base,
-                                      float *w_in, float *w_out, int64_t vocab, int emb, int radius, int n_neg,
-                                      int row_offset, const float *alias_prob, const int32_t *alias_idx, float lr,
-                                      int flags, int32_t *starts_dev, int32_t *walks_dev, double *stats_dev,
-                                      int32_t *walks_host, double *stats_host, void *stream) {
+extern "C" int se_host_walk_sgns_step_sharded(const int64_t *rowptr, const int32_t *col, const float *wcdf, int64_t n_nodes,
+                                              int symmetric, const int32_t *starts_host, int64_t n_walks, int walk_len,
+                                              double p, double q, int node2vec, int rule, uint64_t seed, int64_t walk_id_base,
+                                              float *w_in, float *w_out, int64_t vocab, int emb, int radius, int n_neg,
+                                              int row_offset, const float *alias_prob, const int32_t *alias_idx, float lr,
+                                              int flags, const se_shard_spec *spec, int32_t *starts_dev, int32_t *walks_dev,
+                                              double *stats_dev, int32_t *walks_host, double *stats_host, void *stream) {
     SE_REQUIRE(starts_host && starts_dev && walks_dev && stats_dev && stats_host, "se_host_walk_sgns_step: null buffer");
     cudaStream_t st = (cudaStream_t)stream;
     SE_CUDA(cudaMemcpyAsync(starts_dev, starts_host, sizeof(int32_t) * (size_t)n_walks, cudaMemcpyHostToDevice, st));
@@ -115,9 +115,9 @@ extern "C" int se_host_walk_sgns_step(const int64_t *rowptr, const int32_t *col,
     int rc = se_walk(rowptr, col, wcdf, n_nodes, symmetric, starts_dev, n_walks, walk_len, p, q, node2vec, rule, seed,
                      walk_id_base, 1, walks_dev, nullptr, SE_WALK_AUTO, stream);
     if (rc != SE_OK) return rc;
-    rc = se_sgns_update_walks(w_in, w_out, vocab, emb, walks_dev, n_walks, walk_len, radius, n_neg, row_offset,
-                              alias_prob, alias_idx, lr, seed ^ 0x9E3779B97F4A7C15ull,
-                              walk_id_base * (int64_t)(walk_len - 2 * radius), flags, stats_dev, stream);
+    rc = se_sgns_update_walks_sharded(w_in, w_out, vocab, emb, walks_dev, n_walks, walk_len, radius, n_neg, row_offset,
+                                      alias_prob, alias_idx, lr, seed ^ 0x9E3779B97F4A7C15ull,
+                                      walk_id_base * (int64_t)(walk_len - 2 * radius), flags, spec, stats_dev, stream);
     if (rc != SE_OK) return rc;
     if (walks_host)
         SE_CUDA(cudaMemcpyAsync(walks_host, walks_dev, sizeof(int32_t) * (size_t)n_walks * (size_t)walk_len,
@@ -125,4 +125,17 @@ extern "C" int se_host_walk_sgns_step(const int64_t *rowptr, const int32_t *col,
     SE_CUDA(cudaMemcpyAsync(stats_host, stats_dev, sizeof(double) * SE_STATS_LEN, cudaMemcpyDeviceToHost, st));
     SE_CUDA(cudaStreamSynchronize(st));
     return SE_OK;
+}
+
+extern "C" int se_host_walk_sgns_step(const int64_t *rowptr, const int32_t *col, const float *wcdf, int64_t n_nodes,
+                                      int symmetric, const int32_t *starts_host, int64_t n_walks, int walk_len,
+                                      double p, double q, int node2vec, int rule, uint64_t seed, int64_t walk_id_base,
+                                      float *w_in, float *w_out, int64_t vocab, int emb, int radius, int n_neg,
+                                      int row_offset, const float *alias_prob, const int32_t *alias_idx, float lr,
+                                      int flags, int32_t *starts_dev, int32_t *walks_dev, double *stats_dev,
+                                      int32_t *walks_host, double *stats_host, void *stream) {
+    return se_host_walk_sgns_step_sharded(rowptr, col, wcdf, n_nodes, symmetric, starts_host, n_walks, walk_len, p, q,
+                                          node2vec, rule, seed, walk_id_base, w_in, w_out, vocab, emb, radius, n_neg,
+                                          row_offset, alias_prob, alias_idx, lr, flags, nullptr, starts_dev, walks_dev,
+                                          stats_dev, walks_host, stats_host, stream);
 }

@@ -37,8 +37,18 @@ template <int VEC> __device__ __forceinline__ void store_vec(float *p, const flo
     else if constexpr (VEC == 2) __stcg(reinterpret_cast<float2 *>(p), make_float2(v[0], v[1]));
     else __stcg(p, v[0]);
 }
-// no-return vector reduction at L2 (sm_90+): one instruction per 16 bytes
-template <int VEC> __device__ __forceinline__ void red_vec(float *p, const float (&v)[VEC]) {
+// no-return vector reduction at L2 (sm_90+): one instruction per 16 bytes.  `sys` selects system scope, required when
+// the row may live in a peer GPU's HBM (sharded tables): the reduction then executes at the owner's L2 over NVLink.
+template <int VEC> __device__ __forceinline__ void red_vec(float *p, const float (&v)[VEC], bool sys = false) {
+    if (sys) {
+        if constexpr (VEC == 4)
+            asm volatile("red.relaxed.sys.global.add.v4.f32 [%0], {%1, %2, %3, %4};" ::"l"(p), "f"(v[0]), "f"(v[1]), "f"(v[2]), "f"(v[3]) : "memory");
+        else if constexpr (VEC == 2)
+            asm volatile("red.relaxed.sys.global.add.v2.f32 [%0], {%1, %2};" ::"l"(p), "f"(v[0]), "f"(v[1]) : "memory");
+        else
+            asm volatile("red.relaxed.sys.global.add.f32 [%0], %1;" ::"l"(p), "f"(v[0]) : "memory");
+        return;
+    }
     if constexpr (VEC == 4)
         asm volatile("red.relaxed.gpu.global.add.v4.f32 [%0], {%1, %2, %3, %4};" ::"l"(p), "f"(v[0]), "f"(v[1]), "f"(v[2]), "f"(v[3]) : "memory");
     else if constexpr (VEC == 2)
@@ -73,7 +83,22 @@ struct SgnsArgs {
     uint64_t seed; int64_t id_base;
     int scatter_store;
     int force_generic;                   // SE_SGNS_GENERIC_KERNEL: skip the fast path (testing / comparison)
+    // sharded tables (se_shard_spec): negatives are drawn over neg_vocab ids; with neg_shift >= 0 those are LOCAL ids of
+    // shard neg_rank (stripes of 1 << neg_shift rows, stripe s owned by rank s % neg_world) and are mapped to table rows
+    uint32_t neg_vocab;
+    int neg_shift, neg_world, neg_rank;
+    int sys_scope;                       // rows may live in peer HBM: system-scope reductions
 };
+
+// in-kernel negative: uniform / alias draw, then (local negatives) local id -> row of the stripe this rank owns
+__device__ __forceinline__ int neg_row(const SgnsArgs &a, uint32_t r0, uint32_t r1) {
+    uint32_t j = (uint32_t)draw_row(a.alias_prob, a.alias_idx, a.neg_vocab, r0, r1);
+    if (a.neg_shift >= 0) {
+        const uint32_t s = j >> a.neg_shift;
+        j = ((s * (uint32_t)a.neg_world + (uint32_t)a.neg_rank) << a.neg_shift) | (j & ((1u << a.neg_shift) - 1u));
+    }
+    return (int)j;
+}
 
 template <bool FAST> __device__ __forceinline__ float sigmoidf_(float x) {
     if constexpr (FAST) return __fdividef(1.0f, 1.0f + __expf(-x));
@@ -151,7 +176,7 @@ sgns_kernel(const SgnsArgs a) {
                         const uint64_t cid = (uint64_t)(a.id_base + u);
                         const uint32_t r0 = pick_word(neg_words(a.seed, cid, n, tj - 1, STREAM_NEG), n & 3);
                         const uint32_t r1 = a.alias_prob ? pick_word(neg_words(a.seed, cid, n, tj - 1, STREAM_NEG_COIN), n & 3) : 0u;
-                        my = (int)draw_row(a.alias_prob, a.alias_idx, (uint32_t)a.vocab, r0, r1);
+                        my = neg_row(a, r0, r1);
                     }
                 }
                 int tid[CH];
@@ -223,7 +248,7 @@ sgns_kernel(const SgnsArgs a) {
                                         for (int e = 0; e < VEC; ++e) d[e] += row[c][j][e];
                                         store_vec<VEC>(rp + eoff[j], d);
                                     } else {
-                                        red_vec<VEC>(rp + eoff[j], d);
+                                        red_vec<VEC>(rp + eoff[j], d, a.sys_scope);
                                     }
                                 }
                             }
@@ -246,7 +271,7 @@ sgns_kernel(const SgnsArgs a) {
                     for (int e = 0; e < VEC; ++e) d[e] = cen[j][e] + acc[j][e];
                     store_vec<VEC>(cp, d);
                 } else {
-                    red_vec<VEC>(cp, acc[j]);
+                    red_vec<VEC>(cp, acc[j], a.sys_scope);
                 }
             }
         }
@@ -356,7 +381,7 @@ sgns_fast_kernel(const SgnsArgs a) {
             } else if (explicit_noise) {
                 my = (int)__ldg(a.noise + (u * N + n) * K + (tj - 1));
             } else {
-                my = (int)draw_row(a.alias_prob, a.alias_idx, (uint32_t)a.vocab, pick_word(w_bucket, n & 3), pick_word(w_coin, n & 3));
+                my = neg_row(a, pick_word(w_bucket, n & 3), pick_word(w_coin, n & 3));
             }
         }
         return my;
@@ -463,7 +488,7 @@ sgns_fast_kernel(const SgnsArgs a) {
                                 for (int e = 0; e < VEC; ++e) d[e] += row[c][j][e];
                                 store_vec<VEC>(rp + eoff[j], d);
                             } else {
-                                red_vec<VEC>(rp + eoff[j], d);
+                                red_vec<VEC>(rp + eoff[j], d, a.sys_scope);
                             }
                         }
                     }
@@ -481,7 +506,7 @@ sgns_fast_kernel(const SgnsArgs a) {
                 for (int e = 0; e < VEC; ++e) d[e] = cen[j][e] + acc[j][e];
                 store_vec<VEC>(cp, d);
             } else {
-                red_vec<VEC>(cp, acc[j]);
+                red_vec<VEC>(cp, acc[j], a.sys_scope);
             }
         }
     }
@@ -577,7 +602,7 @@ sgns_ctx_kernel(const SgnsArgs a) {
                     }
                 } else if (lane < T) {
                     if (explicit_noise) id = (int)__ldg(a.noise + (u * N + n) * K + (lane - 1));
-                    else id = (int)draw_row(a.alias_prob, a.alias_idx, (uint32_t)a.vocab, pick_word(wb, j), pick_word(wc, j));
+                    else id = neg_row(a, pick_word(wb, j), pick_word(wc, j));
                 }
             }
             ids[j] = id;
@@ -646,7 +671,7 @@ sgns_ctx_kernel(const SgnsArgs a) {
                             } else {
 #pragma unroll
                                 for (int e = 0; e < 4; ++e) d[e] = step * cen[e];
-                                red_vec<4>(rp, d);
+                                red_vec<4>(rp, d, a.sys_scope);
                             }
                         }
                     }
@@ -661,7 +686,7 @@ sgns_ctx_kernel(const SgnsArgs a) {
                 for (int e = 0; e < 4; ++e) d[e] = cen[e] + acc[e];
                 store_vec<4>(cp, d);
             } else {
-                red_vec<4>(cp, acc);
+                red_vec<4>(cp, acc, a.sys_scope);
             }
         }
     }
@@ -930,6 +955,7 @@ extern "C" int se_sgns_grad(const float *w_in, const float *w_out, int64_t vocab
     a.inputs = inputs; a.targets = targets; a.noise = noise;
     a.stats = stats; a.n_units = batch; a.vocab = vocab; a.emb = emb; a.n_ctx = n_ctx; a.n_neg = n_neg;
     a.grad_scale = batch > 0 ? 1.0f / (float)(batch * n_ctx) : 0.f;
+    a.neg_vocab = (uint32_t)vocab; a.neg_shift = -1; a.neg_world = 1;
     return se::launch<se::MODE_GRAD>(a, (cudaStream_t)stream);
 }
 
@@ -950,13 +976,59 @@ extern "C" int se_sgns_step(float *w_in, float *w_out, int64_t vocab, int emb, c
     a.stats = stats; a.n_units = batch; a.vocab = vocab; a.emb = emb; a.n_ctx = n_ctx; a.n_neg = n_neg;
     a.lr = lr; a.seed = seed; a.id_base = pair_id_base; a.scatter_store = (flags & SE_SGNS_SCATTER_STORE) != 0;
     a.force_generic = (flags & SE_SGNS_GENERIC_KERNEL) != 0;
+    a.neg_vocab = (uint32_t)vocab; a.neg_shift = -1; a.neg_world = 1;
     return se::launch<se::MODE_STEP>(a, (cudaStream_t)stream);
 }
 
-extern "C" int se_sgns_update_walks(float *w_in, float *w_out, int64_t vocab, int emb, const int32_t *tokens,
-                                    int64_t n_seq, int seq_len, int radius, int n_neg, int row_offset,
-                                    const float *alias_prob, const int32_t *alias_idx, float lr, uint64_t seed,
-                                    int64_t centre_id_base, int flags, double *stats, void *stream) {
+// rows of [0, vocab) owned by spec->rank: stripes s with s % world == rank
+static int64_t shard_local_rows(int64_t vocab, const se_shard_spec *spec) {
+    const int64_t sr = spec->stripe_rows;
+    const int64_t n_stripes = (vocab + sr - 1) / sr;
+    if (spec->rank >= n_stripes) return 0;
+    const int64_t mine = (n_stripes - 1 - spec->rank) / spec->world + 1;      // stripes rank, rank + world, ...
+    const int64_t last = spec->rank + (mine - 1) * spec->world;               // the last one may be partial
+    return (mine - 1) * sr + ((last == n_stripes - 1) ? vocab - last * sr : sr);
+}
+
+extern "C" int se_shard_local_rows(int64_t vocab, const se_shard_spec *spec, int64_t *n_rows) {
+    SE_REQUIRE(spec && n_rows && vocab >= 1, "se_shard_local_rows: bad arguments");
+    SE_REQUIRE(spec->world >= 1 && spec->rank >= 0 && spec->rank < spec->world && spec->stripe_rows >= 1,
+               "se_shard_local_rows: bad shard spec (world %d rank %d stripe_rows %lld)", spec->world, spec->rank,
+               (long long)spec->stripe_rows);
+    *n_rows = shard_local_rows(vocab, spec);
+    return SE_OK;
+}
+
+// Fills the negative-sampler / scope fields of the kernel arguments from a shard spec (NULL = one unsharded table).
+static int apply_shard_spec(const char *fn, se::SgnsArgs &a, const se_shard_spec *spec) {
+    a.neg_vocab = (uint32_t)a.vocab; a.neg_shift = -1; a.neg_world = 1; a.neg_rank = 0; a.sys_scope = 0;
+    if (!spec) return SE_OK;
+    if (spec->world < 1 || spec->rank < 0 || spec->rank >= spec->world || spec->stripe_rows < 1) {
+        se::set_error("%s: bad shard spec (world %d rank %d stripe_rows %lld)", fn, spec->world, spec->rank, (long long)spec->stripe_rows);
+        return SE_ERR_INVALID_ARG;
+    }
+    a.sys_scope = spec->world > 1;
+    if (spec->local_negatives && spec->world > 1) {
+        const int64_t sr = spec->stripe_rows;
+        if (sr & (sr - 1)) {
+            se::set_error("%s: local negatives need a power-of-two stripe_rows (got %lld): choose emb and stripe_bytes so that "
+                          "stripe_bytes / (4 * emb) is a power of two", fn, (long long)sr);
+            return SE_ERR_UNSUPPORTED;
+        }
+        int shift = 0;
+        while ((1ll << shift) < sr) ++shift;
+        const int64_t local = shard_local_rows(a.vocab, spec);
+        if (local < 1) { se::set_error("%s: rank %d owns no rows", fn, spec->rank); return SE_ERR_INVALID_ARG; }
+        a.neg_vocab = (uint32_t)local; a.neg_shift = shift; a.neg_world = spec->world; a.neg_rank = spec->rank;
+    }
+    return SE_OK;
+}
+
+extern "C" int se_sgns_update_walks_sharded(float *w_in, float *w_out, int64_t vocab, int emb, const int32_t *tokens,
+                                            int64_t n_seq, int seq_len, int radius, int n_neg, int row_offset,
+                                            const float *alias_prob, const int32_t *alias_idx, float lr, uint64_t seed,
+                                            int64_t centre_id_base, int flags, const se_shard_spec *spec, double *stats,
+                                            void *stream) {
     int rc = se::common_checks("se_sgns_update_walks", w_in, w_out, vocab, emb, n_neg);
     if (rc != SE_OK) return rc;
     SE_REQUIRE(n_seq >= 0 && (tokens || n_seq == 0), "se_sgns_update_walks: null tokens");
@@ -972,7 +1044,19 @@ extern "C" int se_sgns_update_walks(float *w_in, float *w_out, int64_t vocab, in
     a.n_units = n_seq * a.n_cen;
     a.lr = lr; a.seed = seed; a.id_base = centre_id_base; a.scatter_store = (flags & SE_SGNS_SCATTER_STORE) != 0;
     a.force_generic = (flags & SE_SGNS_GENERIC_KERNEL) != 0;
+    rc = apply_shard_spec("se_sgns_update_walks_sharded", a, spec);
+    if (rc != SE_OK) return rc;
+    SE_REQUIRE(!(a.sys_scope && a.scatter_store), "se_sgns_update_walks_sharded: plain-store scatter is not supported on "
+               "sharded tables (updates of other GPUs would be lost); use SE_SGNS_SCATTER_RED");
     return se::launch<se::MODE_WALK>(a, (cudaStream_t)stream);
+}
+
+extern "C" int se_sgns_update_walks(float *w_in, float *w_out, int64_t vocab, int emb, const int32_t *tokens,
+                                    int64_t n_seq, int seq_len, int radius, int n_neg, int row_offset,
+                                    const float *alias_prob, const int32_t *alias_idx, float lr, uint64_t seed,
+                                    int64_t centre_id_base, int flags, double *stats, void *stream) {
+    return se_sgns_update_walks_sharded(w_in, w_out, vocab, emb, tokens, n_seq, seq_len, radius, n_neg, row_offset,
+                                        alias_prob, alias_idx, lr, seed, centre_id_base, flags, nullptr, stats, stream);
 }
 
 extern "C" int se_skipgram_scores_backward(const float *w_in, const float *w_out, int64_t vocab, int emb,

@@ -53,7 +53,30 @@ _SIGNATURES = {
     'se_host_walk_sgns_step': (c_int, [c_p, c_p, c_p, c_i64, c_int, c_p, c_i64, c_int, c_f64, c_f64, c_int, c_int, c_u64,
                                        c_i64, c_p, c_p, c_i64, c_int, c_int, c_int, c_int, c_p, c_p, c_f32, c_int,
                                        c_p, c_p, c_p, c_p, c_p, c_p]),
+    'se_shard_granularity': (c_int, [c_p]),
+    'se_shard_reserve': (c_int, [c_i64, c_p]),
+    'se_shard_unreserve': (c_int, [c_u64, c_i64]),
+    'se_shard_create': (c_int, [c_i64, c_p]),
+    'se_shard_release': (c_int, [c_u64]),
+    'se_shard_export_fd': (c_int, [c_u64, c_p]),
+    'se_shard_import_fd': (c_int, [c_int, c_p]),
+    'se_shard_map': (c_int, [c_u64, c_i64, c_u64]),
+    'se_shard_unmap': (c_int, [c_u64, c_i64]),
+    'se_shard_local_rows': (c_int, [c_i64, c_p, c_p]),
+    'se_sgns_update_walks_sharded': (c_int, [c_p, c_p, c_i64, c_int, c_p, c_i64, c_int, c_int, c_int, c_int, c_p, c_p,
+                                             c_f32, c_u64, c_i64, c_int, c_p, c_p, c_p]),
+    'se_host_walk_sgns_step_sharded': (c_int, [c_p, c_p, c_p, c_i64, c_int, c_p, c_i64, c_int, c_f64, c_f64, c_int, c_int,
+                                               c_u64, c_i64, c_p, c_p, c_i64, c_int, c_int, c_int, c_int, c_p, c_p, c_f32,
+                                               c_int, c_p, c_p, c_p, c_p, c_p, c_p, c_p]),
+    'se_table_fill_uniform': (c_int, [c_p, c_i64, c_f32, c_u64, c_i64, c_int, c_int, c_p]),
+    'se_table_gather_rows': (c_int, [c_p, c_int, c_p, c_i64, c_p, c_p]),
+    'se_table_scatter_rows': (c_int, [c_p, c_int, c_p, c_i64, c_p, c_p]),
 }
+
+
+class ShardSpec(ctypes.Structure):
+    """struct se_shard_spec (include/se_b200.h)."""
+    _fields_ = [('world', c_i32), ('rank', c_i32), ('stripe_rows', c_i64), ('local_negatives', c_i32), ('reserved', c_i32)]
 
 
 def header_symbols():
@@ -120,6 +143,24 @@ def _on(t: torch.Tensor):
 
 def _stream() -> int:
     return torch.cuda.current_stream().cuda_stream
+
+
+def _table(t, name='table'):
+    """(device pointer, vocab, emb, shard spec or None, device guard) of a torch table or a sharded table
+    (shallow_encoders/word2vec/sharded.py: anything with `.ptr`, `.vocab`, `.emb`, `.spec()`, `.device`)."""
+    if isinstance(t, torch.Tensor):
+        return _ptr(t, torch.float32, name), t.shape[0], t.shape[1], None, t.device
+    if hasattr(t, 'ptr') and hasattr(t, 'spec'):
+        return int(t.ptr), int(t.vocab), int(t.emb), t.spec(), t.device
+    raise TypeError(f'{name} must be a CUDA float32 tensor or a ShardedTable, got {type(t)}')
+
+
+def _same_sharding(si, so):
+    if (si is None) != (so is None):
+        raise ValueError('w_in and w_out must both be torch tensors or both be ShardedTables')
+    if si is not None and (si.world, si.rank, si.stripe_rows) != (so.world, so.rank, so.stripe_rows):
+        raise ValueError('w_in and w_out must be sharded the same way')
+    return si
 
 
 def version() -> str:
@@ -301,44 +342,101 @@ def sgns_step(w_in: torch.Tensor, w_out: torch.Tensor, inputs: torch.Tensor, tar
     return _stats_dict(stats) if own_stats else None
 
 
-def sgns_update_walks(w_in: torch.Tensor, w_out: torch.Tensor, tokens: torch.Tensor, radius: int, n_neg: int,
+def sgns_update_walks(w_in, w_out, tokens: torch.Tensor, radius: int, n_neg: int,
                       row_offset: int, lr: float, seed: int, centre_id_base: int = 0,
                       alias: Optional[Dict[str, torch.Tensor]] = None, flags: int = SCATTER_RED,
-                      stats: Optional[torch.Tensor] = None) -> Optional[Dict[str, float]]:
-    """The fused hot path on tokens int32 [n_seq, L]: windows + negatives + in-place SGNS update."""
+                      stats: Optional[torch.Tensor] = None, local_negatives: bool = False) -> Optional[Dict[str, float]]:
+    """The fused hot path on tokens int32 [n_seq, L]: windows + negatives + in-place SGNS update.
+    w_in / w_out: CUDA float32 tensors, or ShardedTables striped over several GPUs (then `local_negatives` selects
+    negatives among the rows this GPU owns; `alias`, if given, must be built over those local rows)."""
     global _launches
     n_seq, seq_len = tokens.shape
+    p_in, vocab, emb, s_in, dev = _table(w_in, 'w_in')
+    p_out, vocab_o, emb_o, s_out, _ = _table(w_out, 'w_out')
+    if (vocab, emb) != (vocab_o, emb_o):
+        raise ValueError('w_in and w_out must have the same shape')
+    spec = _same_sharding(s_in, s_out)
+    if spec is not None:
+        spec = ShardSpec(spec.world, spec.rank, spec.stripe_rows, int(bool(local_negatives)), 0)
+    elif local_negatives:
+        raise ValueError('local_negatives needs sharded tables')
     own_stats = stats is None
     if own_stats:
-        stats = torch.zeros(STATS_LEN, dtype=torch.float64, device=w_in.device)
-    with _on(w_in):
-        _check(load().se_sgns_update_walks(
-            _ptr(w_in, torch.float32, 'w_in'), _ptr(w_out, torch.float32, 'w_out'), w_in.shape[0], w_in.shape[1],
+        stats = torch.zeros(STATS_LEN, dtype=torch.float64, device=dev)
+    with torch.cuda.device(dev):
+        _check(load().se_sgns_update_walks_sharded(
+            p_in, p_out, vocab, emb,
             _ptr(tokens, torch.int32, 'tokens'), n_seq, seq_len, int(radius), int(n_neg), int(row_offset),
             _ptr(alias['prob'], torch.float32) if alias else None, _ptr(alias['alias'], torch.int32) if alias else None,
-            float(lr), int(seed) & (2 ** 64 - 1), int(centre_id_base), int(flags), stats.data_ptr(), _stream()))
+            float(lr), int(seed) & (2 ** 64 - 1), int(centre_id_base), int(flags),
+            ctypes.byref(spec) if spec is not None else None, stats.data_ptr(), _stream()))
     _launches += 1
     return _stats_dict(stats) if own_stats else None
 
 
 def host_walk_sgns_step(csr, starts_host: torch.Tensor, walk_len: int, p: float, q: float, node2vec: bool, rule: int,
-                        seed: int, walk_id_base: int, w_in: torch.Tensor, w_out: torch.Tensor, radius: int, n_neg: int,
+                        seed: int, walk_id_base: int, w_in, w_out, radius: int, n_neg: int,
                         row_offset: int, lr: float, scratch: Dict[str, torch.Tensor], stats_host: torch.Tensor,
                         alias: Optional[Dict[str, torch.Tensor]] = None, flags: int = SCATTER_RED,
-                        walks_host: Optional[torch.Tensor] = None) -> None:
+                        walks_host: Optional[torch.Tensor] = None, local_negatives: bool = False) -> None:
     """HOST-buffer pipeline step (H2D starts -> walk -> fused SGNS -> D2H stats [+ walks]); synchronises."""
     global _launches
     assert not starts_host.is_cuda and starts_host.dtype == torch.int32 and starts_host.is_contiguous()
     assert not stats_host.is_cuda and stats_host.dtype == torch.float64 and stats_host.numel() >= STATS_LEN
     n = starts_host.numel()
-    with _on(w_in):
-        _check(load().se_host_walk_sgns_step(
+    p_in, vocab, emb, s_in, dev = _table(w_in, 'w_in')
+    p_out, vocab_o, emb_o, s_out, _ = _table(w_out, 'w_out')
+    if (vocab, emb) != (vocab_o, emb_o):
+        raise ValueError('w_in and w_out must have the same shape')
+    spec = _same_sharding(s_in, s_out)
+    if spec is not None:
+        spec = ShardSpec(spec.world, spec.rank, spec.stripe_rows, int(bool(local_negatives)), 0)
+    with torch.cuda.device(dev):
+        _check(load().se_host_walk_sgns_step_sharded(
             _ptr(csr.rowptr, torch.int64), _ptr(csr.col_sorted, torch.int32), _ptr(csr.wcdf, torch.float32), csr.n_nodes,
             int(csr.symmetric), starts_host.data_ptr(), n, int(walk_len), float(p), float(q), int(bool(node2vec)),
-            int(rule), int(seed) & (2 ** 64 - 1), int(walk_id_base), _ptr(w_in, torch.float32), _ptr(w_out, torch.float32),
-            w_in.shape[0], w_in.shape[1], int(radius), int(n_neg), int(row_offset),
+            int(rule), int(seed) & (2 ** 64 - 1), int(walk_id_base), p_in, p_out,
+            vocab, emb, int(radius), int(n_neg), int(row_offset),
             _ptr(alias['prob'], torch.float32) if alias else None, _ptr(alias['alias'], torch.int32) if alias else None,
-            float(lr), int(flags), _ptr(scratch['starts'], torch.int32), _ptr(scratch['walks'], torch.int32),
+            float(lr), int(flags), ctypes.byref(spec) if spec is not None else None,
+            _ptr(scratch['starts'], torch.int32), _ptr(scratch['walks'], torch.int32),
             _ptr(scratch['stats'], torch.float64), walks_host.data_ptr() if walks_host is not None else None,
             stats_host.data_ptr(), _stream()))
     _launches += 2
+
+
+# ----------------------------------------------------------------------------------------------------------------
+# table utilities (local torch tensors and sharded tables alike)
+# ----------------------------------------------------------------------------------------------------------------
+def table_fill_uniform(table, bound: float, seed: int) -> None:
+    """Xavier-style uniform(-bound, bound) keyed by the global element index (model.py:26-27 semantics, Philox draws);
+    a ShardedTable fills only the stripes its rank owns."""
+    global _launches
+    ptr, vocab, emb, spec, dev = _table(table)
+    with torch.cuda.device(dev):
+        _check(load().se_table_fill_uniform(ptr, vocab * emb, float(bound), int(seed) & (2 ** 64 - 1),
+                                            spec.stripe_rows * emb if spec is not None else 0,
+                                            spec.world if spec is not None else 1, spec.rank if spec is not None else 0, _stream()))
+    _launches += 1
+
+
+def table_gather_rows(table, rows: torch.Tensor, out: Optional[torch.Tensor] = None) -> torch.Tensor:
+    global _launches
+    ptr, vocab, emb, _, dev = _table(table)
+    rows = rows.reshape(-1)
+    if out is None:
+        out = torch.empty((rows.numel(), emb), dtype=torch.float32, device=dev)
+    with torch.cuda.device(dev):
+        _check(load().se_table_gather_rows(ptr, emb, _ptr(rows, torch.int64, 'rows'), rows.numel(), _ptr(out, torch.float32, 'out'), _stream()))
+    _launches += 1
+    return out
+
+
+def table_scatter_rows(table, rows: torch.Tensor, src: torch.Tensor) -> None:
+    global _launches
+    ptr, vocab, emb, _, dev = _table(table)
+    rows = rows.reshape(-1)
+    assert src.shape == (rows.numel(), emb)
+    with torch.cuda.device(dev):
+        _check(load().se_table_scatter_rows(ptr, emb, _ptr(rows, torch.int64, 'rows'), rows.numel(), _ptr(src, torch.float32, 'src'), _stream()))
+    _launches += 1

@@ -1,0 +1,252 @@
+"""
+Embedding tables striped over the HBM of several B200s (one process per GPU) and addressed as ONE flat array.
+
+The reference trains on a single device (`devices: '1'`, configs/sge_sg_cora.yaml:30) with both tables in one
+`nn.Embedding` each (word2vec/model.py:22-23).  Here `W2VBase`'s two tables can instead be `ShardedTable`s: a flat
+fp32 [vocab x emb] virtual range in every process, whose stripes (2 MiB by default) live round-robin on the G GPUs
+and are mapped into every peer over NVLink / NVSwitch (CUDA virtual memory management, csrc/shard.cu).  The fused
+SGNS kernel is handed the flat pointer and runs unchanged: its row gathers and `red.global.add.v4.f32` scatters reach
+the owner GPU's L2 directly, so there is no separate all-to-all of rows and gradients, no staging buffer and no
+barrier between GPUs -- all GPUs do Hogwild SGD on one model.
+
+Host plumbing only (pointers, file descriptors, sockets); every kernel is behind the C ABI (`_native`).
+"""
+import math
+import os
+import socket
+import struct
+from typing import List, Optional
+
+import torch
+
+from shallow_encoders import _native as nat
+
+_FD_BATCH = 64
+
+
+class _Spec:
+    __slots__ = ('world', 'rank', 'stripe_rows')
+
+    def __init__(self, world, rank, stripe_rows):
+        self.world, self.rank, self.stripe_rows = world, rank, stripe_rows
+
+
+def stripe_owner(stripe: int, world: int) -> int:
+    return stripe % world
+
+
+def local_rows(vocab: int, stripe_rows: int, world: int, rank: int) -> int:
+    """Rows of [0, vocab) whose stripe is owned by `rank` (python restatement of se_shard_local_rows)."""
+    n_stripes = -(-vocab // stripe_rows)
+    total = 0
+    for s in range(rank, n_stripes, world):
+        total += min(stripe_rows, vocab - s * stripe_rows)
+    return total
+
+
+def local_to_global(j, stripe_rows: int, world: int, rank: int):
+    """Local row id (0 .. local_rows) of `rank` -> table row: what the kernel does for local negatives."""
+    return ((j // stripe_rows) * world + rank) * stripe_rows + j % stripe_rows
+
+
+class FdExchange:
+    """All-pairs exchange of file descriptors between the ranks of one node over abstract unix sockets (SCM_RIGHTS).
+    `barrier` is any callable that returns once every rank has reached it (torch.distributed.barrier)."""
+
+    def __init__(self, rank: int, world: int, token: str, barrier):
+        self.rank, self.world = rank, world
+        self.peers = {}
+        if world == 1:
+            return
+        name = lambda r: f'\0se_b200_{token}_{r}'   # noqa: E731  (abstract namespace: nothing to unlink)
+        srv = socket.socket(socket.AF_UNIX, socket.SOCK_STREAM)
+        srv.bind(name(rank))
+        srv.listen(world)
+        barrier()
+        for peer in range(rank + 1, world):          # the lower rank connects, the higher accepts
+            s = socket.socket(socket.AF_UNIX, socket.SOCK_STREAM)
+            s.connect(name(peer))
+            s.sendall(struct.pack('i', rank))
+            self.peers[peer] = s
+        for _ in range(rank):
+            s, _addr = srv.accept()
+            (peer,) = struct.unpack('i', self._recv_exact(s, 4))
+            self.peers[peer] = s
+        srv.close()
+        barrier()
+
+    @staticmethod
+    def _recv_exact(s, n):
+        buf = b''
+        while len(buf) < n:
+            chunk = s.recv(n - len(buf))
+            if not chunk:
+                raise RuntimeError('peer closed the fd-exchange socket')
+            buf += chunk
+        return buf
+
+    def send(self, peer: int, fds: List[int]):
+        socket.send_fds(self.peers[peer], [b'F'], list(fds))
+
+    def recv(self, peer: int, n: int) -> List[int]:
+        msg, fds, _flags, _addr = socket.recv_fds(self.peers[peer], 1, n)
+        if msg != b'F' or len(fds) != n:
+            raise RuntimeError(f'fd exchange with rank {peer}: expected {n} descriptors, got {len(fds)}')
+        return list(fds)
+
+    def close(self):
+        for s in self.peers.values():
+            s.close()
+        self.peers = {}
+
+
+def make_exchange(rank: int, world: int, group=None) -> FdExchange:
+    """FdExchange whose socket names are unique to this job (token broadcast from rank 0)."""
+    import torch.distributed as dist
+    if world == 1:
+        return FdExchange(0, 1, '', lambda: None)
+    tok = [f'{os.getpid()}_{int.from_bytes(os.urandom(4), "little")}' if rank == 0 else None]
+    dist.broadcast_object_list(tok, src=0, group=group)
+    return FdExchange(rank, world, tok[0], lambda: dist.barrier(group=group))
+
+
+class ShardedTable:
+    """Flat fp32 [vocab x emb] table striped over `world` GPUs; stripe s lives on rank s % world.
+
+    world == 1, or simulate=True (every stripe is created on the calling GPU but the table still reports
+    (world, rank): single-GPU tests of the sharding arithmetic), needs no exchange."""
+
+    def __init__(self, vocab: int, emb: int, device, rank: int = 0, world: int = 1, exchange: Optional[FdExchange] = None,
+                 stripe_bytes: Optional[int] = None, simulate: bool = False, max_stripes: int = 4096):
+        import ctypes
+        self.vocab, self.emb = int(vocab), int(emb)
+        self.device = torch.device(device)
+        self.rank, self.world = int(rank), int(world)
+        self.shape = (self.vocab, self.emb)
+        self._handles, self._mapped, self.ptr, self._total = [], [], 0, 0
+        lib = nat.load()
+        with torch.cuda.device(self.device):
+            gran = ctypes.c_int64()
+            nat._check(lib.se_shard_granularity(ctypes.byref(gran)))
+            row_bytes = 4 * self.emb
+            nbytes = self.vocab * row_bytes
+            if stripe_bytes is None:
+                stripe_bytes = gran.value * row_bytes // math.gcd(gran.value, row_bytes)     # whole rows per stripe
+                while -(-nbytes // stripe_bytes) > max_stripes:
+                    stripe_bytes *= 2
+            if stripe_bytes % gran.value or stripe_bytes % row_bytes:
+                raise ValueError(f'stripe_bytes {stripe_bytes} must be a multiple of the allocation granularity '
+                                 f'{gran.value} and of the row size {row_bytes}')
+            self.stripe_bytes = int(stripe_bytes)
+            self.stripe_rows = self.stripe_bytes // row_bytes
+            self.n_stripes = -(-nbytes // self.stripe_bytes)
+            self._total = self.n_stripes * self.stripe_bytes
+            va = ctypes.c_uint64()
+            nat._check(lib.se_shard_reserve(self._total, ctypes.byref(va)))
+            self.ptr = va.value
+
+            def create_and_map(s):
+                h = ctypes.c_uint64()
+                nat._check(lib.se_shard_create(self.stripe_bytes, ctypes.byref(h)))
+                self._handles.append(h.value)
+                nat._check(lib.se_shard_map(self.ptr + s * self.stripe_bytes, self.stripe_bytes, h.value))
+                self._mapped.append(s)
+                return h.value
+
+            mine = [s for s in range(self.n_stripes) if simulate or world == 1 or stripe_owner(s, world) == rank]
+            own_handles = [create_and_map(s) for s in mine]
+            if world > 1 and not simulate:
+                if exchange is None:
+                    raise ValueError('a multi-GPU ShardedTable needs an FdExchange (make_exchange)')
+                self._exchange_stripes(lib, exchange, own_handles)
+            torch.cuda.synchronize(self.device)
+
+    # ------------------------------------------------------------------------------------------------------------
+    def _exchange_stripes(self, lib, ex: FdExchange, own_handles: List[int]):
+        import ctypes
+        world, rank = self.world, self.rank
+        per_rank = [list(range(r, self.n_stripes, world)) for r in range(world)]
+        rounds = -(-max(len(v) for v in per_rank) // _FD_BATCH)
+        for k in range(rounds):
+            lo, hi = k * _FD_BATCH, (k + 1) * _FD_BATCH
+            fds = []
+            for h in own_handles[lo:hi]:
+                fd = ctypes.c_int()
+                nat._check(lib.se_shard_export_fd(h, ctypes.byref(fd)))
+                fds.append(fd.value)
+            for peer in range(world):
+                if peer != rank and fds:
+                    ex.send(peer, fds)
+            for peer in range(world):
+                if peer == rank:
+                    continue
+                theirs = per_rank[peer][lo:hi]
+                if not theirs:
+                    continue
+                got = ex.recv(peer, len(theirs))
+                for s, fd in zip(theirs, got):
+                    h = ctypes.c_uint64()
+                    nat._check(lib.se_shard_import_fd(fd, ctypes.byref(h)))
+                    os.close(fd)
+                    self._handles.append(h.value)
+                    nat._check(lib.se_shard_map(self.ptr + s * self.stripe_bytes, self.stripe_bytes, h.value))
+                    self._mapped.append(s)
+            for fd in fds:
+                os.close(fd)
+
+    # ------------------------------------------------------------------------------------------------------------
+    def spec(self) -> _Spec:
+        return _Spec(self.world, self.rank, self.stripe_rows)
+
+    @property
+    def is_cuda(self) -> bool:
+        return True
+
+    def local_rows(self) -> int:
+        return local_rows(self.vocab, self.stripe_rows, self.world, self.rank)
+
+    def owned_rows(self) -> torch.Tensor:
+        """int64 ids of the rows whose stripe this rank owns, ascending (== local id order of the negative sampler)."""
+        j = torch.arange(self.local_rows(), dtype=torch.int64, device=self.device)
+        return local_to_global(j, self.stripe_rows, self.world, self.rank)
+
+    def fill_uniform(self, bound: float, seed: int) -> None:
+        nat.table_fill_uniform(self, bound, seed)
+
+    def gather(self, rows: torch.Tensor) -> torch.Tensor:
+        return nat.table_gather_rows(self, rows.to(self.device, torch.int64))
+
+    def scatter(self, rows: torch.Tensor, src: torch.Tensor) -> None:
+        nat.table_scatter_rows(self, rows.to(self.device, torch.int64), src.to(self.device, torch.float32).contiguous())
+
+    def load_owned(self, full: torch.Tensor) -> None:
+        """Copy this rank's rows out of a full [vocab x emb] tensor (host or device) into the table."""
+        rows = self.owned_rows()
+        self.scatter(rows, full[rows.to(full.device)].to(self.device))
+
+    def to_tensor(self, chunk_rows: int = 1 << 20) -> torch.Tensor:
+        """Dense copy of the WHOLE table on this GPU (reads peer stripes over NVLink)."""
+        out = torch.empty((self.vocab, self.emb), dtype=torch.float32, device=self.device)
+        for lo in range(0, self.vocab, chunk_rows):
+            hi = min(self.vocab, lo + chunk_rows)
+            nat.table_gather_rows(self, torch.arange(lo, hi, dtype=torch.int64, device=self.device), out=out[lo:hi])
+        return out
+
+    def close(self) -> None:
+        if not self.ptr:
+            return
+        lib = nat.load()
+        with torch.cuda.device(self.device):
+            torch.cuda.synchronize(self.device)
+            for s in self._mapped:
+                lib.se_shard_unmap(self.ptr + s * self.stripe_bytes, self.stripe_bytes)
+            for h in self._handles:
+                lib.se_shard_release(h)
+            lib.se_shard_unreserve(self.ptr, self._total)
+        self._mapped, self._handles, self.ptr = [], [], 0
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:   # noqa: BLE001  (interpreter shutdown)
+            pass

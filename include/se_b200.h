@@ -175,6 +175,72 @@ int se_host_walk_sgns_step(const int64_t *rowptr, const int32_t *col, const floa
                            int32_t *starts_dev, int32_t *walks_dev, double *stats_dev, int32_t *walks_host,
                            double *stats_host, void *stream);
 
+/* ------------------------------------------------------------------------------------------------------------
+ * Multi-GPU: sharded embedding tables over NVLink / NVSwitch peer memory.  The reference is single-device
+ * (`devices: '1'` in every YAML, e.g. configs/sge_sg_cora.yaml:30; tools/train.py:67-81 passes no strategy), so
+ * this group has no reference counterpart: it lets the SAME fused SGNS kernel above run on G GPUs against ONE pair
+ * of tables whose rows are striped over the G HBMs -- the row "all-to-all" and the gradient "all-to-all" of a
+ * row-sharded word2vec become the kernel's own 128-bit loads and red.global.add.v4.f32 to peer memory.
+ *
+ * A sharded table is a flat fp32 [vocab x emb] array at one virtual address range per process; stripe s
+ * (stripe_bytes each, a multiple of se_shard_granularity) is a separate physical allocation living on rank
+ * s % world.  Set-up per process (one process per GPU; host plumbing in shallow_encoders/word2vec/sharded.py):
+ *   se_shard_reserve the range; for every stripe: the owner se_shard_create + se_shard_export_fd and sends the fd
+ *   over a unix socket (SCM_RIGHTS), peers se_shard_import_fd; everybody se_shard_map at offset s * stripe_bytes.
+ * Handles and addresses are plain uint64 (CUmemGenericAllocationHandle / CUdeviceptr).
+ * ---------------------------------------------------------------------------------------------------------- */
+int se_shard_granularity(int64_t *bytes);                       /* minimum stripe size on the current device */
+int se_shard_reserve(int64_t bytes, uint64_t *va);
+int se_shard_unreserve(uint64_t va, int64_t bytes);
+int se_shard_create(int64_t bytes, uint64_t *handle);           /* physical stripe in the current device's HBM */
+int se_shard_release(uint64_t handle);
+int se_shard_export_fd(uint64_t handle, int *fd);               /* caller closes fd after sending it */
+int se_shard_import_fd(int fd, uint64_t *handle);               /* caller closes fd afterwards */
+int se_shard_map(uint64_t va, int64_t bytes, uint64_t handle);  /* map + read/write access for the current device */
+int se_shard_unmap(uint64_t va, int64_t bytes);
+
+/* How the tables passed to the *_sharded entry points are striped. */
+typedef struct se_shard_spec {
+    int32_t world;           /* GPUs the tables are striped over (1 = one local table) */
+    int32_t rank;            /* the shard whose stripes live in the calling GPU's HBM */
+    int64_t stripe_rows;     /* rows per stripe: row r lives on rank (r / stripe_rows) % world */
+    int32_t local_negatives; /* != 0: negatives are drawn only among the rows owned by `rank` (uniform, or from an
+                                alias table built over those local rows: alias arrays then have se_shard_local_rows
+                                entries).  Walks are dealt to GPUs by walk id, so over the job every centre still meets
+                                negatives from every shard; it removes K/(K+1+1/N) of the NVLink traffic.  == 0: the
+                                reference's distribution over all of [0, vocab) (word2vec/utils/sampling.py:21) */
+    int32_t reserved;
+} se_shard_spec;
+
+/* number of rows of [0, vocab) owned by spec->rank */
+int se_shard_local_rows(int64_t vocab, const se_shard_spec *spec, int64_t *n_rows);
+
+/* se_sgns_update_walks / se_host_walk_sgns_step on sharded tables (spec NULL = the unsharded calls).  With
+ * spec->world > 1 the scatter uses system-scope reductions (every GPU's concurrent updates of a row land at the
+ * owner's L2); SE_SGNS_SCATTER_STORE is refused. */
+int se_sgns_update_walks_sharded(float *w_in, float *w_out, int64_t vocab, int emb, const int32_t *tokens,
+                                 int64_t n_seq, int seq_len, int radius, int n_neg, int row_offset,
+                                 const float *alias_prob, const int32_t *alias_idx, float lr, uint64_t seed,
+                                 int64_t centre_id_base, int flags, const se_shard_spec *spec, double *stats,
+                                 void *stream);
+int se_host_walk_sgns_step_sharded(const int64_t *rowptr, const int32_t *col, const float *wcdf, int64_t n_nodes,
+                                   int symmetric, const int32_t *starts_host, int64_t n_walks, int walk_len, double p,
+                                   double q, int node2vec, int rule, uint64_t seed, int64_t walk_id_base,
+                                   float *w_in, float *w_out, int64_t vocab, int emb, int radius, int n_neg,
+                                   int row_offset, const float *alias_prob, const int32_t *alias_idx, float lr,
+                                   int flags, const se_shard_spec *spec, int32_t *starts_dev, int32_t *walks_dev,
+                                   double *stats_dev, int32_t *walks_host, double *stats_host, void *stream);
+
+/* Table utilities that work on local and sharded tables alike (W2VBase.__init__ xavier_uniform_, word2vec/model.py:22-27;
+ * the input_embedding / output_embedding accessors, :29-47).
+ *   fill: element i = (2u-1)*bound with u from Philox(seed; i/4) -- independent of the sharding; a rank writes only the
+ *         stripes it owns (stripe_elems = stripe_rows * emb; 0 = write everything)
+ *   gather / scatter: out[i,:] = w[rows[i],:]  /  w[rows[i],:] = src[i,:] */
+int se_table_fill_uniform(float *w, int64_t n_elems, float bound, uint64_t seed, int64_t stripe_elems, int world,
+                          int rank, void *stream);
+int se_table_gather_rows(const float *w, int emb, const int64_t *rows, int64_t n, float *out, void *stream);
+int se_table_scatter_rows(float *w, int emb, const int64_t *rows, int64_t n, const float *src, void *stream);
+
 #ifdef __cplusplus
 }
 #endif

@@ -1,0 +1,184 @@
+"""Sharded tables (csrc/shard.cu, shallow_encoders/word2vec/sharded.py): the fused SGNS kernel on a table mapped through
+CUDA virtual memory management gives the same results as on a torch tensor; local negatives land on rows the rank owns and
+match the numpy Philox restatement; two real GPUs (when the box has them) train ONE pair of tables over NVLink."""
+import os
+import subprocess
+import sys
+
+import numpy as np
+import pytest
+import torch
+
+import philox_ref
+from helpers import cuda_device
+from oracle import sgns_oracle
+from shallow_encoders import _native as nat
+from shallow_encoders.word2vec.sharded import ShardedTable, local_rows, local_to_global
+
+pytestmark = pytest.mark.gpu
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+
+
+def _t(a, dev):
+    return torch.from_numpy(np.ascontiguousarray(a)).to(dev)
+
+
+def test_fill_is_independent_of_sharding_and_rows_round_trip():
+    dev = cuda_device()
+    vocab, emb = 4096 * 3 + 77, 128
+    dense = torch.empty((vocab, emb), dtype=torch.float32, device=dev)
+    nat.table_fill_uniform(dense, 0.25, seed=11)
+    assert float(dense.abs().max()) <= 0.25 and float(dense.abs().max()) > 0.2 and abs(float(dense.mean())) < 1e-3
+    one = ShardedTable(vocab, emb, dev)                                     # world 1: every stripe local
+    one.fill_uniform(0.25, seed=11)
+    assert torch.equal(one.to_tensor(), dense)
+    # simulated 2-way sharding: each "rank" fills only the stripes it owns
+    parts = []
+    for rank in range(2):
+        t = ShardedTable(vocab, emb, dev, rank=rank, world=2, simulate=True)
+        assert t.stripe_rows == 4096 and t.n_stripes == 4
+        t.scatter(torch.arange(vocab, device=dev), torch.zeros((vocab, emb), device=dev))
+        t.fill_uniform(0.25, seed=11)
+        full = t.to_tensor()
+        own = t.owned_rows()
+        assert own.numel() == local_rows(vocab, 4096, 2, rank)
+        assert torch.equal(full[own], dense[own])
+        mask = torch.ones(vocab, dtype=torch.bool, device=dev)
+        mask[own] = False
+        assert float(full[mask].abs().max()) == 0.0                        # rows of the other rank were not written
+        parts.append(own)
+        t.close()
+    assert torch.equal(torch.sort(torch.cat(parts)).values, torch.arange(vocab, device=dev))
+    rows = torch.tensor([0, 5, vocab - 1, 4096, 4095], device=dev)
+    src = torch.randn((5, emb), device=dev)
+    one.scatter(rows, src)
+    assert torch.equal(one.gather(rows), src)
+    one.close()
+
+
+def _collision_free_case(rng, emb, radius, k, n_seq, vocab, offset, neg_fn):
+    length = 2 * radius + 1
+    tokens = rng.permutation(vocab - offset)[:n_seq * length].reshape(n_seq, length).astype(np.int32)
+    inputs, targets = sgns_oracle.windows_from_walks(tokens.astype(np.int64), radius, offset)
+    for seed in range(77, 600):
+        neg = neg_fn(seed)
+        allrows = np.concatenate([targets.ravel(), neg.ravel()])
+        if len(np.unique(allrows)) == allrows.size:
+            return tokens, inputs, targets, neg, seed
+    raise AssertionError('no collision-free seed')
+
+
+@pytest.mark.parametrize('emb,radius,k', [(128, 5, 5), (128, 2, 3), (64, 2, 5), (256, 3, 2)])
+def test_fused_update_on_vmm_table_equals_torch_table(emb, radius, k):
+    dev = cuda_device()
+    rng = np.random.default_rng(21)
+    vocab, offset, n_seq = 50000, 1, 6
+    tokens, inputs, targets, neg, seed = _collision_free_case(
+        rng, emb, radius, k, n_seq, vocab, offset, lambda s: philox_ref.negatives(s, np.arange(n_seq) + 1000, 2 * radius, k, vocab))
+    w_in = (rng.standard_normal((vocab, emb)) * 0.3).astype(np.float32)
+    w_out = (rng.standard_normal((vocab, emb)) * 0.3).astype(np.float32)
+    t_in, t_out = _t(w_in, dev), _t(w_out, dev)
+    st_ref = nat.sgns_update_walks(t_in, t_out, _t(tokens, dev), radius, k, offset, 0.025, seed, centre_id_base=1000)
+    s_in, s_out = ShardedTable(vocab, emb, dev), ShardedTable(vocab, emb, dev)
+    allrows = torch.arange(vocab, device=dev)
+    s_in.scatter(allrows, _t(w_in, dev)); s_out.scatter(allrows, _t(w_out, dev))
+    st = nat.sgns_update_walks(s_in, s_out, _t(tokens, dev), radius, k, offset, 0.025, seed, centre_id_base=1000)
+    assert torch.equal(s_in.to_tensor(), t_in) and torch.equal(s_out.to_tensor(), t_out)    # collision-free: deterministic
+    assert st == st_ref and st['pairs'] == n_seq * 2 * radius
+    s_in.close(); s_out.close()
+
+
+@pytest.mark.parametrize('rank', [0, 1])
+@pytest.mark.parametrize('use_alias', [False, True])
+def test_local_negatives_stay_on_the_owning_shard_and_match_the_oracle(rank, use_alias):
+    """world = 2 simulated on one GPU: negatives are local ids of `rank` mapped to its stripes (restated in numpy), and the
+    update equals mini-batch SGD on exactly those rows."""
+    dev = cuda_device()
+    rng = np.random.default_rng(31 + rank)
+    emb, radius, k, n_seq, offset, world = 128, 2, 4, 8, 1, 2
+    vocab = 4096 * 5 + 100
+    s_in = ShardedTable(vocab, emb, dev, rank=rank, world=world, simulate=True)
+    s_out = ShardedTable(vocab, emb, dev, rank=rank, world=world, simulate=True)
+    sr = s_in.stripe_rows
+    n_local = local_rows(vocab, sr, world, rank)
+    alias = None
+    prob = ali = None
+    if use_alias:
+        counts = rng.integers(1, 50, n_local).astype(np.float64)
+        alias = nat.alias_build(counts, 0.75, dev)
+        prob, ali = alias['prob'].cpu().numpy(), alias['alias'].cpu().numpy()
+
+    def neg_fn(seed):
+        j = philox_ref.negatives(seed, np.arange(n_seq) + 500, 2 * radius, k, n_local, prob, ali)
+        return local_to_global(j, sr, world, rank)
+
+    tokens, inputs, targets, neg, seed = _collision_free_case(rng, emb, radius, k, n_seq, vocab, offset, neg_fn)
+    assert ((neg // sr) % world == rank).all() and (neg < vocab).all()
+    w_in = (rng.standard_normal((vocab, emb)) * 0.3).astype(np.float32)
+    w_out = (rng.standard_normal((vocab, emb)) * 0.3).astype(np.float32)
+    allrows = torch.arange(vocab, device=dev)
+    s_in.scatter(allrows, _t(w_in, dev)); s_out.scatter(allrows, _t(w_out, dev))
+    lr = 0.025
+    st = nat.sgns_update_walks(s_in, s_out, _t(tokens, dev), radius, k, offset, lr, seed, centre_id_base=500, alias=alias,
+                               local_negatives=True)
+    rows = np.unique(np.concatenate([targets.ravel(), neg.ravel(), inputs.ravel()]))
+    remap = {int(r): i for i, r in enumerate(rows)}
+    rm = np.vectorize(remap.get)
+    want_in, want_out, o = sgns_oracle.sgd_step(w_in[rows].astype(np.float64), w_out[rows].astype(np.float64), rm(inputs), rm(targets),
+                                                rm(neg), lr * n_seq * 2 * radius)
+    got_in, got_out = s_in.to_tensor().cpu().numpy(), s_out.to_tensor().cpu().numpy()
+    np.testing.assert_allclose(got_in[rows], want_in, rtol=1e-4, atol=1e-5)
+    np.testing.assert_allclose(got_out[rows], want_out, rtol=1e-4, atol=1e-5)
+    assert abs(st['loss'] - o['loss']) <= 1e-4 * abs(o['loss'])
+    changed = np.nonzero(np.abs(got_out - w_out).max(axis=1) > 0)[0]
+    assert set(changed) <= set(rows.tolist())
+    neg_changed = np.setdiff1d(changed, targets.ravel())
+    assert ((neg_changed // sr) % world == rank).all()                     # only this rank's stripes received negatives
+    # plain stores are refused on sharded tables, and torch tables cannot ask for local negatives
+    with pytest.raises(AssertionError, match='plain-store'):
+        nat.sgns_update_walks(s_in, s_out, _t(tokens, dev), radius, k, offset, lr, seed, flags=nat.SCATTER_STORE)
+    with pytest.raises(ValueError):
+        nat.sgns_update_walks(_t(w_in, dev), _t(w_out, dev), _t(tokens, dev), radius, k, offset, lr, seed, local_negatives=True)
+    s_in.close(); s_out.close()
+
+
+def test_host_step_on_sharded_tables_matches_device_calls():
+    dev = cuda_device()
+    from helpers import random_csr
+    from shallow_encoders.graph.csr import CSRGraph
+    rowptr, col = random_csr(3000, 9000, 5, sort_rows=True)
+    csr = CSRGraph.from_arrays(rowptr, col, device=dev)
+    vocab, emb, radius, k, L = 3001, 128, 2, 3, 12
+    starts = torch.arange(0, 3000, 3, dtype=torch.int32)
+    res = []
+    for table_kind in ('torch', 'vmm'):
+        if table_kind == 'torch':
+            w_in = torch.empty((vocab, emb), device=dev); w_out = torch.empty((vocab, emb), device=dev)
+        else:
+            w_in, w_out = ShardedTable(vocab, emb, dev), ShardedTable(vocab, emb, dev)
+        nat.table_fill_uniform(w_in, 0.1, 1); nat.table_fill_uniform(w_out, 0.1, 2)
+        scratch = {'starts': torch.empty(starts.numel(), dtype=torch.int32, device=dev),
+                   'walks': torch.empty((starts.numel(), L), dtype=torch.int32, device=dev),
+                   'stats': torch.zeros(nat.STATS_LEN, dtype=torch.float64, device=dev)}
+        stats_host = torch.zeros(nat.STATS_LEN, dtype=torch.float64)
+        walks_host = torch.empty((starts.numel(), L), dtype=torch.int32)
+        nat.host_walk_sgns_step(csr, starts, L, 0.5, 2.0, True, nat.RULE_REFERENCE, 9, 0, w_in, w_out, radius, k, 1, 1e-4, scratch,
+                                stats_host, walks_host=walks_host)
+        dense = (w_in if table_kind == 'torch' else w_in.to_tensor()).cpu().numpy()
+        res.append((stats_host.clone().numpy(), walks_host.clone().numpy(), dense))
+    assert np.array_equal(res[0][1], res[1][1])
+    assert res[0][0][4] == starts.numel() * (L - 2 * radius) * 2 * radius
+    np.testing.assert_allclose(res[0][0], res[1][0], rtol=1e-6)
+    np.testing.assert_allclose(res[0][2], res[1][2], rtol=0, atol=1e-6)
+
+
+@pytest.mark.skipif(torch.cuda.device_count() < 2, reason='needs two GPUs on one NVLink/NVSwitch node')
+def test_two_gpus_train_one_pair_of_tables_over_nvlink():
+    world = min(torch.cuda.device_count(), 4)
+    world = 2 if world < 4 else 4
+    env = dict(os.environ, PYTHONPATH=os.pathsep.join([os.path.join(ROOT, 'deepwalk-and-node2vec_b200'), ROOT, os.path.join(ROOT, 'tests')]))
+    cmd = [sys.executable, '-m', 'torch.distributed.run', '--nnodes=1', f'--nproc-per-node={world}', '--master-addr', '127.0.0.1',
+           '--master-port', str(29700 + os.getpid() % 200), os.path.join(ROOT, 'tests', 'mgpu_worker.py')]
+    out = subprocess.run(cmd, env=env, capture_output=True, text=True, timeout=900)
+    assert out.returncode == 0, out.stdout[-3000:] + out.stderr[-3000:]
+    assert out.stdout.count('MGPU_OK') == world, out.stdout[-3000:]

@@ -1,0 +1,118 @@
+"""Host-side logic of the multi-GPU sharding (no GPU): stripe ownership arithmetic against the C ABI, the unix-socket
+file-descriptor exchange between two ranks, and the gloo world-size-2 rendezvous that names the sockets."""
+import ctypes
+import multiprocessing as mp
+import os
+
+import numpy as np
+import pytest
+
+from shallow_encoders import _native as nat
+from shallow_encoders.word2vec import sharded
+
+
+@pytest.mark.parametrize('vocab,stripe_rows,world', [(1, 4, 2), (4, 4, 2), (5, 4, 2), (8, 4, 2), (9, 4, 2), (100, 8, 4), (4096 * 5 + 100, 4096, 2),
+                                                     (10_000_001, 4096, 8), (267_736, 4096, 4), (35, 16, 8), (1000, 7, 3)])
+def test_local_rows_matches_c_abi_and_partitions_the_table(vocab, stripe_rows, world):
+    lib = nat.load()
+    total = 0
+    seen = np.zeros(vocab, dtype=np.int32)
+    for rank in range(world):
+        spec = nat.ShardSpec(world, rank, stripe_rows, 0, 0)
+        n = ctypes.c_int64()
+        assert lib.se_shard_local_rows(vocab, ctypes.byref(spec), ctypes.byref(n)) == 0
+        want = sharded.local_rows(vocab, stripe_rows, world, rank)
+        assert n.value == want
+        rows = sharded.local_to_global(np.arange(want, dtype=np.int64), stripe_rows, world, rank)
+        assert (rows < vocab).all() and (np.diff(rows) > 0).all()
+        assert ((rows // stripe_rows) % world == rank).all()       # every mapped row lives on this rank
+        seen[rows] += 1
+        total += want
+    assert total == vocab and (seen == 1).all()                    # the shards partition [0, vocab)
+
+
+def test_shard_spec_validation():
+    lib = nat.load()
+    n = ctypes.c_int64()
+    for bad in (nat.ShardSpec(0, 0, 4, 0, 0), nat.ShardSpec(2, 2, 4, 0, 0), nat.ShardSpec(2, -1, 4, 0, 0), nat.ShardSpec(2, 0, 0, 0, 0)):
+        assert lib.se_shard_local_rows(10, ctypes.byref(bad), ctypes.byref(n)) == -1
+        assert b'shard spec' in lib.se_last_error()
+
+
+def _fd_worker(rank, world, token, barrier, q):
+    try:
+        ex = sharded.FdExchange(rank, world, token, barrier.wait)
+        # every rank owns pipes; it sends the WRITE ends to every peer in two batches and reads what the peers wrote
+        pipes = [os.pipe() for _ in range(5)]
+        for lo, hi in ((0, 3), (3, 5)):
+            for peer in range(world):
+                if peer != rank:
+                    ex.send(peer, [w for _r, w in pipes[lo:hi]])
+            for peer in range(world):
+                if peer != rank:
+                    for i, fd in enumerate(ex.recv(peer, hi - lo)):
+                        os.write(fd, f'{rank}->{peer}:{lo + i};'.encode())
+                        os.close(fd)
+        barrier.wait()
+        got = []
+        for r, w in pipes:
+            os.close(w)
+            got.append(os.read(r, 4096).decode())
+            os.close(r)
+        ex.close()
+        q.put((rank, got))
+    except Exception as e:   # noqa: BLE001
+        q.put((rank, repr(e)))
+
+
+@pytest.mark.parametrize('world', [2, 3])
+def test_fd_exchange_between_ranks(world):
+    ctx = mp.get_context('fork')
+    barrier, q = ctx.Barrier(world), ctx.Queue()
+    token = f'test{os.getpid()}_{world}'
+    procs = [ctx.Process(target=_fd_worker, args=(r, world, token, barrier, q)) for r in range(world)]
+    for p in procs:
+        p.start()
+    res = dict(q.get(timeout=60) for _ in range(world))
+    for p in procs:
+        p.join(timeout=30)
+    for rank in range(world):
+        assert isinstance(res[rank], list), res[rank]
+        for i, text in enumerate(res[rank]):
+            parts = sorted(x for x in text.split(';') if x)
+            assert parts == sorted(f'{peer}->{rank}:{i}' for peer in range(world) if peer != rank)
+
+
+def _gloo_worker(rank, world, port, q):
+    import torch.distributed as dist
+    os.environ.update(MASTER_ADDR='127.0.0.1', MASTER_PORT=str(port), RANK=str(rank), WORLD_SIZE=str(world))
+    try:
+        dist.init_process_group('gloo', rank=rank, world_size=world)
+        ex = sharded.make_exchange(rank, world)
+        r, w = os.pipe()
+        peer = 1 - rank
+        ex.send(peer, [w])
+        (fd,) = ex.recv(peer, 1)
+        os.write(fd, b'hello from %d' % rank)
+        os.close(fd)
+        dist.barrier()
+        os.close(w)
+        msg = os.read(r, 100)
+        ex.close()
+        dist.destroy_process_group()
+        q.put((rank, msg))
+    except Exception as e:   # noqa: BLE001
+        q.put((rank, repr(e)))
+
+
+def test_make_exchange_over_gloo_world_size_2():
+    ctx = mp.get_context('spawn')
+    q = ctx.Queue()
+    port = 29600 + os.getpid() % 300
+    procs = [ctx.Process(target=_gloo_worker, args=(r, 2, port, q)) for r in range(2)]
+    for p in procs:
+        p.start()
+    res = dict(q.get(timeout=180) for _ in range(2))
+    for p in procs:
+        p.join(timeout=30)
+    assert res[0] == b'hello from 1' and res[1] == b'hello from 0', res
