@@ -168,8 +168,10 @@ def test_host_step_on_sharded_tables_matches_device_calls():
         res.append((stats_host.clone().numpy(), walks_host.clone().numpy(), dense))
     assert np.array_equal(res[0][1], res[1][1])
     assert res[0][0][4] == starts.numel() * (L - 2 * radius) * 2 * radius
-    np.testing.assert_allclose(res[0][0], res[1][0], rtol=1e-6)
-    np.testing.assert_allclose(res[0][2], res[1][2], rtol=0, atol=1e-6)
+    # Hogwild: rows are read while other warps update them, so two runs agree to the size of one update, not bit for bit
+    assert np.array_equal(res[0][0][4:], res[1][0][4:])
+    np.testing.assert_allclose(res[0][0][:4], res[1][0][:4], rtol=5e-3)
+    np.testing.assert_allclose(res[0][2], res[1][2], rtol=0, atol=1e-4)
 
 
 @pytest.mark.skipif(torch.cuda.device_count() < 2, reason='needs two GPUs on one NVLink/NVSwitch node')
