@@ -57,6 +57,8 @@ def parse_args():
     ap.add_argument('--lr', type=float, default=0.025)
     ap.add_argument('--scatter', default='red', choices=['red', 'store'])
     ap.add_argument('--seed', type=int, default=0)
+    ap.add_argument('--kernel', default='window', choices=['window', 'context'],
+                    help='window: context rows resident in shared memory while in the window; context: gathered per pair')
     ap.add_argument('--multi', default='sharded', choices=['sharded', 'replicas'], help='N > 1: how the tables are held')
     ap.add_argument('--negatives', default='auto', choices=['auto', 'local', 'global'],
                     help='sharded tables: draw negatives among the rows the GPU owns (auto = local) or over the whole table')
@@ -263,6 +265,8 @@ def run_b200(a, rank, local_rank, world):
     nat.table_fill_uniform(w_in, bound, a.seed + 101)     # same content on every rank / for every sharding
     nat.table_fill_uniform(w_out, bound, a.seed + 102)
     flags = nat.SCATTER_RED if a.scatter == 'red' else nat.SCATTER_STORE
+    if a.kernel == 'context':
+        flags |= nat.NO_WINDOW
 
     # ---- schedule: shuffled node list, walks_per_node consecutive walks per node (graph/datasets.py:45,76) -----
     total_steps = a.warmup + 2 * a.steps + 2 + a.extra_steps + 1

@@ -22,6 +22,8 @@ RULE_REFERENCE = 0
 RULE_PAPER = 1
 SCATTER_RED = 0
 SCATTER_STORE = 1
+GENERIC_KERNEL = 2
+NO_WINDOW = 4
 STATS_LEN = 6
 WALK_AUTO, WALK_WARP, WALK_THREAD = 0, 1, 2
 

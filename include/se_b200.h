@@ -44,6 +44,9 @@ extern "C" {
 #define SE_SGNS_SCATTER_STORE 1 /* plain read-modify-write stores: classic racy Hogwild */
 #define SE_SGNS_GENERIC_KERNEL 2 /* bit flag: use the generic group-per-centre kernel even where the warp-per-centre
                                     fast kernel applies (same results; for testing and A/B timing) */
+#define SE_SGNS_NO_WINDOW 4 /* bit flag (se_sgns_update_walks*): use the per-context kernel, which gathers and scatters the
+                               positive row of every pair through L2, instead of the window-resident kernel, which keeps
+                               the 2r+1 context rows around the centre in shared memory (for A/B timing) */
 
 /* stats layout written by the SGNS kernels (double[SE_STATS_LEN], ACCUMULATED into, caller zeroes):
  *   [0] sum over pairs of positive loss   -log clamp(sigmoid(s+), 1e-6)          (word2vec/loss.py:15)
