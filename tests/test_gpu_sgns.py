@@ -305,10 +305,10 @@ def test_fast_and_generic_kernels_agree(emb, radius, k):
     assert checked >= 1
 
 
-@pytest.mark.parametrize('emb,radius,k,length,n_seq', [(128, 5, 5, 80, 3), (128, 2, 3, 10, 700), (96, 3, 2, 9, 50), (128, 1, 7, 3, 40), (128, 8, 1, 40, 9)])
+@pytest.mark.parametrize('emb,radius,k,length,n_seq', [(128, 5, 5, 80, 300), (128, 2, 3, 10, 700), (96, 3, 2, 9, 50), (128, 1, 7, 3, 40), (128, 8, 1, 40, 9)])
 def test_window_resident_kernel_equals_sequential_oracle(emb, radius, k, length, n_seq):
     """sgns_win_kernel keeps the context rows of the window in shared memory and scatters each token's accumulated update
-    once, when it leaves the window.  With all tokens and negatives distinct the result must equal a SEQUENTIAL oracle:
+    once, when it leaves the window.  The result must equal a SEQUENTIAL oracle (up to the staleness of concurrent warps):
     centres of a sequence in order, each one a mini-batch (torch_dataset.py:300-309 windows, loss.py:15-19 arithmetic) --
     also across the places where a warp's span of centres ends in the middle of a sequence (n_seq = 700 spreads the
     launch over every warp of the grid with ragged spans)."""
@@ -316,27 +316,27 @@ def test_window_resident_kernel_equals_sequential_oracle(emb, radius, k, length,
     rng = np.random.default_rng(1000 + length)
     offset = 1
     n_cen = length - 2 * radius
-    vocab = 3_000_000 if n_seq * n_cen * 2 * radius * k > 20000 else 600_000
+    vocab = 3_000_000
     tokens = rng.permutation(vocab - offset)[:n_seq * length].reshape(n_seq, length).astype(np.int32)
     inputs, targets = sgns_oracle.windows_from_walks(tokens.astype(np.int64), radius, offset)
-    seed = 0
-    for seed in range(5, 400):
-        neg = philox_ref.negatives(seed, np.arange(n_seq * n_cen) + 31, 2 * radius, k, vocab)
-        if len(np.unique(neg)) == neg.size and not np.isin(neg, tokens.astype(np.int64) + offset).any():
-            break
-    else:
-        # large cases: a few colliding negatives are unavoidable; they only add second-order noise below the tolerance
-        neg = philox_ref.negatives(seed, np.arange(n_seq * n_cen) + 31, 2 * radius, k, vocab)
+    # negatives may collide with each other / with tokens: the sequential oracle handles that exactly, the GPU differs
+    # from it only by the staleness of concurrently running warps (second order in lr, below the tolerance)
+    seed = 5
+    neg = philox_ref.negatives(seed, np.arange(n_seq * n_cen) + 31, 2 * radius, k, vocab)
     rows = np.unique(np.concatenate([targets.ravel(), neg.ravel(), inputs.ravel()]))
     w_in = np.zeros((vocab, emb), dtype=np.float32); w_out = np.zeros((vocab, emb), dtype=np.float32)
     w_in[rows] = (rng.standard_normal((len(rows), emb)) * 0.05).astype(np.float32)
     w_out[rows] = (rng.standard_normal((len(rows), emb)) * 0.05).astype(np.float32)
-    lr = 0.01
+    lr = 0.002     # first-order updates ~5e-5 .. 5e-4, second-order (stale-row) effects ~1e-7
     wi, wo = w_in[rows].astype(np.float64), w_out[rows].astype(np.float64)
     pos_of = np.full(vocab, -1, dtype=np.int64); pos_of[rows] = np.arange(len(rows))
     loss_sum = 0.0
-    for c in range(len(inputs)):
-        wi, wo, o = sgns_oracle.sgd_step(wi, wo, pos_of[inputs[c:c + 1]], pos_of[targets[c:c + 1]], pos_of[neg[c:c + 1]], lr * 2 * radius)
+    for c in range(len(inputs)):          # one centre = one mini-batch on the handful of rows it touches
+        ri, rt, rn = pos_of[inputs[c:c + 1]], pos_of[targets[c:c + 1]], pos_of[neg[c:c + 1]]
+        sub = np.unique(np.concatenate([ri.ravel(), rt.ravel(), rn.ravel()]))
+        loc = {int(x): i for i, x in enumerate(sub)}
+        rm = np.vectorize(loc.get)
+        wi[sub], wo[sub], o = sgns_oracle.sgd_step(wi[sub], wo[sub], rm(ri), rm(rt), rm(rn), lr * 2 * radius)
         loss_sum += o['loss']
     results = {}
     for name, flags in (('window', nat.SCATTER_RED), ('context', nat.SCATTER_RED | nat.NO_WINDOW)):
@@ -345,14 +345,14 @@ def test_window_resident_kernel_equals_sequential_oracle(emb, radius, k, length,
         results[name] = (t_in.cpu().numpy(), t_out.cpu().numpy(), st)
     got_in, got_out, st = results['window']
     # centres of one sequence that fall into different warps run concurrently (stale by one update: second order in lr)
-    np.testing.assert_allclose(got_in[rows], wi, rtol=0, atol=2e-6)
-    np.testing.assert_allclose(got_out[rows], wo, rtol=0, atol=2e-6)
-    assert np.abs(got_out[rows] - w_out[rows]).max() > 2e-4
+    np.testing.assert_allclose(got_in[rows], wi, rtol=0, atol=3e-6)
+    np.testing.assert_allclose(got_out[rows], wo, rtol=0, atol=3e-6)
+    assert np.abs(got_out[rows] - w_out[rows]).max() > 1e-4
     untouched = np.ones(vocab, dtype=bool); untouched[rows] = False
     assert not got_in[untouched].any() and not got_out[untouched].any()
     assert st['pairs'] == len(inputs) * 2 * radius and st['negatives'] == st['pairs'] * k
     assert abs(st['loss'] - loss_sum / len(inputs)) < 1e-4
     # and the per-context kernel lands on the same table (it orders the updates of a sequence differently)
-    np.testing.assert_allclose(results['context'][1][rows], got_out[rows], rtol=0, atol=5e-6)
-    np.testing.assert_allclose(results['context'][0][rows], got_in[rows], rtol=0, atol=5e-6)
+    np.testing.assert_allclose(results['context'][1][rows], got_out[rows], rtol=0, atol=4e-6)
+    np.testing.assert_allclose(results['context'][0][rows], got_in[rows], rtol=0, atol=4e-6)
     assert results['context'][2]['pairs'] == st['pairs']
