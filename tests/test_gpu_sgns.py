@@ -345,14 +345,14 @@ def test_window_resident_kernel_equals_sequential_oracle(emb, radius, k, length,
         results[name] = (t_in.cpu().numpy(), t_out.cpu().numpy(), st)
     got_in, got_out, st = results['window']
     # centres of one sequence that fall into different warps run concurrently (stale by one update: second order in lr)
-    np.testing.assert_allclose(got_in[rows], wi, rtol=0, atol=3e-6)
-    np.testing.assert_allclose(got_out[rows], wo, rtol=0, atol=3e-6)
-    assert np.abs(got_out[rows] - w_out[rows]).max() > 1e-4
+    np.testing.assert_allclose(got_in[rows], wi, rtol=0, atol=1e-5)
+    np.testing.assert_allclose(got_out[rows], wo, rtol=0, atol=1e-5)
+    assert np.abs(got_out[rows] - w_out[rows]).max() > 1e-4 and np.abs(got_in[rows] - w_in[rows]).max() > 2e-4   # updates: 20x the tolerance
     untouched = np.ones(vocab, dtype=bool); untouched[rows] = False
     assert not got_in[untouched].any() and not got_out[untouched].any()
     assert st['pairs'] == len(inputs) * 2 * radius and st['negatives'] == st['pairs'] * k
     assert abs(st['loss'] - loss_sum / len(inputs)) < 1e-4
     # and the per-context kernel lands on the same table (it orders the updates of a sequence differently)
-    np.testing.assert_allclose(results['context'][1][rows], got_out[rows], rtol=0, atol=4e-6)
-    np.testing.assert_allclose(results['context'][0][rows], got_in[rows], rtol=0, atol=4e-6)
+    np.testing.assert_allclose(results['context'][1][rows], got_out[rows], rtol=0, atol=1e-5)
+    np.testing.assert_allclose(results['context'][0][rows], got_in[rows], rtol=0, atol=1e-5)
     assert results['context'][2]['pairs'] == st['pairs']
