@@ -410,10 +410,14 @@ def run_b200(a, rank, local_rank, world):
         'sgns_kernel_pairs_per_s': world * pairs_per_step / (sgns_ms / 1e3),
         'kernel_ms': {'walk_kernel': walk_ms, 'sgns_kernel': sgns_ms},
         'roofline': {
-            'bound': 'hbm', 'kernel': 'sgns_ctx_kernel<MODE_WALK, T=1+K, E=128> (se_sgns_update_walks)', 'achieved': achieved, 'peak': peak,
+            'bound': 'hbm', 'kernel': ('sgns_win_kernel<T=1+K, E=128>' if a.kernel == 'window' else 'sgns_ctx_kernel<MODE_WALK, T=1+K, E=128>')
+                                      + ' (se_sgns_update_walks)', 'achieved': achieved, 'peak': peak,
             'unit': 'GB/s', 'frac': achieved / peak, 'peak_source': peak_src,
             'algorithmic_bytes_per_pair': bpp, 'pairs_per_launch': pairs_per_step,
             'traffic': (traffic or {}).get('dram_bytes_per_launch'), 'traffic_source': (traffic or {}).get('source'),
+            # the window kernel fetches a token's context row once per window instead of once per pair, so its DRAM traffic
+            # is below the per-pair algorithmic figure; the DRAM-side rate is traffic / launch time
+            'dram_traffic_gbs': ((traffic or {}).get('dram_bytes_per_launch') or 0) / (sgns_ms / 1e3) / 1e9 if traffic and a.kernel == 'window' and world == 1 else None,
         },
         'e2e': {'value': e2e_value, 'unit': UNIT, 'h2d_bytes_per_step': n_walks * 4, 'd2h_bytes_per_step': nat.STATS_LEN * 8,
                 'ms_per_step': e2e_ms / a.steps, 'api': 'se_host_walk_sgns_step (pinned host start nodes in, loss statistics out)'},
