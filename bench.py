@@ -59,7 +59,9 @@ def parse_args():
     ap.add_argument('--seed', type=int, default=0)
     ap.add_argument('--kernel', default='window', choices=['window', 'context'],
                     help='window: context rows resident in shared memory while in the window; context: gathered per pair')
-    ap.add_argument('--multi', default='sharded', choices=['sharded', 'replicas'], help='N > 1: how the tables are held')
+    ap.add_argument('--multi', default='sharded', choices=['sharded', 'replicas', 'a2a'],
+                    help='N > 1: sharded = one striped table pair over NVLink peer memory (product); a2a = the NCCL all-to-all baseline; replicas')
+    ap.add_argument('--a2a-micro-walks', type=int, default=8192, help='a2a baseline: walks per exchange micro-batch')
     ap.add_argument('--negatives', default='auto', choices=['auto', 'local', 'global'],
                     help='sharded tables: draw negatives among the rows the GPU owns (auto = local) or over the whole table')
     ap.add_argument('--tables', default='torch', choices=['torch', 'vmm'], help='N = 1: torch tensor or a 1-shard VMM table')
@@ -77,6 +79,10 @@ def parallelism(a, n_gpus):
     if a.multi == 'replicas':
         return f'dp{n_gpus}: walks sharded by id, table replicas averaged by NCCL all-reduce every step'
     neg = 'global' if a.negatives == 'global' else 'local'
+    if a.multi == 'a2a':
+        return (f'dp{n_gpus} NCCL BASELINE: tables row-sharded by row % {n_gpus}; per micro-batch of {a.a2a_micro_walks} walks: unique ids -> '
+                f'all_to_all ids / rows -> se_sgns_grad on compact tables -> all_to_all gradients -> owners apply; negatives '
+                + ('among the rows each GPU owns' if neg == 'local' else 'uniform over the whole table (reference)'))
     return (f'dp{n_gpus}: walks sharded by id (replicated CSR, no communication); ONE pair of tables row-striped (2 MiB stripes) over '
             f'{n_gpus} HBMs, fused kernel gathers / red.adds peer rows over NVLink; negatives drawn '
             + ('among the rows each GPU owns' if neg == 'local' else 'uniformly over the whole table (reference)'))
@@ -89,17 +95,21 @@ def workload_config(a, n_gpus):
         'walk_len': a.walk_len, 'walks_per_node': a.walks_per_node, 'walks_per_step_per_gpu': a.walks_per_step,
         'emb': a.emb, 'context_radius': a.radius, 'negatives': a.neg,
         'negative_sampling': ('uniform over the rows owned by the GPU (walks are dealt to GPUs by id)'
-                              if (n_gpus > 1 and a.multi == 'sharded' and a.negatives != 'global') else 'uniform (reference)'),
+                              if (n_gpus > 1 and a.multi in ('sharded', 'a2a') and a.negatives != 'global') else 'uniform (reference)'),
         'optimizer': 'in-place SGD (Hogwild, red.global.add.v4.f32)' if a.scatter == 'red' else 'in-place SGD (Hogwild, plain stores)',
         'parallelism': parallelism(a, n_gpus),
         'l2': 'inputs exceed L2 (tables 2 x %.2f GB, CSR ~%.1f GB); no flush' % ((a.nodes + 1) * a.emb * 4 / 1e9, (2 * a.edges * 4 + a.nodes * 8) / 1e9),
     }
 
 
-def bytes_per_pair(emb, neg, radius):
-    """Algorithmic HBM bytes per positive pair: fp32 rows read + written once per use, the centre row
-    amortised over its 2r contexts: 2 * 4E * (1 + K + 1/N)."""
-    return 2.0 * 4.0 * emb * (1.0 + neg + 1.0 / (2 * radius))
+def bytes_per_pair(emb, neg, radius, window=False):
+    """Algorithmic HBM bytes per positive pair, fp32 rows read + written once per use.
+    Per-pair kernel: the K negative rows and the context row per pair, the centre row amortised over its 2r
+    contexts: 2 * 4E * (1 + K + 1/N).
+    Window-resident kernel: a token's context row is fetched and scattered once per window pass (= once per centre, i.e.
+    1/N per pair) instead of once per pair: 2 * 4E * (K + 2/N)."""
+    n = 2 * radius
+    return 2.0 * 4.0 * emb * ((neg + 2.0 / n) if window else (1.0 + neg + 1.0 / n))
 
 
 # --------------------------------------------------------------------------------------------------------------
@@ -253,8 +263,14 @@ def run_b200(a, rank, local_rank, world):
     vocab = a.nodes + 1                                   # row 0 = '<unk>' (torch_dataset.py:99-110)
     bound = (6.0 / (vocab + a.emb)) ** 0.5                # xavier_uniform_ (model.py:26-27)
     sharded = (world > 1 and a.multi == 'sharded') or (world == 1 and a.tables == 'vmm')
-    local_neg = sharded and world > 1 and a.negatives != 'global'
-    if sharded:
+    a2a = world > 1 and a.multi == 'a2a'
+    local_neg = (sharded or a2a) and world > 1 and a.negatives != 'global'
+    if a2a:
+        from shallow_encoders.word2vec.row_exchange import RowShardedTables
+        tables = RowShardedTables(vocab, a.emb, rank, world, dev)
+        tables.fill_uniform(bound, a.seed + 101, a.seed + 102)
+        w_in = w_out = None
+    elif sharded:
         from shallow_encoders.word2vec.sharded import ShardedTable, make_exchange
         ex = make_exchange(rank, world)
         w_in = ShardedTable(vocab, a.emb, dev, rank, world, ex)
@@ -262,8 +278,9 @@ def run_b200(a, rank, local_rank, world):
     else:
         w_in = torch.empty((vocab, a.emb), dtype=torch.float32, device=dev)
         w_out = torch.empty((vocab, a.emb), dtype=torch.float32, device=dev)
-    nat.table_fill_uniform(w_in, bound, a.seed + 101)     # same content on every rank / for every sharding
-    nat.table_fill_uniform(w_out, bound, a.seed + 102)
+    if not a2a:
+        nat.table_fill_uniform(w_in, bound, a.seed + 101)     # same content on every rank / for every sharding
+        nat.table_fill_uniform(w_out, bound, a.seed + 102)
     flags = nat.SCATTER_RED if a.scatter == 'red' else nat.SCATTER_STORE
     if a.kernel == 'context':
         flags |= nat.NO_WINDOW
@@ -291,7 +308,7 @@ def run_b200(a, rank, local_rank, world):
     stats_host = torch.zeros(nat.STATS_LEN, dtype=torch.float64).pin_memory()
 
     def sync_tables():
-        if world > 1 and not sharded:
+        if world > 1 and not sharded and not a2a:
             dist.all_reduce(w_in, op=dist.ReduceOp.AVG)
             dist.all_reduce(w_out, op=dist.ReduceOp.AVG)
 
@@ -306,8 +323,12 @@ def run_b200(a, rank, local_rank, world):
         nat.walk(csr, st, a.walk_len, a.p, a.q, True, nat.RULE_REFERENCE, a.seed, walk_id_base=base, out=walks)
         if record:
             e1.record()
-        nat.sgns_update_walks(w_in, w_out, walks, a.radius, a.neg, 1, a.lr, a.seed + 1, centre_id_base=base * n_cen,
-                              flags=flags, stats=stats, local_negatives=local)
+        if a2a:
+            tables.step(walks, a.radius, a.neg, 1, a.lr, a.seed + 1, draw_id_base=base * n_cen * 2 * a.radius * a.neg,
+                        micro_walks=a.a2a_micro_walks, local_negatives=local, stats=stats)
+        else:
+            nat.sgns_update_walks(w_in, w_out, walks, a.radius, a.neg, 1, a.lr, a.seed + 1, centre_id_base=base * n_cen,
+                                  flags=flags, stats=stats, local_negatives=local)
         if record:
             e2.record()
             walk_events.append((e0, e1))
@@ -316,6 +337,15 @@ def run_b200(a, rank, local_rank, world):
 
     def host_step(step):
         st, base = pinned[step]
+        if a2a:     # baseline: the same host-buffer contract assembled from the device calls
+            scratch['starts'].copy_(st, non_blocking=True)
+            stats.zero_()
+            nat.walk(csr, scratch['starts'], a.walk_len, a.p, a.q, True, nat.RULE_REFERENCE, a.seed, walk_id_base=base, out=walks)
+            tables.step(walks, a.radius, a.neg, 1, a.lr, a.seed + 1, draw_id_base=base * n_cen * 2 * a.radius * a.neg,
+                        micro_walks=a.a2a_micro_walks, local_negatives=local_neg, stats=stats)
+            stats_host.copy_(stats)
+            torch.cuda.synchronize()
+            return
         nat.host_walk_sgns_step(csr, st, a.walk_len, a.p, a.q, True, nat.RULE_REFERENCE, a.seed, base, w_in, w_out, a.radius,
                                 a.neg, 1, a.lr, scratch, stats_host, flags=flags, local_negatives=local_neg)
         sync_tables()
@@ -375,7 +405,7 @@ def run_b200(a, rank, local_rank, world):
 
     # ---- sharded tables: the other negative-sampling mode, a few steps, reported beside the headline -------------
     other = None
-    if sharded and world > 1 and a.extra_steps > 0:
+    if (sharded or a2a) and world > 1 and a.extra_steps > 0:
         first = a.warmup + 2 * a.steps + 1
         device_step(first, local=not local_neg)
         barrier()
@@ -399,7 +429,9 @@ def run_b200(a, rank, local_rank, world):
         return
 
     peak, peak_src = measured_peak()
-    bpp = bytes_per_pair(a.emb, a.neg, a.radius)
+    window = a.kernel == 'window' and not a2a
+    bpp = bytes_per_pair(a.emb, a.neg, a.radius, window)
+    bpp_survey = bytes_per_pair(a.emb, a.neg, a.radius, False)
     achieved = pairs_per_step * bpp / (sgns_ms / 1e3) / 1e9
     traffic = recorded_traffic()
     line = {
@@ -410,10 +442,12 @@ def run_b200(a, rank, local_rank, world):
         'sgns_kernel_pairs_per_s': world * pairs_per_step / (sgns_ms / 1e3),
         'kernel_ms': {'walk_kernel': walk_ms, 'sgns_kernel': sgns_ms},
         'roofline': {
-            'bound': 'hbm', 'kernel': ('sgns_win_kernel<T=1+K, E=128>' if a.kernel == 'window' else 'sgns_ctx_kernel<MODE_WALK, T=1+K, E=128>')
-                                      + ' (se_sgns_update_walks)', 'achieved': achieved, 'peak': peak,
+            'bound': 'hbm', 'kernel': 'se_sgns_grad inside the NCCL row exchange (baseline)' if a2a else (
+                ('sgns_win_kernel<T=1+K, E=128>' if a.kernel == 'window' else 'sgns_ctx_kernel<MODE_WALK, T=1+K, E=128>') + ' (se_sgns_update_walks)'), 'achieved': achieved, 'peak': peak,
             'unit': 'GB/s', 'frac': achieved / peak, 'peak_source': peak_src,
             'algorithmic_bytes_per_pair': bpp, 'pairs_per_launch': pairs_per_step,
+            'bytes_per_pair_formula': '2*4E*(K + 2/N): context rows resident per window' if window else '2*4E*(1 + K + 1/N) (SURVEY 8d)',
+            'survey_unit': {'bytes_per_pair': bpp_survey, 'frac': pairs_per_step * bpp_survey / (sgns_ms / 1e3) / 1e9 / peak},
             'traffic': (traffic or {}).get('dram_bytes_per_launch'), 'traffic_source': (traffic or {}).get('source'),
             # the window kernel fetches a token's context row once per window instead of once per pair, so its DRAM traffic
             # is below the per-pair algorithmic figure; the DRAM-side rate is traffic / launch time
@@ -429,6 +463,8 @@ def run_b200(a, rank, local_rank, world):
     }
     if other is not None:
         line['sharded_other_negative_mode'] = other
+    if a2a:
+        line['a2a'] = {'micro_walks': a.a2a_micro_walks, 'exchanged_bytes_sent_per_rank': tables.exchanged_bytes}
     if sharded:
         line['tables'] = {'kind': 'vmm-striped', 'stripe_bytes': w_in.stripe_bytes, 'stripes_per_table': w_in.n_stripes,
                           'bytes_per_gpu': 2 * w_in.n_stripes * w_in.stripe_bytes // world}

@@ -116,3 +116,53 @@ def test_make_exchange_over_gloo_world_size_2():
     for p in procs:
         p.join(timeout=30)
     assert res[0] == b'hello from 1' and res[1] == b'hello from 0', res
+
+
+def _row_exchange_worker(rank, world, port, q):
+    import torch
+    import torch.distributed as dist
+    from shallow_encoders.word2vec.row_exchange import RowShardedTables
+    os.environ.update(MASTER_ADDR='127.0.0.1', MASTER_PORT=str(port), RANK=str(rank), WORLD_SIZE=str(world))
+    try:
+        dist.init_process_group('gloo', rank=rank, world_size=world)
+        vocab, emb = 101, 4
+        full = torch.arange(vocab * emb, dtype=torch.float32).reshape(vocab, emb)
+        t = RowShardedTables(vocab, emb, rank, world, 'cpu')
+        t.load_full('out', full)
+        assert t.local['out'].shape[0] == len(range(rank, vocab, world))
+        g = torch.Generator().manual_seed(100 + rank)
+        ids = torch.unique(torch.randint(0, vocab, (40 + 7 * rank,), generator=g))
+        plan = t.plan(ids)
+        rows = t.fetch('out', plan)
+        assert torch.equal(rows, full[ids]), 'fetched rows differ'
+        grads = torch.full((ids.numel(), emb), float(rank + 1))
+        t.push('out', plan, grads, lr=0.5)
+        dist.barrier()
+        got = t.gather_full('out')
+        # expected: every rank r subtracted 0.5 * (r + 1) from the rows IT asked for
+        want = full.clone()
+        for r in range(world):
+            gr = torch.Generator().manual_seed(100 + r)
+            ids_r = torch.unique(torch.randint(0, vocab, (40 + 7 * r,), generator=gr))
+            want[ids_r] -= 0.5 * (r + 1)
+        assert torch.equal(got, want), 'pushed gradients were not applied at the owners'
+        c, x = RowShardedTables.windows(torch.arange(16, dtype=torch.int32).reshape(2, 8), 3, 1)
+        assert c.reshape(-1).tolist() == [4, 5, 12, 13] and x[0].tolist() == [1, 2, 3, 5, 6, 7]     # torch_dataset.py:302-306
+        dist.destroy_process_group()
+        q.put((rank, 'ok'))
+    except Exception as e:   # noqa: BLE001
+        import traceback
+        q.put((rank, traceback.format_exc()))
+
+
+def test_row_exchange_fetch_and_push_over_gloo_world_size_2():
+    ctx = mp.get_context('spawn')
+    q = ctx.Queue()
+    port = 29300 + os.getpid() % 300
+    procs = [ctx.Process(target=_row_exchange_worker, args=(r, 2, port, q)) for r in range(2)]
+    for p in procs:
+        p.start()
+    res = dict(q.get(timeout=180) for _ in range(2))
+    for p in procs:
+        p.join(timeout=30)
+    assert res == {0: 'ok', 1: 'ok'}, res
