@@ -127,6 +127,23 @@ def main():
                             scratch, stats_host, local_negatives=True)
     assert stats_host[4].item() == starts.numel() * (L - 2 * radius) * 2 * radius and np.isfinite(stats_host.numpy()).all()
     barrier()
+
+    # 6. the NCCL all-to-all baseline (row % world sharding) is synchronous mini-batch SGD over the union of all ranks' pairs
+    from shallow_encoders.word2vec.row_exchange import RowShardedTables
+    rs = RowShardedTables(vocab, emb, rank, world, dev)
+    rs.load_full('in', d_in); rs.load_full('out', d_out)
+    tok_r = torch.from_numpy(tokens_all[rank]).to(dev)
+    b_r = n_seq * 1
+    rs.step(tok_r, radius, k, offset, lr, 23, draw_id_base=5000 * (rank + 1), micro_walks=n_seq)
+    barrier()
+    inputs, targets = sgns_oracle.windows_from_walks(tokens_all.reshape(-1, length).astype(np.int64), radius, offset)
+    neg = np.concatenate([philox_ref.draws(23, b_r * 2 * radius * k, vocab, base=5000 * (r + 1)).reshape(b_r, 2 * radius, k) for r in range(world)])
+    want_in, want_out, _ = sgns_oracle.sgd_step(w_in0.astype(np.float64), w_out0.astype(np.float64), inputs, targets, neg,
+                                                lr * len(inputs) * 2 * radius)     # each rank applies lr * (sum of ITS pairs' gradients)
+    np.testing.assert_allclose(rs.gather_full('in').cpu().numpy(), want_in, rtol=1e-4, atol=1e-5)
+    np.testing.assert_allclose(rs.gather_full('out').cpu().numpy(), want_out, rtol=1e-4, atol=1e-5)
+    assert rs.exchanged_bytes > 0
+    barrier()
     s_in.close(); s_out.close(); ex.close()
     dist.destroy_process_group()
     print(f'MGPU_OK rank {rank}/{world}', flush=True)

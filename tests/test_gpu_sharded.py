@@ -174,6 +174,31 @@ def test_host_step_on_sharded_tables_matches_device_calls():
     np.testing.assert_allclose(res[0][2], res[1][2], rtol=0, atol=1e-4)
 
 
+def test_nccl_baseline_step_equals_minibatch_sgd_on_one_gpu():
+    """RowShardedTables (the all-to-all baseline) with world = 1: windows + device negatives + unique + se_sgns_grad + apply
+    == the oracle's mini-batch SGD on the same pairs (negatives restated with the numpy Philox)."""
+    dev = cuda_device()
+    from shallow_encoders.word2vec.row_exchange import RowShardedTables
+    rng = np.random.default_rng(41)
+    vocab, emb, radius, k, n_seq, offset, lr, seed = 30000, 64, 2, 3, 40, 1, 0.025, 17
+    length = 9
+    tokens = rng.integers(0, vocab - offset, (n_seq, length)).astype(np.int32)          # repeats allowed: mini-batch semantics
+    inputs, targets = sgns_oracle.windows_from_walks(tokens.astype(np.int64), radius, offset)
+    b, n = targets.shape
+    w_in = (rng.standard_normal((vocab, emb)) * 0.3).astype(np.float32)
+    w_out = (rng.standard_normal((vocab, emb)) * 0.3).astype(np.float32)
+    t = RowShardedTables(vocab, emb, 0, 1, dev)
+    t.load_full('in', _t(w_in, dev)); t.load_full('out', _t(w_out, dev))
+    stats = torch.zeros(nat.STATS_LEN, dtype=torch.float64, device=dev)
+    t.step(_t(tokens, dev), radius, k, offset, lr, seed, draw_id_base=1000, micro_walks=n_seq, stats=stats)
+    neg = philox_ref.draws(seed, b * n * k, vocab, base=1000).reshape(b, n, k)
+    want_in, want_out, o = sgns_oracle.sgd_step(w_in.astype(np.float64), w_out.astype(np.float64), inputs, targets, neg, lr * b * n)
+    np.testing.assert_allclose(t.gather_full('in').cpu().numpy(), want_in, rtol=1e-4, atol=1e-5)
+    np.testing.assert_allclose(t.gather_full('out').cpu().numpy(), want_out, rtol=1e-4, atol=1e-5)
+    st = stats.tolist()
+    assert st[4] == b * n and abs((st[0] + st[1]) / st[4] - o['loss']) < 1e-4 * o['loss']
+
+
 @pytest.mark.skipif(torch.cuda.device_count() < 2, reason='needs two GPUs on one NVLink/NVSwitch node')
 def test_two_gpus_train_one_pair_of_tables_over_nvlink():
     world = min(torch.cuda.device_count(), 4)
