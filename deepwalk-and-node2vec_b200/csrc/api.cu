@@ -139,3 +139,20 @@ extern "C" int se_host_walk_sgns_step(const int64_t *rowptr, const int32_t *col,
                                           row_offset, alias_prob, alias_idx, lr, flags, nullptr, starts_dev, walks_dev,
                                           stats_dev, walks_host, stats_host, stream);
 }
+
+extern "C" int se_host_sgns_update_tokens(const int32_t *tokens_host, int64_t n_seq, int seq_len, float *w_in, float *w_out,
+                                          int64_t vocab, int emb, int radius, int n_neg, int row_offset,
+                                          const float *alias_prob, const int32_t *alias_idx, float lr, uint64_t seed,
+                                          int64_t centre_id_base, int flags, const se_shard_spec *spec, int32_t *tokens_dev,
+                                          double *stats_dev, double *stats_host, void *stream) {
+    SE_REQUIRE(tokens_host && tokens_dev && stats_dev && stats_host && n_seq >= 0 && seq_len >= 1, "se_host_sgns_update_tokens: bad arguments");
+    cudaStream_t st = (cudaStream_t)stream;
+    SE_CUDA(cudaMemcpyAsync(tokens_dev, tokens_host, sizeof(int32_t) * (size_t)n_seq * (size_t)seq_len, cudaMemcpyHostToDevice, st));
+    SE_CUDA(cudaMemsetAsync(stats_dev, 0, sizeof(double) * SE_STATS_LEN, st));
+    int rc = se_sgns_update_walks_sharded(w_in, w_out, vocab, emb, tokens_dev, n_seq, seq_len, radius, n_neg, row_offset, alias_prob,
+                                          alias_idx, lr, seed, centre_id_base, flags, spec, stats_dev, stream);
+    if (rc != SE_OK) return rc;
+    SE_CUDA(cudaMemcpyAsync(stats_host, stats_dev, sizeof(double) * SE_STATS_LEN, cudaMemcpyDeviceToHost, st));
+    SE_CUDA(cudaStreamSynchronize(st));
+    return SE_OK;
+}

@@ -70,6 +70,8 @@ _SIGNATURES = {
     'se_host_walk_sgns_step_sharded': (c_int, [c_p, c_p, c_p, c_i64, c_int, c_p, c_i64, c_int, c_f64, c_f64, c_int, c_int,
                                                c_u64, c_i64, c_p, c_p, c_i64, c_int, c_int, c_int, c_int, c_p, c_p, c_f32,
                                                c_int, c_p, c_p, c_p, c_p, c_p, c_p, c_p]),
+    'se_host_sgns_update_tokens': (c_int, [c_p, c_i64, c_int, c_p, c_p, c_i64, c_int, c_int, c_int, c_int, c_p, c_p, c_f32, c_u64, c_i64,
+                                           c_int, c_p, c_p, c_p, c_p, c_p]),
     'se_table_fill_uniform': (c_int, [c_p, c_i64, c_f32, c_u64, c_i64, c_int, c_int, c_p]),
     'se_table_gather_rows': (c_int, [c_p, c_int, c_p, c_i64, c_p, c_p]),
     'se_table_scatter_rows': (c_int, [c_p, c_int, c_p, c_i64, c_p, c_p]),
@@ -256,14 +258,16 @@ def _stats_dict(stats: torch.Tensor) -> Dict[str, float]:
     }
 
 
-def skipgram_scores(w_in: torch.Tensor, w_out: torch.Tensor, inputs: torch.Tensor, outputs: torch.Tensor,
-                    proba: bool) -> torch.Tensor:
+def skipgram_scores(w_in, w_out, inputs: torch.Tensor, outputs: torch.Tensor, proba: bool) -> torch.Tensor:
+    """SkipGram.forward on torch tables or striped ShardedTables."""
     global _launches
     batch, m = outputs.shape
-    out = torch.empty((batch, m), dtype=torch.float32, device=w_in.device)
-    with _on(w_in):
+    p_in, vocab, emb, _, dev = _table(w_in, 'w_in')
+    p_out, _, _, _, _ = _table(w_out, 'w_out')
+    out = torch.empty((batch, m), dtype=torch.float32, device=dev)
+    with torch.cuda.device(dev):
         _check(load().se_skipgram_scores(
-            _ptr(w_in, torch.float32, 'w_in'), _ptr(w_out, torch.float32, 'w_out'), w_in.shape[0], w_in.shape[1],
+            p_in, p_out, vocab, emb,
             _ptr(inputs.reshape(-1), torch.int64, 'inputs'), _ptr(outputs, torch.int64, 'outputs'), batch, m,
             int(bool(proba)), out.data_ptr(), _stream()))
     _launches += 1
@@ -405,6 +409,31 @@ def host_walk_sgns_step(csr, starts_host: torch.Tensor, walk_len: int, p: float,
             _ptr(scratch['stats'], torch.float64), walks_host.data_ptr() if walks_host is not None else None,
             stats_host.data_ptr(), _stream()))
     _launches += 2
+
+
+def host_sgns_update_tokens(tokens_host: torch.Tensor, w_in, w_out, radius: int, n_neg: int, row_offset: int, lr: float, seed: int,
+                            tokens_dev: torch.Tensor, stats_dev: torch.Tensor, stats_host: torch.Tensor, centre_id_base: int = 0,
+                            alias: Optional[Dict[str, torch.Tensor]] = None, flags: int = SCATTER_RED,
+                            local_negatives: bool = False) -> None:
+    """HOST-buffer step on token-id sequences int32 [n_seq, L] (H2D tokens -> fused SGNS -> D2H stats); synchronises."""
+    global _launches
+    assert not tokens_host.is_cuda and tokens_host.dtype == torch.int32 and tokens_host.is_contiguous()
+    assert not stats_host.is_cuda and stats_host.dtype == torch.float64 and stats_host.numel() >= STATS_LEN
+    n_seq, seq_len = tokens_host.shape
+    assert tokens_dev.numel() >= n_seq * seq_len
+    p_in, vocab, emb, s_in, dev = _table(w_in, 'w_in')
+    p_out, _, _, s_out, _ = _table(w_out, 'w_out')
+    spec = _same_sharding(s_in, s_out)
+    if spec is not None:
+        spec = ShardSpec(spec.world, spec.rank, spec.stripe_rows, int(bool(local_negatives)), 0)
+    with torch.cuda.device(dev):
+        _check(load().se_host_sgns_update_tokens(
+            tokens_host.data_ptr(), n_seq, seq_len, p_in, p_out, vocab, emb, int(radius), int(n_neg), int(row_offset),
+            _ptr(alias['prob'], torch.float32) if alias else None, _ptr(alias['alias'], torch.int32) if alias else None,
+            float(lr), int(seed) & (2 ** 64 - 1), int(centre_id_base), int(flags),
+            ctypes.byref(spec) if spec is not None else None, _ptr(tokens_dev, torch.int32), _ptr(stats_dev, torch.float64),
+            stats_host.data_ptr(), _stream()))
+    _launches += 1
 
 
 # ----------------------------------------------------------------------------------------------------------------

@@ -45,6 +45,7 @@ class TrainConfig:
     devices: str = '1'
     engine: str = 'reference'          # 'reference': autograd + YAML optimizer; 'fused': in-place SGD kernel
     fused_lr: float = 0.025
+    local_negatives: bool = False      # multi-GPU fused engine: draw negatives among the rows the GPU owns
 
     def instantiate_optimizer(self, params):
         return instantiate(self.optimizer, params=params)
@@ -105,16 +106,22 @@ class GlobalConfig:
     path: PathConfig = field(default_factory=PathConfig)
     downstream: dict = field(default_factory=dict)
 
-    def instantiate_model(self, dataset=None):
+    def instantiate_model(self, dataset=None, shard: Optional[dict] = None):
+        """`shard` = {'rank', 'world', 'exchange', 'seed'}: stripe the two tables over the GPUs of the node (multi-GPU runs)."""
         dataset = self.datamodule.instantiate_dataset() if dataset is None else dataset
-        return instantiate(self.model, vocab_size=len(dataset.vocab))
+        extra = {'shard': shard} if shard is not None else {}
+        return instantiate(self.model, vocab_size=len(dataset.vocab), **extra)
 
-    def instantiate_trainer(self, model=None, optimizer=None, scheduler=None, dataset=None, checkpoint_path: Optional[str] = None):
+    def instantiate_trainer(self, model=None, optimizer=None, scheduler=None, dataset=None, checkpoint_path: Optional[str] = None,
+                            shard: Optional[dict] = None):
         from shallow_encoders.word2vec.trainer import Word2VecTrainer
         dataset = self.datamodule.instantiate_dataset() if dataset is None else dataset
-        model = self.instantiate_model(dataset=dataset) if model is None else model
-        optimizer = self.train.instantiate_optimizer(model.parameters()) if optimizer is None else optimizer
-        scheduler = self.train.instantiate_scheduler(optimizer) if scheduler is None else scheduler
+        model = self.instantiate_model(dataset=dataset, shard=shard) if model is None else model
+        params = list(model.parameters())
+        if params:
+            optimizer = self.train.instantiate_optimizer(params) if optimizer is None else optimizer
+            scheduler = self.train.instantiate_scheduler(optimizer) if scheduler is None else scheduler
+        # striped tables are not nn.Parameters: they train through the fused engine (in-place SGD), no torch optimizer
         kwargs = dict(model=model, optimizer=optimizer, scheduler=scheduler,
                       neg_samples=self.train.loss.negative_samples, vocab_size=len(dataset.vocab))
         if checkpoint_path is None:

@@ -86,12 +86,14 @@ class RandomWalkDataset:
         order = torch.tensor(self._order, dtype=torch.int32)
         return order.repeat_interleave(self._walks_per_node)
 
-    def epoch_walks(self, seed: Optional[int] = None) -> torch.Tensor:
+    def epoch_walks(self, seed: Optional[int] = None, rank: int = 0, world: int = 1) -> torch.Tensor:
         """All walks of one epoch, int32 node ids [len(self), walk_length] on the device; reshuffles the node order
-        for the next epoch (reference :86-88)."""
+        for the next epoch (reference :86-88).  With world > 1 only walks rank, rank + world, ... of the epoch are generated
+        (same node order on every rank -- seed python's `random` identically -- and the same `seed`): the union over
+        ranks is exactly the single-GPU epoch, because Philox is keyed by the global walk id."""
         gen = self._walk_generator
-        starts = self.epoch_starts().to(gen.csr.device, non_blocking=True)
-        walks = gen.walk_batch(starts, seed=seed, walk_id_base=self._epoch * len(self))
+        starts = self.epoch_starts()[rank::world].contiguous().to(gen.csr.device, non_blocking=True)
+        walks = gen.walk_batch(starts, seed=seed, walk_id_base=self._epoch * len(self) + rank, walk_id_stride=world)
         self._epoch += 1
         random.shuffle(self._order)
         return walks

@@ -133,9 +133,9 @@ class GraphDataset(IterableDataset):
     def row_offset(self) -> int:
         return 1                       # '<unk>' occupies table row 0
 
-    def epoch_tokens(self, seed: Optional[int] = None) -> torch.Tensor:
-        """One epoch of walks as int32 node ids [n_walks, walk_length] on the device."""
-        return self._dataset.epoch_walks(seed=seed)
+    def epoch_tokens(self, seed: Optional[int] = None, rank: int = 0, world: int = 1) -> torch.Tensor:
+        """One epoch of walks as int32 node ids [n_walks, walk_length] on the device (world > 1: this rank's share)."""
+        return self._dataset.epoch_walks(seed=seed, rank=rank, world=world)
 
 
 class W2VCollateFunctional:

@@ -35,12 +35,25 @@ class _SkipGramScores(torch.autograd.Function):
 class W2VBase(nn.Module):
     """Input and context embedding tables."""
 
-    def __init__(self, vocab_size: int, embedding_size: int, max_norm: Optional[float] = None, device=None):
+    def __init__(self, vocab_size: int, embedding_size: int, max_norm: Optional[float] = None, device=None,
+                 shard: Optional[dict] = None):
+        """`shard` (not in the reference, which is single-device): {'rank', 'world', 'exchange', 'seed'} -> both tables are
+        ONE pair of `ShardedTable`s striped over the GPUs of the node instead of per-process `nn.Embedding`s; only the
+        fused engine and `forward` without autograd work on them."""
         super().__init__()
         if max_norm is not None:
             raise NotImplementedError('max_norm renormalisation is not implemented on the B200 path (only the abcde toy '
                                       'configs of the reference set it)')
         device = torch.device('cuda' if device is None else device)
+        self._sharded = None
+        if shard is not None and shard.get('world', 1) > 1:
+            from shallow_encoders.word2vec.sharded import ShardedTable
+            bound = (6.0 / (vocab_size + embedding_size)) ** 0.5           # xavier_uniform_ (reference :26-27)
+            self._sharded = tuple(ShardedTable(vocab_size, embedding_size, device, shard['rank'], shard['world'], shard['exchange'])
+                                  for _ in range(2))
+            for k, t in enumerate(self._sharded):
+                t.fill_uniform(bound, int(shard.get('seed', 0)) * 2 + k)
+            return
         self._input_embedding = nn.Embedding(vocab_size, embedding_size, device=device)
         self._output_embedding = nn.Embedding(vocab_size, embedding_size, device=device)
         torch.nn.init.xavier_uniform_(self._input_embedding.weight)
@@ -49,22 +62,48 @@ class W2VBase(nn.Module):
     @property
     def input_embedding(self) -> torch.Tensor:
         """Input embedding weights as a CPU tensor (reference :29-37)."""
+        if self._sharded is not None:
+            return self._sharded[0].to_tensor().cpu()
         return self._input_embedding.weight.to('cpu').data
 
     @property
     def output_embedding(self) -> torch.Tensor:
         """Context embedding weights as a CPU tensor (reference :39-47)."""
+        if self._sharded is not None:
+            return self._sharded[1].to_tensor().cpu()
         return self._output_embedding.weight.to('cpu').data
 
     @property
     def tables(self):
-        """(W_in, W_out) device tensors the fused kernels update in place."""
+        """(W_in, W_out) the fused kernels update in place: device tensors, or striped tables."""
+        if self._sharded is not None:
+            return self._sharded
         return self._input_embedding.weight.data, self._output_embedding.weight.data
 
+    # striped tables are not nn.Parameters: give checkpoints the reference's keys anyway (trainer.py state-dict keys
+    # `_model._input_embedding.weight`, `_model._output_embedding.weight`)
+    def state_dict(self, *args, destination=None, prefix='', keep_vars=False):
+        if self._sharded is None:
+            return super().state_dict(*args, destination=destination, prefix=prefix, keep_vars=keep_vars)
+        destination = {} if destination is None else destination
+        destination[prefix + '_input_embedding.weight'] = self._sharded[0].to_tensor()
+        destination[prefix + '_output_embedding.weight'] = self._sharded[1].to_tensor()
+        return destination
+
+    def _load_from_state_dict(self, state_dict, prefix, *args, **kwargs):
+        if self._sharded is None:
+            return super()._load_from_state_dict(state_dict, prefix, *args, **kwargs)
+        self._sharded[0].load_owned(state_dict[prefix + '_input_embedding.weight'])
+        self._sharded[1].load_owned(state_dict[prefix + '_output_embedding.weight'])
+
     def embed_inputs(self, inputs: torch.Tensor) -> torch.Tensor:
+        if self._sharded is not None:
+            return self._sharded[0].gather(inputs.reshape(-1)).reshape(*inputs.shape, -1)
         return self._input_embedding(inputs)
 
     def embed_outs(self, outputs: torch.Tensor) -> torch.Tensor:
+        if self._sharded is not None:
+            return self._sharded[1].gather(outputs.reshape(-1)).reshape(*outputs.shape, -1)
         return self._output_embedding(outputs)
 
 
@@ -72,6 +111,10 @@ class SkipGram(W2VBase):
     """inputs (B, 1), outputs (B, N) -> scores (B, N); sigmoid applied when `proba` (reference :79-91)."""
 
     def forward(self, inputs: torch.Tensor, outputs: torch.Tensor, proba: bool = True) -> torch.Tensor:
+        if self._sharded is not None:      # scoring only: striped tables train through the fused engine, not autograd
+            dev = self._sharded[0].device
+            return nat.skipgram_scores(self._sharded[0], self._sharded[1], inputs.to(dev).reshape(-1).contiguous(),
+                                       outputs.to(dev).contiguous(), proba=proba)
         w_in, w_out = self._input_embedding.weight, self._output_embedding.weight
         inputs = inputs.to(w_in.device).reshape(-1)
         outputs = outputs.to(w_in.device)

@@ -16,6 +16,12 @@ Engines (`train.engine`):
     fused       per epoch: one walk-kernel launch + one fused window/negatives/SGNS launch per `batch_size` walks,
                 in-place SGD with lr = train.fused_lr / (pairs per launch) decayed by the YAML's StepLR schedule.
 An existing experiment directory is replaced without the reference's interactive prompt (train.py:36-42) unless --keep.
+
+Several GPUs (not in the reference, whose YAMLs all say `devices: '1'`): launch under torchrun, one process per GPU,
+    python -m torch.distributed.run --nproc-per-node G --master-addr 127.0.0.1 tools/train.py --config-name=... train.engine=fused
+Both tables then exist ONCE, striped over the G HBMs (shallow_encoders/word2vec/sharded.py); every rank generates walks
+rank, rank+G, ... of each epoch and runs the fused kernel on the shared tables (Hogwild across GPUs, barrier per epoch);
+rank 0 writes the checkpoints (same state-dict keys, dense tensors).
 """
 import argparse
 import json
@@ -41,19 +47,49 @@ def experiment_dirs(output_dir: str, dataset: str, experiment: str):
             'tb_logs': os.path.join(output_dir, 'tb_logs', dataset, experiment)}
 
 
+def distributed_context():
+    """(rank, world, shard spec or None); initialises NCCL when launched under torchrun with WORLD_SIZE > 1."""
+    world = int(os.environ.get('WORLD_SIZE', '1'))
+    if world == 1:
+        return 0, 1, None
+    import random
+    import torch.distributed as dist
+    from shallow_encoders.word2vec.sharded import make_exchange
+    rank, local = int(os.environ['RANK']), int(os.environ.get('LOCAL_RANK', os.environ['RANK']))
+    torch.cuda.set_device(local)
+    if not dist.is_initialized():
+        dist.init_process_group('nccl', device_id=torch.device('cuda', local))
+    random.seed(0x5EED)                   # every rank must shuffle the node order identically (graph/datasets.py)
+    return rank, world, {'rank': rank, 'world': world, 'exchange': make_exchange(rank, world), 'seed': 0x5EED}
+
+
 def train(cfg, keep: bool = False, quiet: bool = False):
+    rank, world, shard = distributed_context()
+    if world > 1 and cfg.train.engine != 'fused':
+        raise ValueError('multi-GPU training runs the fused engine on striped tables: pass train.engine=fused')
+    quiet = quiet or rank != 0
     dirs = experiment_dirs(cfg.path.output_dir, cfg.datamodule.dataset_name, cfg.train.experiment)
-    for key in ('checkpoints', 'tb_logs'):
-        if os.path.exists(dirs[key]) and not keep:
-            shutil.rmtree(dirs[key])
-    for d in dirs.values():
-        os.makedirs(d, exist_ok=True)
+    if rank == 0:
+        for key in ('checkpoints', 'tb_logs'):
+            if os.path.exists(dirs[key]) and not keep:
+                shutil.rmtree(dirs[key])
+        for d in dirs.values():
+            os.makedirs(d, exist_ok=True)
+    if world > 1:
+        torch.distributed.barrier()
 
     dataset = cfg.datamodule.instantiate_dataset()
-    trainer = cfg.instantiate_trainer(dataset=dataset)
-    scalars = open(os.path.join(dirs['tb_logs'], 'scalars.jsonl'), 'a')
+    trainer = cfg.instantiate_trainer(dataset=dataset, shard=shard)
+    scalars = open(os.path.join(dirs['tb_logs'], 'scalars.jsonl'), 'a') if rank == 0 else None
 
     def end_of_epoch(tr, epoch, means):
+        if world > 1:                     # all ranks' updates are in the striped tables before rank 0 reads them
+            torch.cuda.synchronize()
+            torch.distributed.barrier()
+        if rank != 0:
+            if world > 1:
+                torch.distributed.barrier()
+            return
         name = f'checkpoint_epoch={epoch:06d}_step={tr.global_step:09d}.ckpt'
         tr.save_checkpoint(os.path.join(dirs['checkpoints'], name))
         tr.save_checkpoint(os.path.join(dirs['checkpoints'], 'last.ckpt'))
@@ -61,12 +97,14 @@ def train(cfg, keep: bool = False, quiet: bool = False):
         scalars.flush()
         if not quiet:
             print(f'epoch {epoch:3d} step {tr.global_step:7d} ' + ' '.join(f'{k}={v:.4f}' for k, v in means.items()), flush=True)
+        if world > 1:
+            torch.distributed.barrier()
 
     t0 = time.time()
     if cfg.train.engine == 'reference':
         trainer.fit(cfg.datamodule.instantiate_dataloader(dataset=dataset), cfg.train.max_epochs, on_epoch_end=end_of_epoch)
     elif cfg.train.engine == 'fused':
-        fit_fused(cfg, dataset, trainer, end_of_epoch)
+        fit_fused(cfg, dataset, trainer, end_of_epoch, rank, world)
     else:
         raise ValueError(f'unknown train.engine "{cfg.train.engine}"')
     torch.cuda.synchronize()
@@ -75,8 +113,9 @@ def train(cfg, keep: bool = False, quiet: bool = False):
     return trainer, dataset
 
 
-def fit_fused(cfg, dataset, trainer, end_of_epoch):
-    """Walk kernel + fused SGNS kernel; one launch per `batch_size` walks so that a launch is the reference's mini-batch."""
+def fit_fused(cfg, dataset, trainer, end_of_epoch, rank: int = 0, world: int = 1):
+    """Walk kernel + fused SGNS kernel; one launch per `batch_size` walks so that a launch is the reference's mini-batch.
+    world > 1: this rank's share of every batch (walks rank, rank + world, ...) against the striped tables."""
     r = cfg.datamodule.context_radius
     sched = cfg.train.scheduler.get('scheduler', cfg.train.scheduler)
     step_size, gamma = int(sched.get('step_size', 10 ** 9)), float(sched.get('gamma', 1.0))
@@ -85,14 +124,18 @@ def fit_fused(cfg, dataset, trainer, end_of_epoch):
     for epoch in range(cfg.train.max_epochs):
         trainer.current_epoch = epoch
         lr_batch = cfg.train.fused_lr * gamma ** (epoch // step_size)
-        tokens = dataset.epoch_tokens()[:, :cfg.datamodule.max_length]
+        tokens = dataset.epoch_tokens(rank=rank, world=world)[:, :cfg.datamodule.max_length]
         stats.zero_()
-        for lo in range(0, tokens.shape[0], cfg.datamodule.batch_size):
-            chunk = tokens[lo:lo + cfg.datamodule.batch_size].contiguous()
-            pairs = chunk.shape[0] * (chunk.shape[1] - 2 * r) * 2 * r
+        share = -(-cfg.datamodule.batch_size // world)             # this rank's walks of one global batch
+        for lo in range(0, tokens.shape[0], share):
+            chunk = tokens[lo:lo + share].contiguous()
+            pairs = chunk.shape[0] * (chunk.shape[1] - 2 * r) * 2 * r * world
             trainer.fused_step(chunk, r, lr_batch / pairs, row_offset=dataset.row_offset,
-                               seed=epoch * 1_000_003 + lo, stats=stats)
+                               seed=(epoch * 1_000_003 + lo) * world + rank, stats=stats,
+                               local_negatives=bool(getattr(cfg.train, 'local_negatives', False)) and world > 1)
             trainer.global_step += 1
+        if world > 1:
+            torch.distributed.all_reduce(stats)
         s = stats.tolist()
         p = max(s[4], 1.0)
         means = {'train-epoch/loss': (s[0] + s[1]) / p, 'train-epoch/positive-loss': s[0] / p,

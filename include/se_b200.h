@@ -234,6 +234,16 @@ int se_host_walk_sgns_step_sharded(const int64_t *rowptr, const int32_t *col, co
                                    int flags, const se_shard_spec *spec, int32_t *starts_dev, int32_t *walks_dev,
                                    double *stats_dev, int32_t *walks_host, double *stats_host, void *stream);
 
+/* Host-buffer step for sequences that are already token ids (the text path after W2VDataset.sentence_pipeline,
+ * word2vec/dataloader/torch_dataset.py:124-156, 205-213: one int32 id per token, sentences of equal length): copies
+ * tokens_host[n_seq * seq_len] to tokens_dev, runs the fused window / negatives / SGNS update, copies the SE_STATS_LEN
+ * doubles back and synchronises.  spec may be NULL. */
+int se_host_sgns_update_tokens(const int32_t *tokens_host, int64_t n_seq, int seq_len, float *w_in, float *w_out,
+                               int64_t vocab, int emb, int radius, int n_neg, int row_offset, const float *alias_prob,
+                               const int32_t *alias_idx, float lr, uint64_t seed, int64_t centre_id_base, int flags,
+                               const se_shard_spec *spec, int32_t *tokens_dev, double *stats_dev, double *stats_host,
+                               void *stream);
+
 /* Table utilities that work on local and sharded tables alike (W2VBase.__init__ xavier_uniform_, word2vec/model.py:22-27;
  * the input_embedding / output_embedding accessors, :29-47).
  *   fill: element i = (2u-1)*bound with u from Philox(seed; i/4) -- independent of the sharding; a rank writes only the

@@ -356,3 +356,30 @@ def test_window_resident_kernel_equals_sequential_oracle(emb, radius, k, length,
     np.testing.assert_allclose(results['context'][1][rows], got_out[rows], rtol=0, atol=1e-5)
     np.testing.assert_allclose(results['context'][0][rows], got_in[rows], rtol=0, atol=1e-5)
     assert results['context'][2]['pairs'] == st['pairs']
+
+
+def test_host_token_step_equals_device_call():
+    """se_host_sgns_update_tokens (host token ids in, statistics out) == se_sgns_update_walks on the same tokens."""
+    dev = cuda_device()
+    rng = np.random.default_rng(77)
+    vocab, emb, radius, k, n_seq, length = 50000, 128, 2, 3, 12, 5
+    tokens = rng.permutation(vocab - 1)[:n_seq * length].reshape(n_seq, length).astype(np.int32)      # distinct: deterministic
+    w_in = (rng.standard_normal((vocab, emb)) * 0.2).astype(np.float32)
+    w_out = (rng.standard_normal((vocab, emb)) * 0.2).astype(np.float32)
+    counts = 1.0 / np.arange(1, vocab + 1) ** 0.5
+    alias = nat.alias_build(counts, 0.75, dev)
+    a_in, a_out = _t(w_in, dev), _t(w_out, dev)
+    st = nat.sgns_update_walks(a_in, a_out, _t(tokens, dev), radius, k, 1, 0.025, 5, centre_id_base=9, alias=alias)
+    b_in, b_out = _t(w_in, dev), _t(w_out, dev)
+    stats_dev = torch.zeros(nat.STATS_LEN, dtype=torch.float64, device=dev)
+    stats_host = torch.zeros(nat.STATS_LEN, dtype=torch.float64)
+    scratch = torch.empty((n_seq, length), dtype=torch.int32, device=dev)
+    nat.host_sgns_update_tokens(torch.from_numpy(tokens), b_in, b_out, radius, k, 1, 0.025, 5, scratch, stats_dev, stats_host,
+                                centre_id_base=9, alias=alias)
+    # negatives drawn from the skewed alias table may repeat: rows hit twice are accumulated in a different order
+    np.testing.assert_allclose(b_in.cpu().numpy(), a_in.cpu().numpy(), rtol=0, atol=1e-6)
+    np.testing.assert_allclose(b_out.cpu().numpy(), a_out.cpu().numpy(), rtol=0, atol=1e-6)
+    assert stats_host[4].item() == st['pairs'] == n_seq * 2 * radius
+    assert abs((stats_host[0].item() + stats_host[1].item()) / stats_host[4].item() - st['loss']) < 1e-5
+    with pytest.raises(RuntimeError):
+        nat.host_sgns_update_tokens(torch.from_numpy(tokens), w_in, b_out, radius, k, 1, 0.025, 5, scratch, stats_dev, stats_host)

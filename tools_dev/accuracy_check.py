@@ -1,5 +1,5 @@
 """North-star gate 3: downstream node-classification accuracy of embeddings trained on the B200 path vs the reference's
-CPU pattern (oracle/cpu_port.train_reference_cpu) at identical settings, seed-averaged.  Writes profiles/r01_accuracy.json."""
+CPU pattern (oracle/cpu_port.train_reference_cpu) at identical settings, seed-averaged.  Writes gpurun_out/accuracy.json (copied to profiles/)."""
 import json
 import os
 import sys
@@ -22,7 +22,12 @@ CASES = {
     'karate': ('sge_sg_karate_club', [], ['train.fused_lr=40.0'], 5, 100),
     'triplets': ('sge_sg_graph_triplets', ['train.max_epochs=60', 'train.optimizer.lr=0.05', 'train.scheduler.step_size=30'], ['train.fused_lr=4.0'], 8, 10),
     'cora_synthetic': ('sge_sg_cora', ['train.max_epochs=8', 'train.scheduler.step_size=4'], ['train.fused_lr=60.0'], 2, 10),
+    # BASELINE.json configs[1]: node2vec p=1 q=0.5, dim 128 -- the shape that runs the window-resident hot kernel
+    'cora_synthetic_dim128': ('sge_sg_cora', ['train.max_epochs=8', 'train.scheduler.step_size=4', 'model.embedding_size=128',
+                                              'datamodule.additional_parameters.method_params.q=0.5'], ['train.fused_lr=60.0'], 2, 10),
 }
+if len(sys.argv) > 1:
+    CASES = {k: v for k, v in CASES.items() if k in sys.argv[1:]}
 out = {}
 workers = os.cpu_count() or 1
 for name, (yaml_name, common, fused_over, seeds, n_exp) in CASES.items():
