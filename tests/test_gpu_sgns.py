@@ -382,4 +382,4 @@ def test_host_token_step_equals_device_call():
     assert stats_host[4].item() == st['pairs'] == n_seq * 2 * radius
     assert abs((stats_host[0].item() + stats_host[1].item()) / stats_host[4].item() - st['loss']) < 1e-5
     with pytest.raises(RuntimeError):
-        nat.host_sgns_update_tokens(torch.from_numpy(tokens), w_in, b_out, radius, k, 1, 0.025, 5, scratch, stats_dev, stats_host)
+        nat.host_sgns_update_tokens(torch.from_numpy(tokens), torch.from_numpy(w_in), b_out, radius, k, 1, 0.025, 5, scratch, stats_dev, stats_host)   # no CPU fallback
