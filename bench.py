@@ -270,6 +270,7 @@ def run_b200(a, rank, local_rank, world):
     csr = powerlaw_graph_device(a.nodes, a.edges, a.seed, dev)
     vocab = a.nodes + 1                                   # row 0 = '<unk>' (torch_dataset.py:99-110)
     bound = (6.0 / (vocab + a.emb)) ** 0.5                # xavier_uniform_ (model.py:26-27)
+    fallback_note = None
     sharded = (world > 1 and a.multi == 'sharded') or (world == 1 and a.tables == 'vmm')
     a2a = world > 1 and a.multi == 'a2a'
     local_neg = (sharded or a2a) and world > 1 and a.negatives != 'global'
@@ -279,10 +280,31 @@ def run_b200(a, rank, local_rank, world):
         tables.fill_uniform(bound, a.seed + 101, a.seed + 102)
         w_in = w_out = None
     elif sharded:
+        # Striped tables need CUDA VMM handle export between processes (POSIX fds over unix sockets).  If the platform
+        # refuses that on ANY rank, every rank drops to the replica mode (still the same CUDA kernels) and the line says so.
         from shallow_encoders.word2vec.sharded import ShardedTable, make_exchange
-        ex = make_exchange(rank, world)
-        w_in = ShardedTable(vocab, a.emb, dev, rank, world, ex)
-        w_out = ShardedTable(vocab, a.emb, dev, rank, world, ex)
+        ex = w_in = w_out = None
+        try:
+            ex = make_exchange(rank, world)
+            w_in = ShardedTable(vocab, a.emb, dev, rank, world, ex)
+            w_out = ShardedTable(vocab, a.emb, dev, rank, world, ex)
+            ok, why = 1, ''
+        except Exception as e:   # noqa: BLE001
+            ok, why = 0, repr(e)
+        if world > 1:
+            flag = torch.tensor([ok], dtype=torch.int32, device=dev)
+            dist.all_reduce(flag, op=dist.ReduceOp.MIN)
+            ok = int(flag.item())
+        if not ok:
+            if world == 1:
+                raise RuntimeError(f'striped-table set-up failed: {why}')
+            for t in (w_in, w_out):
+                if t is not None:
+                    t.close()
+            sharded, local_neg, fallback_note = False, False, f'striped tables unavailable ({why or "on another rank"}): ran --multi replicas'
+            a.multi = 'replicas'
+            w_in = torch.empty((vocab, a.emb), dtype=torch.float32, device=dev)
+            w_out = torch.empty((vocab, a.emb), dtype=torch.float32, device=dev)
     else:
         w_in = torch.empty((vocab, a.emb), dtype=torch.float32, device=dev)
         w_out = torch.empty((vocab, a.emb), dtype=torch.float32, device=dev)
@@ -469,6 +491,8 @@ def run_b200(a, rank, local_rank, world):
         'graph': {'n_nodes': csr.n_nodes, 'nnz': csr.nnz, 'max_degree': csr.max_degree},
         'library': nat.version(),
     }
+    if fallback_note:
+        line['multi_gpu_fallback'] = fallback_note
     if other is not None:
         line['sharded_other_negative_mode'] = other
     if a2a:
