@@ -62,7 +62,7 @@ def parse_args():
     ap.add_argument('--neg', type=int, default=5)
     ap.add_argument('--p', type=float, default=0.5)
     ap.add_argument('--q', type=float, default=2.0)
-    ap.add_argument('--lr', type=float, default=0.025)
+    ap.add_argument('--lr', type=float, default=None, help='per-pair SGD step (default 0.025 on S3; 0.0025 on the Zipf-hot S4 stream)')
     ap.add_argument('--scatter', default='red', choices=['red', 'store'])
     ap.add_argument('--seed', type=int, default=0)
     ap.add_argument('--kernel', default='window', choices=['window', 'context'],
@@ -603,7 +603,7 @@ def run_s4(a):
                    'vocab': a.s4_vocab, 'zipf_s': a.s4_zipf, 'sentence_len': L, 'sentences_per_step': n_seq, 'tokens_per_step': n_seq * L,
                    'emb': a.emb, 'context_radius': a.radius, 'negatives': a.neg,
                    'negative_sampling': f'alias table, unigram^{a.s4_power}' if alias else 'uniform (reference)',
-                   'optimizer': 'in-place SGD (Hogwild, red.global.add.v4.f32)', 'parallelism': 'single GPU',
+                   'optimizer': f'in-place SGD lr {a.lr} (Hogwild, red.global.add.v4.f32)', 'parallelism': 'single GPU',
                    'l2': 'tables 2 x %.0f MB vs 126 MB L2: largely L2-resident, no flush (hot set is the point of this workload)' % (vocab * a.emb * 4 / 1e6)},
         'roofline': {'bound': 'hbm', 'kernel': ('sgns_win_kernel' if window else 'sgns_ctx_kernel') + '<T=1+K, E=128> (se_sgns_update_walks)',
                      'achieved': achieved, 'peak': peak, 'unit': 'GB/s', 'frac': achieved / peak, 'peak_source': peak_src,
@@ -621,6 +621,8 @@ def run_s4(a):
 
 def main():
     a = parse_args()
+    if a.lr is None:
+        a.lr = 0.025 if a.workload == 's3' else 0.0025
     rank = int(os.environ.get('RANK', '0'))
     local_rank = int(os.environ.get('LOCAL_RANK', '0'))
     world = int(os.environ.get('WORLD_SIZE', '1'))

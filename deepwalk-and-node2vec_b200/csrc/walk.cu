@@ -8,6 +8,17 @@
 //                       same distribution as sequential tries), neighbour lists up to STAGE_CAP entries staged in
 //                       shared memory so the membership test "x in N(t)" of the NEXT step is a shared-memory
 //                       binary search instead of a chain of dependent global loads.
+//
+// Rejection scheme of the production kernels (undirected graphs).  Target: pi(x | t, v) ~ w_vx * mult(x) with
+// mult(t) = 1/p and mult(x != t) in {1/q, 1} (random_walk_generator.py:101-108).  A naive envelope max(1/p, 1, 1/q)
+// wastes tries whenever 1/p is the maximum (p < 1: every ordinary candidate is then accepted with probability <= p).
+// Instead the RETURN EDGE IS SPLIT OFF: with m = max(1, 1/q) and Z = w_vt/p + W_v * m (W_v = total edge weight of v),
+//   with probability (w_vt/p) / Z   take x = t, accepted outright (no memory access at all);
+//   otherwise draw x ~ w_vx / W_v; x == t is rejected; x != t is accepted with probability mult(x) / m.
+// P(accept x != t) = (W_v m / Z)(w_vx / W_v)(mult(x) / m) = w_vx mult(x) / Z and P(accept t) = (w_vt/p) / Z: exactly the
+// target, and the acceptance rate is sum_x w_vx mult(x) / Z, i.e. ~1 try per step for q >= 1 whatever p is.  t is a
+// neighbour of v because the walk arrived over that edge; its weight w_vt = w_tv is remembered from the previous step.
+// Directed inputs (symmetric == 0) keep the plain envelope.
 #include "common.cuh"
 
 namespace se {
@@ -156,7 +167,8 @@ walk_kernel(const int64_t *__restrict__ rowptr, const int32_t *__restrict__ col,
     const int lane = threadIdx.x & 31;
     const int wib = threadIdx.x >> 5;
     const int64_t n_warps = (int64_t)gridDim.x * WALK_WPB;
-    const float wmax = fmaxf(1.0f, fmaxf(inv_p, inv_q));
+    const float wmax = fmaxf(1.0f, fmaxf(inv_p, inv_q));      // plain envelope (directed inputs)
+    const float m_o = fmaxf(1.0f, inv_q);                     // envelope of the candidates other than t (return edge split off)
     const bool any_bias = node2vec && !(inv_p == 1.0f && inv_q == 1.0f);
 
     for (int64_t wk = (int64_t)blockIdx.x * WALK_WPB + wib; wk < n_walks; wk += n_warps) {
@@ -164,6 +176,7 @@ walk_kernel(const int64_t *__restrict__ rowptr, const int32_t *__restrict__ col,
         int32_t *o = out + wk * (int64_t)walk_len;
         int32_t v = __ldg(starts + wk), t = -1;
         int64_t tbase = 0, tdeg = 0;
+        float wprev = 1.0f;                                   // weight of the edge the walk arrived over
         bool prev_staged = false;
         int cb = 0;
         int32_t keep = v;  // lane (s & 31) keeps the node of step s; flushed as one coalesced store per 32 steps
@@ -187,30 +200,50 @@ walk_kernel(const int64_t *__restrict__ rowptr, const int32_t *__restrict__ col,
                     const uint4 r = philox(seed, walk_id, (uint32_t)s, STREAM_WALK);
                     const int64_t k = pick_index<WEIGHTED>(wcdf, base, deg, r.x, r.y);
                     x = cur_staged ? cur[k] : __ldg(col + base + k);
+                    if (WEIGHTED && any_bias) wprev = __ldg(wcdf + base + k) - (k > 0 ? __ldg(wcdf + base + k - 1) : 0.f);
                 } else {
                     const int32_t *prv = stage[wib][cb ^ 1];
+                    const float zt = symmetric ? (WEIGHTED ? wprev * inv_p : inv_p) : 0.f;           // return-edge mass
+                    const float wtot = WEIGHTED ? __ldg(wcdf + base + deg - 1) : (float)deg;
+                    const float env = symmetric ? m_o : wmax;
+                    const float ztot = zt + wtot * env;
                     for (uint32_t round = 0;; ++round) {
-                        const uint4 r = philox(seed, walk_id, (uint32_t)s, STREAM_WALK | (round * 32u + (uint32_t)lane));
-                        const int64_t k = pick_index<WEIGHTED>(wcdf, base, deg, r.x, r.y);
-                        const int32_t cand = cur_staged ? cur[k] : __ldg(col + base + k);
-                        float mult;
-                        if (cand == t) {
-                            mult = inv_p;
+                        const uint32_t attempt = round * 32u + (uint32_t)lane;
+                        const uint4 r = philox(seed, walk_id, (uint32_t)s, STREAM_WALK | attempt);
+                        int32_t cand = t;
+                        int64_t k = -1;
+                        bool acc;
+                        if (symmetric && __uint2float_rz(r.w) * 2.3283064365386963e-10f * ztot < zt) {
+                            acc = true;                                   // return to t, no memory touched
                         } else {
-                            bool m;
-                            if (symmetric) {
-                                m = prev_staged ? member_smem(prv, (int)tdeg, cand)
-                                                : member_sorted(col, tbase, tbase + tdeg, cand);
+                            k = pick_index<WEIGHTED>(wcdf, base, deg, r.x, r.y);
+                            cand = cur_staged ? cur[k] : __ldg(col + base + k);
+                            float mult;
+                            if (cand == t) {
+                                mult = symmetric ? 0.f : inv_p;          // symmetric: t is only reachable through the split
                             } else {
-                                const int64_t xb = __ldg(rowptr + cand);
-                                m = member_sorted(col, xb, __ldg(rowptr + cand + 1), t);
+                                bool m;
+                                if (symmetric) {
+                                    m = prev_staged ? member_smem(prv, (int)tdeg, cand)
+                                                    : member_sorted(col, tbase, tbase + tdeg, cand);
+                                } else {
+                                    const int64_t xb = __ldg(rowptr + cand);
+                                    m = member_sorted(col, xb, __ldg(rowptr + cand + 1), t);
+                                }
+                                mult = ((rule == SE_RULE_REFERENCE) ? m : !m) ? inv_q : 1.0f;
                             }
-                            mult = ((rule == SE_RULE_REFERENCE) ? m : !m) ? inv_q : 1.0f;
+                            acc = u01(r.z) * env < mult;
                         }
-                        const bool acc = u01(r.z) * wmax < mult || (round * 32u + (uint32_t)lane) >= (1u << 25) - 1;
+                        acc = acc || attempt >= (1u << 25) - 1;
                         const unsigned ballot = __ballot_sync(FULL, acc);
                         if (ballot) {
-                            x = __shfl_sync(FULL, cand, __ffs(ballot) - 1);
+                            const int win = __ffs(ballot) - 1;
+                            x = __shfl_sync(FULL, cand, win);
+                            if (WEIGHTED) {
+                                float wsel = wprev;                       // the return edge keeps its weight
+                                if (lane == win && k >= 0) wsel = __ldg(wcdf + base + k) - (k > 0 ? __ldg(wcdf + base + k - 1) : 0.f);
+                                wprev = __shfl_sync(FULL, wsel, win);
+                            }
                             break;
                         }
                     }
@@ -277,6 +310,7 @@ walk_thread_kernel(const int64_t *__restrict__ rowptr, const int32_t *__restrict
                    float inv_q, int node2vec, int rule, uint64_t seed, int64_t walk_id_base, int64_t walk_id_stride,
                    int32_t *__restrict__ out, int32_t *__restrict__ err_count) {
     const float wmax = fmaxf(1.0f, fmaxf(inv_p, inv_q));
+    const float m_o = fmaxf(1.0f, inv_q);
     const bool any_bias = node2vec && !(inv_p == 1.0f && inv_q == 1.0f);
     const bool vec_out = ((walk_len & 3) == 0) && ((reinterpret_cast<uintptr_t>(out) & 15) == 0);
 
@@ -286,6 +320,7 @@ walk_thread_kernel(const int64_t *__restrict__ rowptr, const int32_t *__restrict
         int32_t v = __ldg(starts + wk), t = -1;
         int64_t base = 0, deg = 0, tbase = 0, tdeg = 0;
         int32_t tfirst = 0, tlast = 0, vfirst = 0, vlast = 0;
+        float wprev = 1.0f, wtot = 0.f;
         int32_t pend[4];
         pend[0] = v;
         if (!vec_out && walk_len > 0) o[0] = v;
@@ -300,6 +335,7 @@ walk_thread_kernel(const int64_t *__restrict__ rowptr, const int32_t *__restrict
                     vfirst = __ldg(col + base);
                     vlast = __ldg(col + base + deg - 1);
                 }
+                if (deg > 0 && any_bias) wtot = WEIGHTED ? __ldg(wcdf + base + deg - 1) : (float)deg;
                 need_row = false;
                 attempt = 0;
             }
@@ -309,25 +345,34 @@ walk_thread_kernel(const int64_t *__restrict__ rowptr, const int32_t *__restrict
                 dead = true;                    // the reference raises on an isolated node; stay and count
             } else {
                 const uint4 r = philox(seed, walk_id, (uint32_t)s, STREAM_WALK | attempt);
-                const int64_t k = pick_index<WEIGHTED>(wcdf, base, deg, r.x, r.y);
-                const int32_t cand = __ldg(col + base + k);
-                x = cand;
-                if (any_bias && t >= 0) {
-                    float mult;
-                    if (cand == t) {
-                        mult = inv_p;
-                    } else {
-                        bool m;
-                        if (symmetric) {
-                            m = member_interp(col, tbase, tdeg, tfirst, tlast, cand);
-                        } else {
-                            const int64_t xb = __ldg(rowptr + cand);
-                            m = member_sorted(col, xb, __ldg(rowptr + cand + 1), t);
-                        }
-                        mult = ((rule == SE_RULE_REFERENCE) ? m : !m) ? inv_q : 1.0f;
-                    }
-                    commit = (u01(r.z) * wmax < mult) || attempt >= (1u << 25) - 1;
+                const bool biased = any_bias && t >= 0;
+                const float zt = (biased && symmetric) ? (WEIGHTED ? wprev * inv_p : inv_p) : 0.f;
+                const float env = symmetric ? m_o : wmax;
+                if (biased && symmetric && __uint2float_rz(r.w) * 2.3283064365386963e-10f * (zt + wtot * env) < zt) {
+                    x = t;                                  // return edge, accepted outright (see the scheme above)
                     ++attempt;
+                } else {
+                    const int64_t k = pick_index<WEIGHTED>(wcdf, base, deg, r.x, r.y);
+                    const int32_t cand = __ldg(col + base + k);
+                    x = cand;
+                    if (biased) {
+                        float mult;
+                        if (cand == t) {
+                            mult = symmetric ? 0.f : inv_p;
+                        } else {
+                            bool m;
+                            if (symmetric) {
+                                m = member_interp(col, tbase, tdeg, tfirst, tlast, cand);
+                            } else {
+                                const int64_t xb = __ldg(rowptr + cand);
+                                m = member_sorted(col, xb, __ldg(rowptr + cand + 1), t);
+                            }
+                            mult = ((rule == SE_RULE_REFERENCE) ? m : !m) ? inv_q : 1.0f;
+                        }
+                        commit = (u01(r.z) * env < mult) || attempt >= (1u << 25) - 1;
+                        ++attempt;
+                    }
+                    if (WEIGHTED && any_bias && commit) wprev = __ldg(wcdf + base + k) - (k > 0 ? __ldg(wcdf + base + k - 1) : 0.f);
                 }
             }
             if (commit) {
