@@ -29,6 +29,10 @@ def test_fill_is_independent_of_sharding_and_rows_round_trip():
     dense = torch.empty((vocab, emb), dtype=torch.float32, device=dev)
     nat.table_fill_uniform(dense, 0.25, seed=11)
     assert float(dense.abs().max()) <= 0.25 and float(dense.abs().max()) > 0.2 and abs(float(dense.mean())) < 1e-3
+    # numpy restatement: element 4v+j = (2*u01(word j of Philox(seed; v, 0, 0x50000000)) - 1) * bound
+    words = philox_ref.philox(11, np.arange(64, dtype=np.uint64), 0, 0x50000000)
+    want = np.stack([(np.float32(2.0) * philox_ref.u01(w) - np.float32(1.0)) * np.float32(0.25) for w in words], axis=1).reshape(-1)
+    assert np.array_equal(dense.reshape(-1)[:256].cpu().numpy(), want.astype(np.float32))
     one = ShardedTable(vocab, emb, dev)                                     # world 1: every stripe local
     one.fill_uniform(0.25, seed=11)
     assert torch.equal(one.to_tensor(), dense)
