@@ -26,6 +26,7 @@ GENERIC_KERNEL = 2
 NO_WINDOW = 4
 STATS_LEN = 6
 WALK_AUTO, WALK_WARP, WALK_THREAD = 0, 1, 2
+EDGE_OPS = {'average': 0, 'hadamard': 1, 'weighted_l1': 2, 'weighted_l2': 3}
 
 _lib = None
 _launches = 0    # kernels launched through this module (bench.py reports it as gpu_launches)
@@ -72,6 +73,9 @@ _SIGNATURES = {
                                                c_int, c_p, c_p, c_p, c_p, c_p, c_p, c_p]),
     'se_host_sgns_update_tokens': (c_int, [c_p, c_i64, c_int, c_p, c_p, c_i64, c_int, c_int, c_int, c_int, c_p, c_p, c_f32, c_u64, c_i64,
                                            c_int, c_p, c_p, c_p, c_p, c_p]),
+    'se_edge_features': (c_int, [c_p, c_i64, c_int, c_p, c_p, c_i64, c_int, c_p, c_p]),
+    'se_edge_op': (c_int, [c_p, c_p, c_i64, c_int, c_p, c_p]),
+    'se_sample_negative_edges': (c_int, [c_p, c_p, c_i64, c_i64, c_u64, c_i64, c_p, c_p, c_p, c_p]),
     'se_table_fill_uniform': (c_int, [c_p, c_i64, c_f32, c_u64, c_i64, c_int, c_int, c_p]),
     'se_table_gather_rows': (c_int, [c_p, c_int, c_p, c_i64, c_p, c_p]),
     'se_table_scatter_rows': (c_int, [c_p, c_int, c_p, c_i64, c_p, c_p]),
@@ -471,3 +475,55 @@ def table_scatter_rows(table, rows: torch.Tensor, src: torch.Tensor) -> None:
     with torch.cuda.device(dev):
         _check(load().se_table_scatter_rows(ptr, emb, _ptr(rows, torch.int64, 'rows'), rows.numel(), _ptr(src, torch.float32, 'src'), _stream()))
     _launches += 1
+
+
+# ----------------------------------------------------------------------------------------------------------------
+# link-prediction features
+# ----------------------------------------------------------------------------------------------------------------
+def _edge_op_code(op) -> int:
+    if isinstance(op, str):
+        name = op.lower()
+        assert name in EDGE_OPS, f'Operator "{op}" is not supported. Available: {list(EDGE_OPS.keys())}'
+        return EDGE_OPS[name]
+    return int(op)
+
+
+def edge_features(table: torch.Tensor, src_rows: torch.Tensor, dst_rows: torch.Tensor, op) -> torch.Tensor:
+    """out[i] = op(table[src_rows[i]], table[dst_rows[i]]) -> float32 [n_edges, emb] on the device."""
+    global _launches
+    n = src_rows.numel()
+    out = torch.empty((n, table.shape[1]), dtype=torch.float32, device=table.device)
+    with _on(table):
+        _check(load().se_edge_features(_ptr(table, torch.float32, 'table'), table.shape[0], table.shape[1],
+                                       _ptr(src_rows.reshape(-1), torch.int64, 'src_rows'), _ptr(dst_rows.reshape(-1), torch.int64, 'dst_rows'),
+                                       n, _edge_op_code(op), out.data_ptr(), _stream()))
+    _launches += 1
+    return out
+
+
+def edge_op(lhs: torch.Tensor, rhs: torch.Tensor, op) -> torch.Tensor:
+    global _launches
+    assert lhs.shape == rhs.shape
+    out = torch.empty_like(lhs)
+    with _on(lhs):
+        _check(load().se_edge_op(_ptr(lhs, torch.float32, 'lhs'), _ptr(rhs, torch.float32, 'rhs'), lhs.numel(), _edge_op_code(op),
+                                 out.data_ptr(), _stream()))
+    _launches += 1
+    return out
+
+
+def sample_negative_edges(csr, n: int, seed: int, sample_id_base: int = 0):
+    """(src, dst) int32 node ids of n sampled non-edges; raises if some sample found no non-neighbour."""
+    global _launches
+    dev = csr.device
+    src = torch.empty(n, dtype=torch.int32, device=dev)
+    dst = torch.empty(n, dtype=torch.int32, device=dev)
+    fail = torch.zeros(1, dtype=torch.int32, device=dev)
+    with _on(src):
+        _check(load().se_sample_negative_edges(_ptr(csr.rowptr, torch.int64), _ptr(csr.col_sorted, torch.int32), csr.n_nodes, int(n),
+                                               int(seed) & (2 ** 64 - 1), int(sample_id_base), src.data_ptr(), dst.data_ptr(),
+                                               fail.data_ptr(), _stream()))
+    _launches += 1
+    if int(fail.item()):
+        raise RuntimeError(f'{int(fail.item())} negative-edge samples found no non-neighbour (graph too dense)')
+    return src, dst

@@ -31,3 +31,48 @@ def node_classification(embedding: np.ndarray, itos: List[str], labels: Dict[str
         total += acc
         best = max(best, acc)
     return total / n_experiments, best
+
+
+def edge_classification(embedding, csr, train_ratio: float, n_experiments: int, edge_operator_name: str,
+                        classifier_params: Optional[dict] = None, row_offset: int = 1, seed: int = 0) -> Tuple[float, float]:
+    """Link prediction, restating perform_edge_classification (tools/graph_model_downstream_classification.py:227-299):
+    per experiment a random `train_ratio` of the graph's edges are the positive training set, as many sampled non-edges the
+    negative one (`sample_negative_edges`, :170-200); the classifier is scored on ALL edges plus the training and validation
+    negatives (:268-287).  Features are built on the device (`se_edge_features`, `se_sample_negative_edges`); the logistic
+    regression is sklearn on the host, as in the reference.  `embedding`: [vocab x emb] CUDA tensor (row = node id + row_offset);
+    `csr`: the graph (CSRGraph).  Returns (mean accuracy, best accuracy)."""
+    import torch
+    from shallow_encoders import _native as nat
+    from shallow_encoders.graph.edge_operators import edge_embeddings
+    dev = csr.device
+    embedding = embedding.to(dev, torch.float32).contiguous()
+    deg = (csr.rowptr[1:] - csr.rowptr[:-1])
+    src_all = torch.repeat_interleave(torch.arange(csr.n_nodes, device=dev), deg)
+    dst_all = csr.col_sorted.to(torch.int64)
+    keep = src_all <= dst_all                                      # each undirected edge once, like graph.edges
+    e_src, e_dst = src_all[keep], dst_all[keep]
+    n_edges = int(e_src.numel())
+    n_train = round(train_ratio * n_edges)
+    n_val = n_edges - n_train
+    gen = torch.Generator(device=dev)
+    total, best = 0.0, 0.0
+    for i in range(n_experiments):
+        gen.manual_seed(seed * 1_000_003 + i)
+        perm = torch.randperm(n_edges, generator=gen, device=dev)                       # random.shuffle(edges), :252
+        tr_pos = perm[:n_train]
+        neg_src, neg_dst = nat.sample_negative_edges(csr, n_train + n_val, seed * 7919 + i)
+        neg_src, neg_dst = neg_src.to(torch.int64), neg_dst.to(torch.int64)
+        tr_s = torch.cat([e_src[tr_pos], neg_src[:n_train]]) + row_offset
+        tr_d = torch.cat([e_dst[tr_pos], neg_dst[:n_train]]) + row_offset
+        all_s = torch.cat([e_src, neg_src]) + row_offset
+        all_d = torch.cat([e_dst, neg_dst]) + row_offset
+        X_train = edge_embeddings(embedding, tr_s, tr_d, edge_operator_name).cpu().numpy()
+        X = edge_embeddings(embedding, all_s, all_d, edge_operator_name).cpu().numpy()
+        y_train = np.array(n_train * [1] + n_train * [0], dtype=np.float32)
+        y = np.array(n_edges * [1] + (n_train + n_val) * [0], dtype=np.float32)
+        clf = LogisticRegression(**(classifier_params or {}))
+        clf.fit(X_train, y_train)
+        acc = float(np.equal(clf.predict(X), y).astype(np.float32).mean())
+        total += acc
+        best = max(best, acc)
+    return total / n_experiments, best

@@ -244,6 +244,27 @@ int se_host_sgns_update_tokens(const int32_t *tokens_host, int64_t n_seq, int se
                                const se_shard_spec *spec, int32_t *tokens_dev, double *stats_dev, double *stats_host,
                                void *stream);
 
+/* ------------------------------------------------------------------------------------------------------------
+ * Link-prediction features on device-resident embeddings (the evaluation step right after training).
+ * Replaces shallow_encoders/graph/edge_operators.py:10-64 (average, hadamard, weighted_l1, weighted_l2),
+ * create_edge_embeddings and sample_negative_edges (tools/graph_model_downstream_classification.py:170-224).
+ * ---------------------------------------------------------------------------------------------------------- */
+#define SE_EDGE_AVERAGE 0     /* (lhs + rhs) / 2 */
+#define SE_EDGE_HADAMARD 1    /* lhs * rhs */
+#define SE_EDGE_WEIGHTED_L1 2 /* |lhs - rhs| */
+#define SE_EDGE_WEIGHTED_L2 3 /* (lhs - rhs) ** 2 */
+
+/* out[i, :] = op(table[src_rows[i], :], table[dst_rows[i], :]);  table fp32 [vocab x emb], out fp32 [n_edges x emb]. */
+int se_edge_features(const float *table, int64_t vocab, int emb, const int64_t *src_rows, const int64_t *dst_rows,
+                     int64_t n_edges, int op, float *out, void *stream);
+/* out[i] = op(lhs[i], rhs[i]) on dense operands (what edge_operator_factory(name)(lhs, rhs) computes). */
+int se_edge_op(const float *lhs, const float *rhs, int64_t n_elems, int op, float *out, void *stream);
+/* n non-edges: node uniform over [0, n_nodes), partner uniform over the nodes that are not its neighbours (the node
+ * itself included, like the reference's set difference); col_sorted rows ascending; Philox(seed; sample_id_base + i, try).
+ * fail_count (int32[1], may be NULL) counts samples that found no non-neighbour in 4096 tries (complete graphs). */
+int se_sample_negative_edges(const int64_t *rowptr, const int32_t *col_sorted, int64_t n_nodes, int64_t n, uint64_t seed,
+                             int64_t sample_id_base, int32_t *out_src, int32_t *out_dst, int32_t *fail_count, void *stream);
+
 /* Table utilities that work on local and sharded tables alike (W2VBase.__init__ xavier_uniform_, word2vec/model.py:22-27;
  * the input_embedding / output_embedding accessors, :29-47).
  *   fill: element i = (2u-1)*bound with u from Philox(seed; i/4) -- independent of the sharding; a rank writes only the

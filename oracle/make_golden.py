@@ -12,6 +12,8 @@ Everything written here is produced by the reference's own code:
              (word2vec/model.py:79-91, word2vec/loss.py:14-22) and Word2VecTrainer.training_step
              (word2vec/trainer.py:131-152) with `generate_noise_batch` pinned to a recorded tensor
   vocab_*    GraphDataset vocabulary order           (torch_dataset.py:99-110)
+  edge_ops   the four edge operators                 (graph/edge_operators.py:10-64) applied the way
+             create_edge_embeddings does (tools/graph_model_downstream_classification.py:203-224)
 
 Versions used for the committed fixtures are stored inside each file (`meta`).
 """
@@ -268,10 +270,39 @@ def emit_vocab():
     print('vocab OK', itos[:3], tri.vocab.get_itos())
 
 
+def emit_edge_ops():
+    """Edge features of a random embedding table for a random edge list, computed by the reference's own operators."""
+    from shallow_encoders.graph import edge_operators as ref_ops       # the reference's module
+    from oracle import edge_oracle
+    assert ref_ops.__file__.startswith(ref_import.REFERENCE_ROOT), ref_ops.__file__
+    rng = np.random.default_rng(123)
+    out = {}
+    for emb in (2, 8, 100, 128):
+        table = (rng.standard_normal((120, emb)) * 0.7).astype(np.float32)
+        edges = rng.integers(0, 120, (150, 2))
+        edges[:5, 1] = edges[:5, 0]                                     # self pairs
+        out[f'table_{emb}'] = table
+        out[f'edges_{emb}'] = edges.astype(np.int64)
+        for name in ('average', 'hadamard', 'weighted_l1', 'weighted_l2'):
+            op = ref_ops.edge_operator_factory(name)
+            ref = np.stack([op(table[s, :], table[e, :]) for s, e in edges])     # create_edge_embeddings, :219-224
+            assert ref.dtype == np.float32
+            assert np.array_equal(ref, edge_oracle.edge_embeddings(table, edges, name)), name
+            out[f'{name}_{emb}'] = ref
+    try:
+        ref_ops.edge_operator_factory('cosine')
+        raise RuntimeError('reference accepted an unknown operator')
+    except AssertionError as e:
+        out['unknown_operator_message'] = np.array(str(e))
+    np.savez_compressed(os.path.join(GOLDEN, 'edge_ops.npz'), meta=np.array(META), **out)
+    print('edge_ops: 4 operators x 4 embedding sizes')
+
+
 if __name__ == '__main__':
     os.makedirs(GOLDEN, exist_ok=True)
     emit_walks()
     emit_collate()
     emit_sgns()
     emit_vocab()
+    emit_edge_ops()
     print('golden fixtures written to', GOLDEN)

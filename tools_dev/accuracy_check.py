@@ -14,7 +14,7 @@ import torch
 from oracle import cpu_port
 from shallow_encoders.config_parser import load_config
 from shallow_encoders.config_parser.core import instantiate
-from tools.downstream import node_classification
+from tools.downstream import edge_classification, node_classification
 from tools.train import train
 
 CASES = {
@@ -31,7 +31,7 @@ if len(sys.argv) > 1:
 out = {}
 workers = os.cpu_count() or 1
 for name, (yaml_name, common, fused_over, seeds, n_exp) in CASES.items():
-    res = {'cpu_port': [], 'b200_reference_engine': [], 'b200_fused_engine': []}
+    res = {'cpu_port': [], 'b200_reference_engine': [], 'b200_fused_engine': [], 'b200_fused_engine_edge_classification': []}
     for seed in range(seeds):
         base = common + [f'path.output_dir=/tmp/se_acc/{name}_{seed}']
         cfg = load_config(yaml_name, base)
@@ -58,8 +58,13 @@ for name, (yaml_name, common, fused_over, seeds, n_exp) in CASES.items():
             acc = node_classification(tr.model.input_embedding.numpy(), ds2.vocab.get_itos(), ds2.labels,
                                       instantiate(nc['split_algorithm']), n_exp, nc.get('classifier_params'))
             res[key].append(acc[0])
+            ec = cfg.downstream.get('edge_classification')
+            if key == 'b200_fused_engine' and ec:       # link prediction on the same embeddings (reference README: karate 69.5 %, triplets 85.8 %, real Cora 81.7 %)
+                eacc = edge_classification(tr.model.tables[0], ds2._dataset.walk_generator.csr, ec['train_ratio'], min(ec['n_experiments'], 20),
+                                           ec['operator_name'], ec.get('classifier_params'), seed=seed)
+                res['b200_fused_engine_edge_classification'].append(eacc[0])
         print(name, seed, {k: round(v[-1], 4) for k, v in res.items()}, f'cpu {t1 - t0:.0f}s gpu {time.time() - t1:.0f}s', flush=True)
-    out[name] = {k: {'mean': float(np.mean(v)), 'std': float(np.std(v)), 'runs': v} for k, v in res.items()}
+    out[name] = {k: {'mean': float(np.mean(v)), 'std': float(np.std(v)), 'runs': v} for k, v in res.items() if v}
     out[name]['delta_reference_engine_pp'] = 100 * (out[name]['b200_reference_engine']['mean'] - out[name]['cpu_port']['mean'])
     out[name]['delta_fused_engine_pp'] = 100 * (out[name]['b200_fused_engine']['mean'] - out[name]['cpu_port']['mean'])
     out[name]['settings'] = {'yaml': yaml_name, 'overrides': common, 'fused_overrides': fused_over, 'seeds': seeds, 'n_experiments': n_exp}
