@@ -61,3 +61,17 @@ for name, flags in [('red', nat.SCATTER_RED), ('store', nat.SCATTER_STORE), ('ge
     print(f'sgns {name:14s}: {ms:8.3f} ms  {pairs / ms / 1e6:8.2f} M pairs/s  {pairs * bpp / ms / 1e6:8.1f} GB/s algorithmic '
           f'({pairs * bpp / ms / 1e6 / 6450.6 * 100:.1f}% of 6450.6)', flush=True)
 print('tables GB', 2 * vocab * args.emb * 4 / 1e9)
+
+# ---- link-prediction features: fused gather + operator, 3 * 4E bytes per edge (two random row reads, one streamed write) --------------
+n_e = min(csr.nnz, 20_000_000)
+deg = csr.rowptr[1:] - csr.rowptr[:-1]
+e_src = torch.repeat_interleave(torch.arange(csr.n_nodes, device=dev), deg)[:n_e] + 1
+e_dst = csr.col_sorted[:n_e].to(torch.int64) + 1
+perm = torch.randperm(n_e, device=dev)          # random edge order: both row reads are random, as for sampled edge lists
+e_src, e_dst = e_src[perm].contiguous(), e_dst[perm].contiguous()
+for op in ('hadamard', 'weighted_l2'):
+    ms = timed(lambda i: nat.edge_features(w_in, e_src, e_dst, op), args.iters)
+    gbs = n_e * 3 * 4 * args.emb / ms / 1e6
+    print(f'edge_features {op:12s}: {ms:8.3f} ms  {n_e / ms / 1e6:8.3f} G edges/s  {gbs:8.1f} GB/s algorithmic ({gbs / 6450.6 * 100:.1f}% of 6450.6)', flush=True)
+ms = timed(lambda i: nat.sample_negative_edges(csr, n_e, seed=i), args.iters)
+print(f'negative edges       : {ms:8.3f} ms  {n_e / ms / 1e6:8.3f} G samples/s', flush=True)
