@@ -361,13 +361,11 @@ sgns_fast_kernel(const SgnsArgs a) {
         const int cnt = min(CH, T - t0);
         int my = -1;
         const int tj = t0 + lane;
-        const bool negative_lane = lane < cnt && tj > 0 && !explicit_noise;
-        if (K > 0 && !explicit_noise && (!cache_words || (n & 3) == 0 || n == 0)) {
-            if (!cache_words || negative_lane || true) {
-                const uint64_t cid = (uint64_t)(a.id_base + u);
-                w_bucket = neg_words(a.seed, cid, n, max(tj - 1, 0), STREAM_NEG);
-                if (a.alias_prob) w_coin = neg_words(a.seed, cid, n, max(tj - 1, 0), STREAM_NEG_COIN);
-            }
+        // all lanes refresh together (the words are cached across calls, so no lane may skip a refresh it will need later)
+        if (K > 0 && !explicit_noise && (!cache_words || (n & 3) == 0)) {
+            const uint64_t cid = (uint64_t)(a.id_base + u);
+            w_bucket = neg_words(a.seed, cid, n, max(tj - 1, 0), STREAM_NEG);
+            if (a.alias_prob) w_coin = neg_words(a.seed, cid, n, max(tj - 1, 0), STREAM_NEG_COIN);
         }
         if (lane < cnt) {
             if (tj == 0) {

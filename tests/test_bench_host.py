@@ -1,0 +1,48 @@
+"""Host-side logic of bench.py (no GPU): algorithmic byte counts, configuration strings, the reference-arm line."""
+import json
+import subprocess
+import sys
+import os
+
+import bench
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+
+
+def _args(argv):
+    old = sys.argv
+    sys.argv = ['bench.py'] + argv
+    try:
+        return bench.parse_args()
+    finally:
+        sys.argv = old
+
+
+def test_algorithmic_bytes_per_pair():
+    # 2 * 4E * (1 + K + 1/N) = 6246.4 B at E=128, K=5, N=10; window kernel: 2 * 4E * (K + 2/N) = 5324.8 B
+    assert abs(bench.bytes_per_pair(128, 5, 5) - 6246.4) < 1e-9
+    assert abs(bench.bytes_per_pair(128, 5, 5, window=True) - 5324.8) < 1e-9
+    assert abs(bench.bytes_per_pair(128, 5, 2) - 6400.0) < 1e-9
+    assert abs(bench.bytes_per_pair(48, 3, 5) - 1574.4) < 1e-9
+
+
+def test_workload_config_names_the_parallelism():
+    a = _args(['--gpus', '8'])
+    cfg = bench.workload_config(a, 8)
+    assert cfg['nodes'] == 10_000_000 and cfg['edges'] == 250_000_000 and cfg['walk_len'] == 80 and cfg['emb'] == 128
+    assert 'row-striped' in cfg['parallelism'] and 'rows each GPU owns' in cfg['parallelism']
+    assert 'owned by the GPU' in cfg['negative_sampling']
+    a = _args(['--gpus', '2', '--negatives', 'global'])
+    assert 'uniform (reference)' == bench.workload_config(a, 2)['negative_sampling']
+    a = _args(['--gpus', '2', '--multi', 'a2a'])
+    assert 'NCCL BASELINE' in bench.workload_config(a, 2)['parallelism']
+    assert bench.workload_config(_args([]), 1)['parallelism'] == 'single GPU'
+
+
+def test_reference_arm_prints_one_json_line_on_a_tiny_sample():
+    out = subprocess.run([sys.executable, os.path.join(ROOT, 'bench.py'), '--impl', 'reference', '--steps', '1', '--warmup', '1', '--cpu-nodes', '2000',
+                          '--cpu-walks-per-step', '8', '--walk-len', '12', '--emb', '16'], capture_output=True, text=True, timeout=600)
+    assert out.returncode == 0, out.stderr[-2000:]
+    line = json.loads(out.stdout.strip().splitlines()[-1])
+    assert line['impl'] == 'reference' and line['metric'] == 'sgns_pairs_per_s' and line['value'] > 0
+    assert line['cpu_baseline']['kind'] == 'port' and line['e2e']['h2d_bytes_per_step'] == 0 and line['gpu_launches'] == 0
