@@ -27,13 +27,13 @@ ap = argparse.ArgumentParser()
 ap.add_argument('--nodes', type=int, default=200_000)
 ap.add_argument('--edges', type=int, default=2_000_000)
 ap.add_argument('--blocks', type=int, default=20)
-ap.add_argument('--p-in', type=float, default=0.15)
+ap.add_argument('--p-in', type=float, default=0.3)
 ap.add_argument('--emb', type=int, default=128)
 ap.add_argument('--walk-len', type=int, default=40)
 ap.add_argument('--walks-per-node', type=int, default=10)
 ap.add_argument('--radius', type=int, default=5)
 ap.add_argument('--neg', type=int, default=5)
-ap.add_argument('--epochs', type=int, default=1)
+ap.add_argument('--epochs', type=int, default=2)
 ap.add_argument('--lr', type=float, default=0.025)
 ap.add_argument('--batch-walks', type=int, default=65536)
 a = ap.parse_args()
@@ -96,7 +96,8 @@ if rank == 0:
     t0 = time.time()
     losses = train(w_in, w_out, 0, 1, False)
     torch.cuda.synchronize()
-    out['one_gpu_global_negatives'] = {'accuracy': evaluate(w_in), 'epoch_losses': losses, 'seconds': time.time() - t0}
+    secs = time.time() - t0
+    out['one_gpu_global_negatives'] = {'accuracy': evaluate(w_in), 'epoch_losses': losses, 'seconds': secs}
     print('1 GPU', out['one_gpu_global_negatives'], flush=True)
     del w_in, w_out
 barrier()
