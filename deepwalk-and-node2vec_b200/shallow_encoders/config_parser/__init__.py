@@ -1,1 +1,2 @@
-from shallow_encoders.config_parser.core import GlobalConfig, load_config  # noqa: F401
+"""YAML experiment configs -> dataclasses and object factories (see core.py)."""
+from .core import GlobalConfig, load_config  # noqa: F401
