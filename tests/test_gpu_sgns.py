@@ -305,7 +305,7 @@ def test_fast_and_generic_kernels_agree(emb, radius, k):
     assert checked >= 1
 
 
-@pytest.mark.parametrize('emb,radius,k,length,n_seq', [(128, 5, 5, 80, 300), (128, 2, 3, 10, 700), (96, 3, 2, 9, 50), (128, 1, 7, 3, 40), (128, 8, 1, 40, 9)])
+@pytest.mark.parametrize('emb,radius,k,length,n_seq', [(128, 5, 5, 80, 300), (128, 2, 3, 10, 700), (96, 3, 2, 9, 50), (128, 1, 7, 3, 40), (128, 8, 1, 40, 9), (128, 9, 2, 25, 30)])
 def test_window_resident_kernel_equals_sequential_oracle(emb, radius, k, length, n_seq):
     """sgns_win_kernel keeps the context rows of the window in shared memory and scatters each token's accumulated update
     once, when it leaves the window.  The result must equal a SEQUENTIAL oracle (up to the staleness of concurrent warps):

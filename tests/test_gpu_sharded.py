@@ -60,6 +60,27 @@ def test_fill_is_independent_of_sharding_and_rows_round_trip():
     one.close()
 
 
+def test_empty_inputs_are_no_ops_on_the_new_entry_points():
+    dev = cuda_device()
+    t = ShardedTable(5000, 128, dev)
+    t.fill_uniform(0.1, 3)
+    before = t.to_tensor().clone()
+    other = ShardedTable(5000, 128, dev)
+    st = nat.sgns_update_walks(t, other, torch.empty((0, 12), dtype=torch.int32, device=dev), 2, 3, 1, 0.1, 1)
+    assert st['pairs'] == 0 and torch.equal(t.to_tensor(), before)
+    assert t.gather(torch.empty(0, dtype=torch.int64, device=dev)).shape == (0, 128)
+    t.scatter(torch.empty(0, dtype=torch.int64, device=dev), torch.empty((0, 128), device=dev))
+    dense = before.clone()
+    assert nat.edge_features(dense, torch.empty(0, dtype=torch.int64, device=dev), torch.empty(0, dtype=torch.int64, device=dev), 'hadamard').shape == (0, 128)
+    # sequences shorter than a window are refused exactly like the reference's collate assert (torch_dataset.py:298)
+    with pytest.raises(AssertionError, match='Text is too short'):
+        nat.sgns_update_walks(t, other, torch.zeros((4, 4), dtype=torch.int32, device=dev), 2, 3, 1, 0.1, 1)
+    # mixing a striped and a torch table is refused
+    with pytest.raises(ValueError):
+        nat.sgns_update_walks(t, dense, torch.zeros((4, 12), dtype=torch.int32, device=dev), 2, 3, 1, 0.1, 1)
+    t.close(); other.close()
+
+
 def _collision_free_case(rng, emb, radius, k, n_seq, vocab, offset, neg_fn):
     length = 2 * radius + 1
     tokens = rng.permutation(vocab - offset)[:n_seq * length].reshape(n_seq, length).astype(np.int32)
