@@ -70,8 +70,9 @@ def parse_args():
     ap.add_argument('--multi', default='sharded', choices=['sharded', 'replicas', 'a2a'],
                     help='N > 1: sharded = one striped table pair over NVLink peer memory (product); a2a = the NCCL all-to-all baseline; replicas')
     ap.add_argument('--a2a-micro-walks', type=int, default=8192, help='a2a baseline: walks per exchange micro-batch')
-    ap.add_argument('--negatives', default='auto', choices=['auto', 'local', 'global'],
-                    help='sharded tables: draw negatives among the rows the GPU owns (auto = local) or over the whole table')
+    ap.add_argument('--negatives', default='auto', choices=['auto', 'local', 'global', 'owner'],
+                    help='sharded tables: local (auto) = draw negatives among the rows the GPU owns; global = reference draw over the whole table, rows '
+                         'fetched over NVLink; owner = reference draw, every GPU processes the negatives it owns for all GPUs\' centres')
     ap.add_argument('--tables', default='torch', choices=['torch', 'vmm'], help='N = 1: torch tensor or a 1-shard VMM table')
     ap.add_argument('--extra-steps', type=int, default=5, help='sharded: steps of the other negative mode timed after the main run')
     ap.add_argument('--no-cpu-baseline', action='store_true')
@@ -86,14 +87,16 @@ def parallelism(a, n_gpus):
         return 'single GPU' + (' (tables in a 1-shard VMM mapping)' if a.tables == 'vmm' else '')
     if a.multi == 'replicas':
         return f'dp{n_gpus}: walks sharded by id, table replicas averaged by NCCL all-reduce every step'
-    neg = 'global' if a.negatives == 'global' else 'local'
+    neg = 'local' if a.negatives == 'auto' else a.negatives
     if a.multi == 'a2a':
         return (f'dp{n_gpus} NCCL BASELINE: tables row-sharded by row % {n_gpus}; per micro-batch of {a.a2a_micro_walks} walks: unique ids -> '
                 f'all_to_all ids / rows -> se_sgns_grad on compact tables -> all_to_all gradients -> owners apply; negatives '
                 + ('among the rows each GPU owns' if neg == 'local' else 'uniform over the whole table (reference)'))
     return (f'dp{n_gpus}: walks sharded by id (replicated CSR, no communication); ONE pair of tables row-striped (2 MiB stripes) over '
             f'{n_gpus} HBMs, fused kernel gathers / red.adds peer rows over NVLink; negatives drawn '
-            + ('among the rows each GPU owns' if neg == 'local' else 'uniformly over the whole table (reference)'))
+            + {'local': 'among the rows each GPU owns', 'global': 'uniformly over the whole table (reference)',
+               'owner': 'uniformly over the whole table (reference), processed by the GPU that owns the negative row (walks all-gathered, '
+                        'centre rows read / updated over NVLink)'}[neg])
 
 
 def workload_config(a, n_gpus):
@@ -103,7 +106,7 @@ def workload_config(a, n_gpus):
         'walk_len': a.walk_len, 'walks_per_node': a.walks_per_node, 'walks_per_step_per_gpu': a.walks_per_step,
         'emb': a.emb, 'context_radius': a.radius, 'negatives': a.neg,
         'negative_sampling': ('uniform over the rows owned by the GPU (walks are dealt to GPUs by id)'
-                              if (n_gpus > 1 and a.multi in ('sharded', 'a2a') and a.negatives != 'global') else 'uniform (reference)'),
+                              if (n_gpus > 1 and a.multi in ('sharded', 'a2a') and a.negatives in ('auto', 'local')) else 'uniform (reference)'),
         'optimizer': 'in-place SGD (Hogwild, red.global.add.v4.f32)' if a.scatter == 'red' else 'in-place SGD (Hogwild, plain stores)',
         'parallelism': parallelism(a, n_gpus),
         'l2': 'inputs exceed L2 (tables 2 x %.2f GB, CSR ~%.1f GB); no flush' % ((a.nodes + 1) * a.emb * 4 / 1e9, (2 * a.edges * 4 + a.nodes * 8) / 1e9),
@@ -273,7 +276,11 @@ def run_b200(a, rank, local_rank, world):
     fallback_note = None
     sharded = (world > 1 and a.multi == 'sharded') or (world == 1 and a.tables == 'vmm')
     a2a = world > 1 and a.multi == 'a2a'
-    local_neg = (sharded or a2a) and world > 1 and a.negatives != 'global'
+    neg_mode = 'global'
+    if (sharded or a2a) and world > 1:
+        neg_mode = 'local' if a.negatives == 'auto' else a.negatives
+        assert not (a2a and neg_mode == 'owner'), 'the NCCL baseline has no owner-computes mode'
+    local_neg = neg_mode == 'local'
     if a2a:
         from shallow_encoders.word2vec.row_exchange import RowShardedTables
         tables = RowShardedTables(vocab, a.emb, rank, world, dev)
@@ -301,7 +308,7 @@ def run_b200(a, rank, local_rank, world):
             for t in (w_in, w_out):
                 if t is not None:
                     t.close()
-            sharded, local_neg, fallback_note = False, False, f'striped tables unavailable ({why or "on another rank"}): ran --multi replicas'
+            sharded, local_neg, neg_mode, fallback_note = False, False, 'global', f'striped tables unavailable ({why or "on another rank"}): ran --multi replicas'
             a.multi = 'replicas'
             w_in = torch.empty((vocab, a.emb), dtype=torch.float32, device=dev)
             w_out = torch.empty((vocab, a.emb), dtype=torch.float32, device=dev)
@@ -316,7 +323,7 @@ def run_b200(a, rank, local_rank, world):
         flags |= nat.NO_WINDOW
 
     # ---- schedule: shuffled node list, walks_per_node consecutive walks per node (graph/datasets.py:45,76) -----
-    total_steps = a.warmup + 2 * a.steps + 2 + a.extra_steps + 1
+    total_steps = a.warmup + 2 * a.steps + 2 + 2 * (a.extra_steps + 1)
     n_walks = a.walks_per_step
     g_cpu = torch.Generator()
     g_cpu.manual_seed(a.seed)
@@ -345,7 +352,22 @@ def run_b200(a, rank, local_rank, world):
     ev = lambda: torch.cuda.Event(enable_timing=True)   # noqa: E731
     sgns_events, walk_events = [], []
 
-    def device_step(step, record=False, local=local_neg):
+    gather_buf = torch.empty((world * n_walks, a.walk_len), dtype=torch.int32, device=dev) if sharded and world > 1 else None
+
+    def sgns_stage(base, step, mode):
+        if a2a:
+            tables.step(walks, a.radius, a.neg, 1, a.lr, a.seed + 1, draw_id_base=base * n_cen * 2 * a.radius * a.neg,
+                        micro_walks=a.a2a_micro_walks, local_negatives=mode == 'local', stats=stats)
+        elif mode == 'owner':
+            from shallow_encoders.word2vec.sharded import sgns_update_walks_owner_computes
+            sgns_update_walks_owner_computes(w_in, w_out, walks, a.radius, a.neg, 1, a.lr, a.seed + 1, step * world * n_walks * n_cen,
+                                             rank, world, stats=stats, gather_buf=gather_buf)
+        else:
+            nat.sgns_update_walks(w_in, w_out, walks, a.radius, a.neg, 1, a.lr, a.seed + 1, centre_id_base=base * n_cen,
+                                  flags=flags, stats=stats, local_negatives=mode == 'local')
+
+    def device_step(step, record=False, mode=None):
+        mode = neg_mode if mode is None else mode
         st, base = dev_starts[step]
         if record:
             e0, e1, e2 = ev(), ev(), ev()
@@ -353,12 +375,7 @@ def run_b200(a, rank, local_rank, world):
         nat.walk(csr, st, a.walk_len, a.p, a.q, True, nat.RULE_REFERENCE, a.seed, walk_id_base=base, out=walks)
         if record:
             e1.record()
-        if a2a:
-            tables.step(walks, a.radius, a.neg, 1, a.lr, a.seed + 1, draw_id_base=base * n_cen * 2 * a.radius * a.neg,
-                        micro_walks=a.a2a_micro_walks, local_negatives=local, stats=stats)
-        else:
-            nat.sgns_update_walks(w_in, w_out, walks, a.radius, a.neg, 1, a.lr, a.seed + 1, centre_id_base=base * n_cen,
-                                  flags=flags, stats=stats, local_negatives=local)
+        sgns_stage(base, step, mode)
         if record:
             e2.record()
             walk_events.append((e0, e1))
@@ -367,12 +384,11 @@ def run_b200(a, rank, local_rank, world):
 
     def host_step(step):
         st, base = pinned[step]
-        if a2a:     # baseline: the same host-buffer contract assembled from the device calls
+        if a2a or neg_mode == 'owner':     # a collective sits inside the step: the host-buffer contract assembled from the device calls
             scratch['starts'].copy_(st, non_blocking=True)
             stats.zero_()
             nat.walk(csr, scratch['starts'], a.walk_len, a.p, a.q, True, nat.RULE_REFERENCE, a.seed, walk_id_base=base, out=walks)
-            tables.step(walks, a.radius, a.neg, 1, a.lr, a.seed + 1, draw_id_base=base * n_cen * 2 * a.radius * a.neg,
-                        micro_walks=a.a2a_micro_walks, local_negatives=local_neg, stats=stats)
+            sgns_stage(base, step, neg_mode)
             stats_host.copy_(stats)
             torch.cuda.synchronize()
             return
@@ -436,19 +452,22 @@ def run_b200(a, rank, local_rank, world):
     # ---- sharded tables: the other negative-sampling mode, a few steps, reported beside the headline -------------
     other = None
     if (sharded or a2a) and world > 1 and a.extra_steps > 0:
-        first = a.warmup + 2 * a.steps + 1
-        device_step(first, local=not local_neg)
-        barrier()
-        x0, x1 = ev(), ev()
-        x0.record()
-        for s in range(first + 1, first + 1 + a.extra_steps):
-            device_step(s, local=not local_neg)
-        x1.record()
-        barrier()
-        other_ms = max_over_ranks(x0.elapsed_time(x1))
-        other = {'negatives': 'global (uniform over the whole table, reference)' if local_neg else 'local',
-                 'value': world * pairs_per_step * a.extra_steps / (other_ms / 1e3), 'unit': UNIT, 'steps': a.extra_steps,
-                 'ms_per_step': other_ms / a.extra_steps}
+        names = {'local': 'local (rows the GPU owns)', 'global': 'global (reference draw, negative rows fetched over NVLink)',
+                 'owner': 'global, owner-computes (reference draw, centre rows travel instead of negative rows)'}
+        other, first = [], a.warmup + 2 * a.steps + 1
+        for mode in [m for m in (('local', 'global') if a2a else ('local', 'global', 'owner')) if m != neg_mode]:
+            device_step(first, mode=mode)
+            barrier()
+            x0, x1 = ev(), ev()
+            x0.record()
+            for s in range(first + 1, first + 1 + a.extra_steps):
+                device_step(s, mode=mode)
+            x1.record()
+            barrier()
+            other_ms = max_over_ranks(x0.elapsed_time(x1))
+            other.append({'negatives': names[mode], 'value': world * pairs_per_step * a.extra_steps / (other_ms / 1e3), 'unit': UNIT,
+                          'steps': a.extra_steps, 'ms_per_step': other_ms / a.extra_steps})
+            first += a.extra_steps + 1
 
     if rank != 0:
         if world > 1:
@@ -494,7 +513,7 @@ def run_b200(a, rank, local_rank, world):
     if fallback_note:
         line['multi_gpu_fallback'] = fallback_note
     if other is not None:
-        line['sharded_other_negative_mode'] = other
+        line['sharded_other_negative_modes'] = other
     if a2a:
         line['a2a'] = {'micro_walks': a.a2a_micro_walks, 'exchanged_bytes_sent_per_rank': tables.exchanged_bytes}
     if sharded:

@@ -89,6 +89,7 @@ struct SgnsArgs {
     int neg_shift, neg_world, neg_rank;
     int sys_scope;                       // rows may live in peer HBM: system-scope reductions
     int no_window;                       // SE_SGNS_NO_WINDOW: per-context kernel instead of the window-resident one
+    int own_shift;                       // sgns_negown_kernel: log2(stripe_rows); row r is owned by (r >> own_shift) % neg_world
 };
 
 // in-kernel negative: uniform / alias draw, then (local negatives) local id -> row of the stripe this rank owns
@@ -941,6 +942,155 @@ int launch_win(const SgnsArgs &a, cudaStream_t stream) {
     return a.emb == 128 ? launch_win_t<true>(a, stream) : launch_win_t<false>(a, stream);
 }
 
+
+// ------------------------------------------------------------------------------------------------------------------
+// Owner-computes negatives (striped tables, the reference's GLOBAL negative distribution).  Fetching the K negative rows
+// of a pair from their owners costs K rows each way over NVLink (measured: ~0.2 G pairs/s per GPU).  Here the centre row
+// travels instead: every GPU walks over the centres of ALL GPUs' walks (tokens are all-gathered, 4 bytes per centre),
+// re-draws each centre's N*K negatives from the same Philox keys as the single-GPU kernel, keeps the ones whose rows it
+// OWNS, and for those computes dot / sigmoid / update against its local HBM; the centre row is read once per centre
+// (peer load) and the centre's accumulated gradient goes back with one peer red.add -- 2 rows per centre per GPU over
+// NVLink instead of 2*N*K.  Positive pairs are done by the walk's home GPU (sgns_win_kernel with K = 0).  Lane l < NG*K
+// draws the ids of negative (l % K) for the four contexts of group (l / K) with ONE Philox call, exactly the keying of
+// `neg_words`; owned ids are compacted into a per-warp list and processed eight rows at a time.
+// ------------------------------------------------------------------------------------------------------------------
+template <bool EXACT>
+__global__ void __launch_bounds__(SGNS_THREADS, 2)
+sgns_negown_kernel(const SgnsArgs a) {
+    constexpr int P = 8, SHIFT = 2;
+    __shared__ int own_list[SGNS_THREADS / 32][64];
+    __shared__ double sred[SE_STATS_LEN];
+    const int lane = threadIdx.x & 31;
+    int *list = own_list[threadIdx.x >> 5];
+    const int64_t gid = (int64_t)blockIdx.x * (SGNS_THREADS / 32) + (threadIdx.x >> 5);
+    const int64_t n_groups = (int64_t)gridDim.x * (SGNS_THREADS / 32);
+    const int E = EXACT ? 128 : a.emb;
+    const int eoff = lane * 4;
+    const bool ok = EXACT || eoff < E;
+    const int N = a.n_ctx, K = a.n_neg, NG = (a.n_ctx + 3) >> 2;
+    const int l_g = lane / K, l_k = lane - l_g * K;
+    const bool drawer = lane < NG * K;
+    const int owner_t = lane >> SHIFT;
+    const bool owner_rep = (lane & 3) == 0;
+    const uint32_t world = (uint32_t)a.neg_world, me = (uint32_t)a.neg_rank;
+    const int shift = a.own_shift;
+
+    float loss_neg = 0.f;
+    unsigned cnt_fp = 0, cnt_neg = 0;
+
+    const int64_t span = (a.n_units + n_groups - 1) / n_groups;
+    const int64_t u_end = min(a.n_units, gid * span + span);
+    for (int64_t u = gid * span; u < u_end; ++u) {
+        // ---- which of this centre's N*K negatives live in my HBM? --------------------------------------------------
+        int ids[4] = {0, 0, 0, 0};
+        bool own[4] = {false, false, false, false};
+        if (drawer) {
+            const uint64_t cid = (uint64_t)(a.id_base + u);
+            const uint4 wb = neg_words(a.seed, cid, l_g * 4, l_k, STREAM_NEG);
+            uint4 wc = make_uint4(0, 0, 0, 0);
+            if (a.alias_prob) wc = neg_words(a.seed, cid, l_g * 4, l_k, STREAM_NEG_COIN);
+#pragma unroll
+            for (int j = 0; j < 4; ++j) {
+                if (l_g * 4 + j < N) {
+                    const uint32_t id = (uint32_t)draw_row(a.alias_prob, a.alias_idx, (uint32_t)a.vocab, pick_word(wb, j), pick_word(wc, j));
+                    ids[j] = (int)id;
+                    own[j] = ((id >> shift) % world) == me;
+                }
+            }
+        }
+        const int cnt = (int)own[0] + (int)own[1] + (int)own[2] + (int)own[3];
+        int incl = cnt;
+#pragma unroll
+        for (int off = 1; off < 32; off <<= 1) {
+            const int v = __shfl_up_sync(FULL, incl, off);
+            if (lane >= off) incl += v;
+        }
+        const int total = __shfl_sync(FULL, incl, 31);
+        if (total == 0) continue;
+        __syncwarp();
+        {
+            int pos = incl - cnt;
+#pragma unroll
+            for (int j = 0; j < 4; ++j) if (own[j]) list[pos++] = ids[j];
+        }
+        __syncwarp();
+
+        const int64_t sq = u / a.n_cen;
+        const int64_t crow = (int64_t)__ldg(a.tokens + sq * a.seq_len + a.radius + (int)(u - sq * a.n_cen)) + a.row_offset;
+        float cen[4] = {0.f, 0.f, 0.f, 0.f}, acc[4] = {0.f, 0.f, 0.f, 0.f};
+        if (ok) load_vec<4>(a.w_in + crow * E + eoff, cen);
+
+        for (int c0 = 0; c0 < total; c0 += P) {
+            const int m = min(P, total - c0);
+            int tid[P];
+            float row[P][4];
+            float dot[P];
+#pragma unroll
+            for (int t = 0; t < P; ++t) tid[t] = (t < m) ? list[c0 + t] : 0;
+#pragma unroll
+            for (int t = 0; t < P; ++t) {
+                row[t][0] = row[t][1] = row[t][2] = row[t][3] = 0.f;
+                if (t < m && ok) load_vec<4>(a.w_out + (int64_t)tid[t] * E + eoff, row[t]);
+            }
+#pragma unroll
+            for (int t = 0; t < P; ++t) {
+                float d = 0.f;
+#pragma unroll
+                for (int e = 0; e < 4; ++e) d = fmaf(row[t][e], cen[e], d);
+                dot[t] = d;
+            }
+            const float sc = transposed_reduce<P>(dot, lane);
+            float step_mine = 0.f;
+            if (owner_t < m) {
+                const float x = -sc;                                          // loss = -log clamp(sigmoid(-s), 1e-6)   (loss.py:16)
+                const float ex = __expf(-x);
+                const float sig = __fdividef(1.0f, 1.0f + ex);
+                const float gmag = (sig > CLAMP_MIN) ? ex * sig : 0.f;        // dL/ds = sigmoid(s)
+                step_mine = -a.lr * gmag;
+                if (owner_rep) { loss_neg -= __logf(fmaxf(sig, CLAMP_MIN)); cnt_fp += x <= 0.f; cnt_neg += 1; }
+            }
+#pragma unroll
+            for (int t = 0; t < P; ++t) {
+                const float step = __shfl_sync(FULL, step_mine, t << SHIFT);
+                if (t < m) {
+                    float d[4];
+#pragma unroll
+                    for (int e = 0; e < 4; ++e) { acc[e] = fmaf(step, row[t][e], acc[e]); d[e] = step * cen[e]; }
+                    if (ok) red_vec<4>(a.w_out + (int64_t)tid[t] * E + eoff, d, false);      // my own HBM: device scope is enough
+                }
+            }
+        }
+        if (ok) red_vec<4>(a.w_in + crow * E + eoff, acc, a.sys_scope);
+    }
+
+    if (threadIdx.x < SE_STATS_LEN) sred[threadIdx.x] = 0.0;
+    __syncthreads();
+    if (cnt_neg != 0) {
+        atomicAdd(&sred[1], (double)loss_neg);
+        atomicAdd(&sred[3], (double)cnt_fp);
+        atomicAdd(&sred[5], (double)cnt_neg);
+    }
+    __syncthreads();
+    if (threadIdx.x < SE_STATS_LEN && a.stats && sred[threadIdx.x] != 0.0) atomicAdd(a.stats + threadIdx.x, sred[threadIdx.x]);
+}
+
+template <bool EXACT>
+int launch_negown(const SgnsArgs &a, cudaStream_t stream) {
+    auto kern = sgns_negown_kernel<EXACT>;
+    int occ = 0;
+    if (check_cuda(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, kern, SGNS_THREADS, 0), "occupancy") != SE_OK) return SE_ERR_CUDA;
+    if (occ < 1) occ = 1;
+    const int sms = sm_count();
+    if (sms <= 0) return SE_ERR_CUDA;
+    constexpr int GPB = SGNS_THREADS / 32;
+    int64_t blocks = (a.n_units + GPB - 1) / GPB;
+    const int64_t cap = (int64_t)sms * occ;
+    if (blocks > cap) blocks = cap;
+    if (blocks < 1) blocks = 1;
+    kern<<<(int)blocks, SGNS_THREADS, 0, stream>>>(a);
+    return check_cuda(cudaGetLastError(), "sgns_negown_kernel launch");
+}
+
 template <int MODE, int T, bool EXACT>
 int launch_ctx_one(const SgnsArgs &a, cudaStream_t stream) {
     auto kern = sgns_ctx_kernel<MODE, T, EXACT>;
@@ -1288,6 +1438,41 @@ extern "C" int se_sgns_update_walks_sharded(float *w_in, float *w_out, int64_t v
     SE_REQUIRE(!(a.sys_scope && a.scatter_store), "se_sgns_update_walks_sharded: plain-store scatter is not supported on "
                "sharded tables (updates of other GPUs would be lost); use SE_SGNS_SCATTER_RED");
     return se::launch<se::MODE_WALK>(a, (cudaStream_t)stream);
+}
+
+extern "C" int se_sgns_update_negatives_owned(float *w_in, float *w_out, int64_t vocab, int emb, const int32_t *tokens,
+                                              int64_t n_seq, int seq_len, int radius, int n_neg, int row_offset,
+                                              const float *alias_prob, const int32_t *alias_idx, float lr, uint64_t seed,
+                                              int64_t centre_id_base, const se_shard_spec *spec, double *stats, void *stream) {
+    int rc = se::common_checks("se_sgns_update_negatives_owned", w_in, w_out, vocab, emb, n_neg);
+    if (rc != SE_OK) return rc;
+    SE_REQUIRE(spec, "se_sgns_update_negatives_owned: a shard spec is required");
+    SE_REQUIRE(spec->world >= 1 && spec->rank >= 0 && spec->rank < spec->world && spec->stripe_rows >= 1,
+               "se_sgns_update_negatives_owned: bad shard spec (world %d rank %d stripe_rows %lld)", spec->world, spec->rank,
+               (long long)spec->stripe_rows);
+    SE_REQUIRE(n_seq >= 0 && (tokens || n_seq == 0), "se_sgns_update_negatives_owned: null tokens");
+    SE_REQUIRE(radius >= 1 && seq_len >= 2 * radius + 1, "Text is too short! [text_length=%d] < [min_text_length=%d]", seq_len, 2 * radius + 1);
+    SE_REQUIRE((alias_prob == nullptr) == (alias_idx == nullptr), "se_sgns_update_negatives_owned: pass both alias arrays or neither");
+    if (n_neg == 0 || n_seq == 0) return SE_OK;
+    const int64_t sr = spec->stripe_rows;
+    if ((sr & (sr - 1)) || emb % 4 != 0 || emb <= 64 || emb > 128 || n_neg > 7 || ((2 * radius + 3) / 4) * n_neg > 32 ||
+        ((uintptr_t)w_in % 16) || ((uintptr_t)w_out % 16)) {
+        se::set_error("se_sgns_update_negatives_owned: needs 64 < emb <= 128 (multiple of 4), n_neg <= 7, ceil(2r/4)*n_neg <= 32, "
+                      "16-byte aligned tables and a power-of-two stripe_rows (emb %d, n_neg %d, radius %d, stripe_rows %lld)",
+                      emb, n_neg, radius, (long long)sr);
+        return SE_ERR_UNSUPPORTED;
+    }
+    se::SgnsArgs a{};
+    a.w_in = w_in; a.w_out = w_out; a.tokens = tokens; a.alias_prob = alias_prob; a.alias_idx = alias_idx;
+    a.stats = stats; a.vocab = vocab; a.emb = emb; a.n_ctx = 2 * radius; a.n_neg = n_neg;
+    a.seq_len = seq_len; a.radius = radius; a.n_cen = seq_len - 2 * radius; a.row_offset = row_offset;
+    a.n_units = n_seq * a.n_cen;
+    a.lr = lr; a.seed = seed; a.id_base = centre_id_base;
+    a.neg_vocab = (uint32_t)vocab; a.neg_shift = -1; a.neg_world = spec->world; a.neg_rank = spec->rank;
+    a.sys_scope = spec->world > 1;
+    a.own_shift = 0;
+    while ((1ll << a.own_shift) < sr) ++a.own_shift;
+    return emb == 128 ? se::launch_negown<true>(a, (cudaStream_t)stream) : se::launch_negown<false>(a, (cudaStream_t)stream);
 }
 
 extern "C" int se_sgns_update_walks(float *w_in, float *w_out, int64_t vocab, int emb, const int32_t *tokens,

@@ -68,6 +68,8 @@ _SIGNATURES = {
     'se_shard_local_rows': (c_int, [c_i64, c_p, c_p]),
     'se_sgns_update_walks_sharded': (c_int, [c_p, c_p, c_i64, c_int, c_p, c_i64, c_int, c_int, c_int, c_int, c_p, c_p,
                                              c_f32, c_u64, c_i64, c_int, c_p, c_p, c_p]),
+    'se_sgns_update_negatives_owned': (c_int, [c_p, c_p, c_i64, c_int, c_p, c_i64, c_int, c_int, c_int, c_int, c_p, c_p, c_f32, c_u64,
+                                               c_i64, c_p, c_p, c_p]),
     'se_host_walk_sgns_step_sharded': (c_int, [c_p, c_p, c_p, c_i64, c_int, c_p, c_i64, c_int, c_f64, c_f64, c_int, c_int,
                                                c_u64, c_i64, c_p, c_p, c_i64, c_int, c_int, c_int, c_int, c_p, c_p, c_f32,
                                                c_int, c_p, c_p, c_p, c_p, c_p, c_p, c_p]),
@@ -382,6 +384,28 @@ def sgns_update_walks(w_in, w_out, tokens: torch.Tensor, radius: int, n_neg: int
             ctypes.byref(spec) if spec is not None else None, stats.data_ptr(), _stream()))
     _launches += 1
     return _stats_dict(stats) if own_stats else None
+
+
+def sgns_update_negatives_owned(w_in, w_out, tokens: torch.Tensor, radius: int, n_neg: int, row_offset: int, lr: float, seed: int,
+                                centre_id_base: int = 0, alias: Optional[Dict[str, torch.Tensor]] = None,
+                                stats: Optional[torch.Tensor] = None) -> None:
+    """Owner-computes negatives on striped tables: processes, for every centre of `tokens` (any GPU's walks), the
+    negatives whose rows this rank owns (global negative distribution, same Philox keys as `sgns_update_walks`)."""
+    global _launches
+    n_seq, seq_len = tokens.shape
+    p_in, vocab, emb, s_in, dev = _table(w_in, 'w_in')
+    p_out, _, _, s_out, _ = _table(w_out, 'w_out')
+    spec = _same_sharding(s_in, s_out)
+    if spec is None:
+        raise ValueError('sgns_update_negatives_owned needs striped tables (ShardedTable)')
+    spec = ShardSpec(spec.world, spec.rank, spec.stripe_rows, 0, 0)
+    with torch.cuda.device(dev):
+        _check(load().se_sgns_update_negatives_owned(
+            p_in, p_out, vocab, emb, _ptr(tokens, torch.int32, 'tokens'), n_seq, seq_len, int(radius), int(n_neg), int(row_offset),
+            _ptr(alias['prob'], torch.float32) if alias else None, _ptr(alias['alias'], torch.int32) if alias else None,
+            float(lr), int(seed) & (2 ** 64 - 1), int(centre_id_base), ctypes.byref(spec),
+            stats.data_ptr() if stats is not None else None, _stream()))
+    _launches += 1
 
 
 def host_walk_sgns_step(csr, starts_host: torch.Tensor, walk_len: int, p: float, q: float, node2vec: bool, rule: int,

@@ -232,6 +232,10 @@ class ShardedTable:
             nat.table_gather_rows(self, torch.arange(lo, hi, dtype=torch.int64, device=self.device), out=out[lo:hi])
         return out
 
+    def as_rank(self, rank: int) -> '_RankView':
+        """The same memory seen as another rank of a SIMULATED sharding (single-GPU tests of the per-rank kernels)."""
+        return _RankView(self, rank)
+
     def close(self) -> None:
         if not self.ptr:
             return
@@ -250,3 +254,41 @@ class ShardedTable:
             self.close()
         except Exception:   # noqa: BLE001  (interpreter shutdown)
             pass
+
+
+class _RankView:
+    """Borrowed view of a ShardedTable that reports a different rank; owns nothing."""
+
+    def __init__(self, table: ShardedTable, rank: int):
+        assert 0 <= rank < table.world
+        self._table, self.rank = table, int(rank)
+        self.ptr, self.vocab, self.emb, self.device, self.world, self.stripe_rows = (table.ptr, table.vocab, table.emb, table.device,
+                                                                                   table.world, table.stripe_rows)
+
+    def spec(self) -> _Spec:
+        return _Spec(self.world, self.rank, self.stripe_rows)
+
+
+def sgns_update_walks_owner_computes(w_in, w_out, my_walks: torch.Tensor, radius: int, n_neg: int, row_offset: int, lr: float, seed: int,
+                                     centre_id_base: int, rank: int, world: int, group=None, stats: Optional[torch.Tensor] = None,
+                                     alias=None, gather_buf: Optional[torch.Tensor] = None) -> None:
+    """One multi-GPU SGNS step with the reference's GLOBAL negative distribution and little NVLink traffic: the positive
+    pairs of this rank's walks run in the window-resident kernel (n_neg = 0); the walks of all ranks are all-gathered
+    (4 bytes per token) and every rank processes, for every centre of every rank, the negatives whose rows it owns
+    (`se_sgns_update_negatives_owned`).  `centre_id_base` is the Philox id of centre 0 of RANK 0's walks; rank r's
+    centres follow at r * n_walks * n_centres, so the negatives are the ones a single GPU would draw for the
+    concatenated batch.  Every rank must call this with the same number of walks."""
+    import torch.distributed as dist
+    n_walks, length = my_walks.shape
+    n_cen = length - 2 * radius
+    if world > 1:
+        if gather_buf is None:
+            gather_buf = torch.empty((world * n_walks, length), dtype=torch.int32, device=my_walks.device)
+        dist.all_gather_into_tensor(gather_buf, my_walks.contiguous(), group=group)
+        all_walks = gather_buf
+    else:
+        all_walks = my_walks
+    nat.sgns_update_walks(w_in, w_out, my_walks, radius, 0, row_offset, lr, seed, centre_id_base=centre_id_base + rank * n_walks * n_cen,
+                          stats=stats)
+    nat.sgns_update_negatives_owned(w_in, w_out, all_walks, radius, n_neg, row_offset, lr, seed, centre_id_base=centre_id_base,
+                                    alias=alias, stats=stats)

@@ -226,6 +226,16 @@ int se_sgns_update_walks_sharded(float *w_in, float *w_out, int64_t vocab, int e
                                  const float *alias_prob, const int32_t *alias_idx, float lr, uint64_t seed,
                                  int64_t centre_id_base, int flags, const se_shard_spec *spec, double *stats,
                                  void *stream);
+/* Owner-computes negatives: the NEGATIVE half of se_sgns_update_walks for tokens that may belong to ANY GPU's walks
+ * (all-gathered), restricted to the negatives whose rows spec->rank owns.  Negative k of (centre c, context n) is drawn
+ * from Philox(seed; centre_id_base + c, n, k) exactly as in se_sgns_update_walks (word2vec/utils/sampling.py:21
+ * distribution over the WHOLE table, or the alias table), so calling it on every rank with the same tokens and keys,
+ * plus se_sgns_update_walks with n_neg = 0 on each rank's own walks for the positive pairs, performs the same pair
+ * updates as one GPU would -- with 2 rows per centre per GPU over NVLink instead of 2*N*K.  stats: [1], [3], [5]. */
+int se_sgns_update_negatives_owned(float *w_in, float *w_out, int64_t vocab, int emb, const int32_t *tokens,
+                                   int64_t n_seq, int seq_len, int radius, int n_neg, int row_offset,
+                                   const float *alias_prob, const int32_t *alias_idx, float lr, uint64_t seed,
+                                   int64_t centre_id_base, const se_shard_spec *spec, double *stats, void *stream);
 int se_host_walk_sgns_step_sharded(const int64_t *rowptr, const int32_t *col, const float *wcdf, int64_t n_nodes,
                                    int symmetric, const int32_t *starts_host, int64_t n_walks, int walk_len, double p,
                                    double q, int node2vec, int rule, uint64_t seed, int64_t walk_id_base,

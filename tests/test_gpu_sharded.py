@@ -167,6 +167,63 @@ def test_local_negatives_stay_on_the_owning_shard_and_match_the_oracle(rank, use
     s_in.close(); s_out.close()
 
 
+@pytest.mark.parametrize('use_alias', [False, True])
+def test_owner_computes_negatives_perform_the_same_pair_updates(use_alias):
+    """Positives on the home rank (window kernel, K = 0) + owner-computes negatives on every simulated rank == the pair
+    updates of the ordinary fused kernel == the oracle's mini-batch SGD, with the GLOBAL negative distribution."""
+    dev = cuda_device()
+    rng = np.random.default_rng(51)
+    emb, radius, k, n_seq, offset, world = 128, 2, 4, 10, 1, 2
+    vocab = 4096 * 5 + 100
+    alias = None
+    prob = ali = None
+    if use_alias:
+        alias = nat.alias_build(rng.integers(1, 50, vocab).astype(np.float64), 0.75, dev)
+        prob, ali = alias['prob'].cpu().numpy(), alias['alias'].cpu().numpy()
+    tokens, inputs, targets, neg, seed = _collision_free_case(
+        rng, emb, radius, k, n_seq, vocab, offset, lambda s_: philox_ref.negatives(s_, np.arange(n_seq) + 300, 2 * radius, k, vocab, prob, ali))
+    w_in = (rng.standard_normal((vocab, emb)) * 0.3).astype(np.float32)
+    w_out = (rng.standard_normal((vocab, emb)) * 0.3).astype(np.float32)
+    lr = 1e-3          # the three launches see each other's updates of W_in: second order in lr, far below the tolerance
+    s_in = ShardedTable(vocab, emb, dev, rank=0, world=world, simulate=True)
+    s_out = ShardedTable(vocab, emb, dev, rank=0, world=world, simulate=True)
+    allrows = torch.arange(vocab, device=dev)
+    s_in.scatter(allrows, _t(w_in, dev)); s_out.scatter(allrows, _t(w_out, dev))
+    tok = _t(tokens, dev)
+    stats = torch.zeros(nat.STATS_LEN, dtype=torch.float64, device=dev)
+    nat.sgns_update_walks(s_in, s_out, tok, radius, 0, offset, lr, seed, centre_id_base=300, stats=stats)          # positive pairs
+    owned_negs = 0
+    for r in range(world):
+        before = stats[5].item()
+        nat.sgns_update_negatives_owned(s_in.as_rank(r), s_out.as_rank(r), tok, radius, k, offset, lr, seed, centre_id_base=300,
+                                        alias=alias, stats=stats)
+        got_r = stats[5].item() - before
+        assert got_r == int((((neg // s_in.stripe_rows) % world) == r).sum())                                 # exactly the rows rank r owns
+        owned_negs += got_r
+    assert owned_negs == neg.size and stats[4].item() == n_seq * 2 * radius
+    rows = np.unique(np.concatenate([targets.ravel(), neg.ravel(), inputs.ravel()]))
+    remap = {int(x): i for i, x in enumerate(rows)}
+    rm = np.vectorize(remap.get)
+    want_in, want_out, o = sgns_oracle.sgd_step(w_in[rows].astype(np.float64), w_out[rows].astype(np.float64), rm(inputs), rm(targets),
+                                                rm(neg), lr * n_seq * 2 * radius)
+    got_in, got_out = s_in.to_tensor().cpu().numpy(), s_out.to_tensor().cpu().numpy()
+    np.testing.assert_allclose(got_out[rows], want_out, rtol=0, atol=2e-6)
+    np.testing.assert_allclose(got_in[rows], want_in, rtol=0, atol=2e-6)
+    assert np.abs(got_out[rows] - w_out[rows]).max() > 1e-4
+    st = stats.tolist()
+    assert abs((st[0] + st[1]) / st[4] - o['loss']) < 1e-3 * o['loss']
+    untouched = np.setdiff1d(np.arange(vocab), rows)
+    assert np.array_equal(got_in[untouched], w_in[untouched]) and np.array_equal(got_out[untouched], w_out[untouched])
+    # the same launches as ONE ordinary fused call land on the same tables
+    t_in, t_out = _t(w_in, dev), _t(w_out, dev)
+    nat.sgns_update_walks(t_in, t_out, tok, radius, k, offset, lr, seed, centre_id_base=300, alias=alias)
+    np.testing.assert_allclose(got_out, t_out.cpu().numpy(), rtol=0, atol=2e-6)
+    np.testing.assert_allclose(got_in, t_in.cpu().numpy(), rtol=0, atol=2e-6)
+    with pytest.raises(ValueError):
+        nat.sgns_update_negatives_owned(t_in, t_out, tok, radius, k, offset, lr, seed)          # needs striped tables
+    s_in.close(); s_out.close()
+
+
 def test_host_step_on_sharded_tables_matches_device_calls():
     dev = cuda_device()
     from helpers import random_csr
