@@ -89,6 +89,42 @@ def main():
     run_case(local_neg=False)
     run_case(local_neg=True)
 
+    # 3b. owner-computes negatives: reference-exact GLOBAL draw, every rank processes the negatives it owns for the centres of
+    #     all ranks (walks all-gathered); same pair updates as one GPU on the concatenated batch
+    from shallow_encoders.word2vec.sharded import sgns_update_walks_owner_computes
+    n_tot = world * n_seq
+    for seed in range(100, 2000):
+        neg = philox_ref.negatives(seed, np.arange(n_tot) + 7000, 2 * radius, k, vocab)
+        inputs, targets = sgns_oracle.windows_from_walks(tokens_all.reshape(-1, length).astype(np.int64), radius, offset)
+        allrows = np.concatenate([targets.ravel(), neg.ravel()])
+        if len(np.unique(allrows)) == allrows.size:
+            break
+    else:
+        raise AssertionError('no collision-free seed')
+    allr = torch.arange(vocab, device=dev)
+    if rank == 0:
+        s_in.scatter(allr, d_in); s_out.scatter(allr, d_out)
+    barrier()
+    small = 1e-3
+    stats = torch.zeros(nat.STATS_LEN, dtype=torch.float64, device=dev)
+    sgns_update_walks_owner_computes(s_in, s_out, torch.from_numpy(tokens_all[rank]).to(dev), radius, k, offset, small, seed, 7000,
+                                     rank, world, stats=stats)
+    barrier()
+    dist.all_reduce(stats)
+    assert stats[4].item() == n_tot * 2 * radius and stats[5].item() == n_tot * 2 * radius * k, stats.tolist()
+    rows = np.unique(np.concatenate([allrows, inputs.ravel()]))
+    remap = {int(r): i for i, r in enumerate(rows)}
+    rm = np.vectorize(remap.get)
+    want_in, want_out, _ = sgns_oracle.sgd_step(w_in0[rows].astype(np.float64), w_out0[rows].astype(np.float64), rm(inputs), rm(targets),
+                                                rm(neg), small * len(inputs) * 2 * radius)
+    got_in, got_out = s_in.to_tensor().cpu().numpy(), s_out.to_tensor().cpu().numpy()
+    np.testing.assert_allclose(got_in[rows], want_in, rtol=0, atol=2e-6)
+    np.testing.assert_allclose(got_out[rows], want_out, rtol=0, atol=2e-6)
+    assert np.abs(got_out[rows] - w_out0[rows]).max() > 1e-4
+    untouched = np.setdiff1d(np.arange(vocab), rows)
+    assert np.array_equal(got_in[untouched], w_in0[untouched]) and np.array_equal(got_out[untouched], w_out0[untouched])
+    barrier()
+
     # 4. contention: ALL ranks push the same update into the same rows at the same time; system-scope reductions must
     #    accumulate every contribution (to first order in lr: world x the single update)
     allr = torch.arange(vocab, device=dev)
