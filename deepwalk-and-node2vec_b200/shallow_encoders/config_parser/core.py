@@ -46,6 +46,7 @@ class TrainConfig:
     engine: str = 'reference'          # 'reference': autograd + YAML optimizer; 'fused': in-place SGD kernel
     fused_lr: float = 0.025
     local_negatives: bool = False      # multi-GPU fused engine: draw negatives among the rows the GPU owns
+    multi_gpu_negatives: str = 'global'   # multi-GPU fused engine: global | local | owner (reference draw, owner-computes negatives)
 
     def instantiate_optimizer(self, params):
         return instantiate(self.optimizer, params=params)

@@ -127,12 +127,23 @@ def fit_fused(cfg, dataset, trainer, end_of_epoch, rank: int = 0, world: int = 1
         tokens = dataset.epoch_tokens(rank=rank, world=world)[:, :cfg.datamodule.max_length]
         stats.zero_()
         share = -(-cfg.datamodule.batch_size // world)             # this rank's walks of one global batch
+        mode = 'local' if getattr(cfg.train, 'local_negatives', False) else getattr(cfg.train, 'multi_gpu_negatives', 'global')
+        mode = mode if world > 1 else 'global'
+        n_cen = tokens.shape[1] - 2 * r
+        n_min = len(dataset) // world                              # walks every rank is guaranteed to have this epoch
         for lo in range(0, tokens.shape[0], share):
             chunk = tokens[lo:lo + share].contiguous()
-            pairs = chunk.shape[0] * (chunk.shape[1] - 2 * r) * 2 * r * world
-            trainer.fused_step(chunk, r, lr_batch / pairs, row_offset=dataset.row_offset,
-                               seed=(epoch * 1_000_003 + lo) * world + rank, stats=stats,
-                               local_negatives=bool(getattr(cfg.train, 'local_negatives', False)) and world > 1)
+            pairs = chunk.shape[0] * n_cen * 2 * r * world
+            seed = epoch * 1_000_003 + lo
+            if mode == 'owner' and lo + share <= n_min:          # same decision on every rank (the step contains a collective);
+                                                                 # a ragged last batch falls back to fetching the rows
+                from shallow_encoders.word2vec.sharded import sgns_update_walks_owner_computes
+                w_in, w_out = trainer.model.tables
+                sgns_update_walks_owner_computes(w_in, w_out, chunk, r, cfg.train.loss.negative_samples, dataset.row_offset, lr_batch / pairs,
+                                                 seed, trainer.global_step * world * share * n_cen, rank, world, stats=stats)
+            else:
+                trainer.fused_step(chunk, r, lr_batch / pairs, row_offset=dataset.row_offset, seed=seed * world + rank, stats=stats,
+                                   local_negatives=mode == 'local')
             trainer.global_step += 1
         if world > 1:
             torch.distributed.all_reduce(stats)

@@ -295,7 +295,8 @@ def test_two_gpus_train_one_pair_of_tables_over_nvlink():
 
 @pytest.mark.skipif(torch.cuda.device_count() < 2, reason='needs two GPUs on one NVLink/NVSwitch node')
 def test_train_cli_on_two_gpus_matches_single_gpu_accuracy(tmp_path):
-    """`torchrun tools/train.py ... train.engine=fused` on 2 GPUs trains ONE striped model; rank 0's checkpoint has the
+    """`torchrun tools/train.py ... train.engine=fused train.multi_gpu_negatives=owner` on 2 GPUs trains ONE striped model
+    (positives on the home GPU, negatives on the GPU that owns their rows); rank 0's checkpoint has the
     reference's state-dict keys and its downstream node-classification accuracy (tools/graph_model_downstream_classification.py
     :94-148 restated in tools/downstream.py) matches what one GPU reaches on the same config (0.98 +- 0.01)."""
     from shallow_encoders.config_parser import load_config
@@ -303,7 +304,7 @@ def test_train_cli_on_two_gpus_matches_single_gpu_accuracy(tmp_path):
     from tools.downstream import node_classification
     pkg = os.path.join(ROOT, 'deepwalk-and-node2vec_b200')
     over = ['train.engine=fused', 'train.fused_lr=60.0', 'train.max_epochs=8', 'train.scheduler.step_size=4', 'model.embedding_size=128',
-            'datamodule.additional_parameters.method_params.q=0.5', f'path.output_dir={tmp_path}']
+            'datamodule.additional_parameters.method_params.q=0.5', 'train.multi_gpu_negatives=owner', f'path.output_dir={tmp_path}']
     env = dict(os.environ, PYTHONPATH=os.pathsep.join([pkg, ROOT]))
     cmd = [sys.executable, '-m', 'torch.distributed.run', '--nnodes=1', '--nproc-per-node=2', '--master-addr', '127.0.0.1',
            '--master-port', str(29900 + os.getpid() % 90), os.path.join(pkg, 'tools', 'train.py'), '--config-name=sge_sg_cora', *over]
