@@ -3,6 +3,7 @@ engine in three ways and compares downstream node-classification accuracy of W_i
     1 GPU, reference negatives (uniform over the whole table)
     G GPUs, one striped table pair, reference (global) negatives
     G GPUs, one striped table pair, LOCAL negatives (each GPU draws among the rows it owns; bench.py's default)
+    G GPUs, one striped table pair, reference negatives, OWNER-COMPUTES (every GPU processes the negatives whose rows it owns)
 Run under torchrun with G >= 2 ranks (rank 0 also does the 1-GPU run); writes gpurun_out/multi_gpu_accuracy.json.
 
     python -m torch.distributed.run --nproc-per-node 2 --master-addr 127.0.0.1 tools_dev/multi_gpu_accuracy.py
@@ -21,7 +22,7 @@ import torch.distributed as dist
 
 from shallow_encoders import _native as nat
 from shallow_encoders.graph.synthetic import sbm_graph_device
-from shallow_encoders.word2vec.sharded import ShardedTable, make_exchange
+from shallow_encoders.word2vec.sharded import ShardedTable, make_exchange, sgns_update_walks_owner_computes
 
 ap = argparse.ArgumentParser()
 ap.add_argument('--nodes', type=int, default=200_000)
@@ -57,7 +58,7 @@ def barrier():
         torch.cuda.synchronize()
 
 
-def train(w_in, w_out, r, g, local_neg):
+def train(w_in, w_out, r, g, local_neg, owner=False):
     """Epochs of walks -> fused update; rank r of g takes walks r, r+g, ... of every batch."""
     gen = torch.Generator()
     gen.manual_seed(1)
@@ -70,8 +71,13 @@ def train(w_in, w_out, r, g, local_neg):
             starts = order[lo:lo + a.batch_walks][r::g].contiguous().to(dev)
             base = epoch * order.numel() + lo + r
             walks = nat.walk(csr, starts, a.walk_len, 1.0, 0.5, True, nat.RULE_REFERENCE, seed=7, walk_id_base=base, walk_id_stride=g)
-            nat.sgns_update_walks(w_in, w_out, walks, a.radius, a.neg, 1, a.lr * (1.0 - 0.5 * epoch / max(a.epochs, 1)), seed=11,
-                                  centre_id_base=base * n_cen, stats=stats, local_negatives=local_neg)
+            lr = a.lr * (1.0 - 0.5 * epoch / max(a.epochs, 1))
+            if owner and walks.shape[0] * g == min(a.batch_walks, order.numel() - lo):      # same decision on every rank
+                sgns_update_walks_owner_computes(w_in, w_out, walks, a.radius, a.neg, 1, lr, 11, (epoch * order.numel() + lo) * n_cen, r, g,
+                                                 stats=stats)
+            else:
+                nat.sgns_update_walks(w_in, w_out, walks, a.radius, a.neg, 1, lr, seed=11, centre_id_base=base * n_cen, stats=stats,
+                                      local_negatives=local_neg)
         s = stats.tolist()
         losses.append((s[0] + s[1]) / max(s[4], 1))
     return losses
@@ -104,12 +110,13 @@ barrier()
 # ---- G GPUs, striped tables ---------------------------------------------------------------------------------------------
 if world > 1:
     ex = make_exchange(rank, world)
-    for name, local_neg in (('striped_global_negatives', False), ('striped_local_negatives', True)):
+    for name, local_neg, owner in (('striped_global_negatives', False, False), ('striped_local_negatives', True, False),
+                                   ('striped_owner_computes_negatives', False, True)):
         s_in, s_out = ShardedTable(vocab, a.emb, dev, rank, world, ex), ShardedTable(vocab, a.emb, dev, rank, world, ex)
         s_in.fill_uniform(bound, 101); s_out.fill_uniform(bound, 102)
         barrier()
         t0 = time.time()
-        losses = train(s_in, s_out, rank, world, local_neg)
+        losses = train(s_in, s_out, rank, world, local_neg, owner)
         barrier()
         secs = time.time() - t0
         if rank == 0:
