@@ -274,19 +274,19 @@ walk_kernel(const int64_t *__restrict__ rowptr, const int32_t *__restrict__ col,
 // (try = round * 32 + lane, first accepted try wins), so both kernels produce bit-identical walks and the choice
 // between them is a pure scheduling decision.  The loop is flattened into "one try per iteration" so a lane that
 // accepts early moves on to its next step instead of idling while its neighbours retry.  Membership of the candidate in
-// N(t) uses interpolation search (node ids in an adjacency row are close to uniformly spread), falling back to binary
-// search, which cuts the dependent loads on hub rows (degree 10^3..10^5) from 10-17 to ~4.  Outputs are written as
+// N(t) uses interpolation search (node ids in an adjacency row are close to uniformly spread) between VIRTUAL anchors
+// (-1 before the row, n_nodes after it: no loads of the row's ends), falling back to binary search, which cuts the
+// dependent loads on hub rows (degree 10^3..10^5) from 10-17 to ~4.  Outputs are written as
 // 16-byte vectors (4 steps) when the walk rows are 16-byte aligned.
 // ------------------------------------------------------------------------------------------------------------
-__device__ __forceinline__ bool member_interp(const int32_t *__restrict__ col, int64_t lo, int64_t n, int32_t vfirst,
-                                              int32_t vlast, int32_t key) {
-    if (n <= 0 || key < vfirst || key > vlast) return false;
-    if (key == vfirst || key == vlast) return true;
-    int64_t l = lo, r = lo + n - 1;          // col[l] = vl < key < vr = col[r]
-    int32_t vl = vfirst, vr = vlast;
+__device__ __forceinline__ bool member_interp(const int32_t *__restrict__ col, int64_t lo, int64_t n, int32_t key, int32_t n_nodes) {
+    if (n <= 0) return false;
+    // virtual anchors: id -1 just before the row and id n_nodes just after it, so the first probe needs no load of the row's ends
+    int64_t l = lo - 1, r = lo + n;          // col[l] = vl < key < vr = col[r]  (virtually at the two ends)
+    int32_t vl = -1, vr = n_nodes;
 #pragma unroll 1
     for (int it = 0; it < 4 && r - l > 8; ++it) {
-        const float frac = (float)(key - vl) / (float)(vr - vl);
+        const float frac = (float)((int64_t)key - vl) / (float)((int64_t)vr - vl);
         int64_t m = l + (int64_t)(frac * (float)(r - l));
         m = max(l + 1, min(r - 1, m));
         const int32_t vm = __ldg(col + m);
@@ -306,7 +306,7 @@ __device__ __forceinline__ bool member_interp(const int32_t *__restrict__ col, i
 template <bool WEIGHTED>
 __global__ void __launch_bounds__(256)
 walk_thread_kernel(const int64_t *__restrict__ rowptr, const int32_t *__restrict__ col, const float *__restrict__ wcdf,
-                   int symmetric, const int32_t *__restrict__ starts, int64_t n_walks, int walk_len, float inv_p,
+                   int symmetric, int32_t n_nodes, const int32_t *__restrict__ starts, int64_t n_walks, int walk_len, float inv_p,
                    float inv_q, int node2vec, int rule, uint64_t seed, int64_t walk_id_base, int64_t walk_id_stride,
                    int32_t *__restrict__ out, int32_t *__restrict__ err_count) {
     const float wmax = fmaxf(1.0f, fmaxf(inv_p, inv_q));
@@ -319,7 +319,6 @@ walk_thread_kernel(const int64_t *__restrict__ rowptr, const int32_t *__restrict
         int32_t *o = out + wk * (int64_t)walk_len;
         int32_t v = __ldg(starts + wk), t = -1;
         int64_t base = 0, deg = 0, tbase = 0, tdeg = 0;
-        int32_t tfirst = 0, tlast = 0, vfirst = 0, vlast = 0;
         float wprev = 1.0f, wtot = 0.f;
         int32_t pend[4];
         pend[0] = v;
@@ -331,10 +330,6 @@ walk_thread_kernel(const int64_t *__restrict__ rowptr, const int32_t *__restrict
             if (need_row) {
                 base = __ldg(rowptr + v);
                 deg = __ldg(rowptr + v + 1) - base;
-                if (deg > 0 && any_bias && symmetric) {     // ends of N(v): the interpolation anchors of the NEXT step
-                    vfirst = __ldg(col + base);
-                    vlast = __ldg(col + base + deg - 1);
-                }
                 if (deg > 0 && any_bias) wtot = WEIGHTED ? __ldg(wcdf + base + deg - 1) : (float)deg;
                 need_row = false;
                 attempt = 0;
@@ -362,7 +357,7 @@ walk_thread_kernel(const int64_t *__restrict__ rowptr, const int32_t *__restrict
                         } else {
                             bool m;
                             if (symmetric) {
-                                m = member_interp(col, tbase, tdeg, tfirst, tlast, cand);
+                                m = member_interp(col, tbase, tdeg, cand, n_nodes);
                             } else {
                                 const int64_t xb = __ldg(rowptr + cand);
                                 m = member_sorted(col, xb, __ldg(rowptr + cand + 1), t);
@@ -382,7 +377,7 @@ walk_thread_kernel(const int64_t *__restrict__ rowptr, const int32_t *__restrict
                 } else {
                     o[s] = x;
                 }
-                if (deg > 0) { t = v; tbase = base; tdeg = deg; tfirst = vfirst; tlast = vlast; v = x; need_row = true; }
+                if (deg > 0) { t = v; tbase = base; tdeg = deg; v = x; need_row = true; }
                 ++s;
             }
         }
@@ -450,10 +445,10 @@ extern "C" int se_walk(const int64_t *rowptr, const int32_t *col, const float *w
         const int64_t cap = (int64_t)sms * 8;
         if (blocks > cap) blocks = cap;
         if (wcdf)
-            se::walk_thread_kernel<true><<<(int)blocks, 256, 0, st>>>(rowptr, col, wcdf, symmetric, starts, n_walks, walk_len, inv_p,
+            se::walk_thread_kernel<true><<<(int)blocks, 256, 0, st>>>(rowptr, col, wcdf, symmetric, (int32_t)n_nodes, starts, n_walks, walk_len, inv_p,
                                                                       inv_q, node2vec, rule, seed, walk_id_base, walk_id_stride, out, err_count);
         else
-            se::walk_thread_kernel<false><<<(int)blocks, 256, 0, st>>>(rowptr, col, wcdf, symmetric, starts, n_walks, walk_len, inv_p,
+            se::walk_thread_kernel<false><<<(int)blocks, 256, 0, st>>>(rowptr, col, wcdf, symmetric, (int32_t)n_nodes, starts, n_walks, walk_len, inv_p,
                                                                        inv_q, node2vec, rule, seed, walk_id_base, walk_id_stride, out, err_count);
         return se::check_cuda(cudaGetLastError(), "walk_thread_kernel launch");
     }
