@@ -110,6 +110,17 @@ def main():
     sgns_update_walks_owner_computes(s_in, s_out, torch.from_numpy(tokens_all[rank]).to(dev), radius, k, offset, small, seed, 7000,
                                      rank, world, stats=stats)
     barrier()
+    first_pass = s_out.to_tensor().clone()
+    barrier()
+    # the same step interleaved in micro-batches of 4 walks (one all-gather, positives / negatives alternating) lands on the same tables
+    if rank == 0:
+        s_in.scatter(allr, d_in); s_out.scatter(allr, d_out)
+    barrier()
+    sgns_update_walks_owner_computes(s_in, s_out, torch.from_numpy(tokens_all[rank]).to(dev), radius, k, offset, small, seed, 7000,
+                                     rank, world, micro_walks=4)
+    barrier()
+    assert float((s_out.to_tensor() - first_pass).abs().max()) < 2e-6
+    barrier()
     dist.all_reduce(stats)
     assert stats[4].item() == n_tot * 2 * radius and stats[5].item() == n_tot * 2 * radius * k, stats.tolist()
     rows = np.unique(np.concatenate([allrows, inputs.ravel()]))

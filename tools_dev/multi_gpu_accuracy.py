@@ -37,6 +37,7 @@ ap.add_argument('--neg', type=int, default=5)
 ap.add_argument('--epochs', type=int, default=2)
 ap.add_argument('--lr', type=float, default=0.025)
 ap.add_argument('--batch-walks', type=int, default=65536)
+ap.add_argument('--owner-micro-walks', type=int, default=0, help='owner-computes arm: interleave positives / negatives in slices of this many walks')
 a = ap.parse_args()
 
 rank, world, local = int(os.environ.get('RANK', 0)), int(os.environ.get('WORLD_SIZE', 1)), int(os.environ.get('LOCAL_RANK', 0))
@@ -74,7 +75,7 @@ def train(w_in, w_out, r, g, local_neg, owner=False):
             lr = a.lr * (1.0 - 0.5 * epoch / max(a.epochs, 1))
             if owner and walks.shape[0] * g == min(a.batch_walks, order.numel() - lo):      # same decision on every rank
                 sgns_update_walks_owner_computes(w_in, w_out, walks, a.radius, a.neg, 1, lr, 11, (epoch * order.numel() + lo) * n_cen, r, g,
-                                                 stats=stats)
+                                                 stats=stats, micro_walks=a.owner_micro_walks or None)
             else:
                 nat.sgns_update_walks(w_in, w_out, walks, a.radius, a.neg, 1, lr, seed=11, centre_id_base=base * n_cen, stats=stats,
                                       local_negatives=local_neg)
