@@ -38,6 +38,28 @@ METRIC = 'sgns_pairs_per_s'
 UNIT = 'pairs/s'
 
 
+_REAL_STDOUT = None
+
+
+def quiet_stdout():
+    """Route everything libraries print on fd 1 (e.g. NCCL's version banner) to stderr: stdout carries exactly ONE JSON line."""
+    global _REAL_STDOUT
+    if _REAL_STDOUT is None:
+        sys.stdout.flush()
+        _REAL_STDOUT = os.dup(1)
+        os.dup2(2, 1)
+
+
+def emit(line):
+    data = (json.dumps(line) + '\n').encode()
+    if _REAL_STDOUT is None:
+        sys.stdout.write(data.decode())
+        sys.stdout.flush()
+    else:
+        sys.stdout.flush()
+        os.write(_REAL_STDOUT, data)
+
+
 def parse_args():
     ap = argparse.ArgumentParser()
     ap.add_argument('--gpus', type=int, default=1)
@@ -232,7 +254,7 @@ def run_reference(a, rank, world):
         'e2e': {'value': r['pairs_per_s'], 'unit': UNIT, 'h2d_bytes_per_step': 0, 'd2h_bytes_per_step': 0},
         'walk_steps_per_s': r['walk_steps_per_s'], 'gpu_launches': 0,
     }
-    print(json.dumps(line), flush=True)
+    emit(line)
 
 
 def cpu_baseline(a):
@@ -528,7 +550,7 @@ def run_b200(a, rank, local_rank, world):
             line['cpu_baseline'] = cpu_baseline(a)
         except Exception as e:   # noqa: BLE001
             line['cpu_baseline'] = {'value': None, 'unit': UNIT, 'cores': os.cpu_count(), 'kind': 'port', 'sample': f'failed: {e!r}'}
-    print(json.dumps(line), flush=True)
+    emit(line)
     if world > 1:
         barrier()
         if sharded:
@@ -635,7 +657,7 @@ def run_s4(a):
         'train_stats': {'loss': (stat_vals[0] + stat_vals[1]) / max(stat_vals[4], 1), 'pairs': stat_vals[4]},
         'tokens_per_s': n_seq * L * a.steps / (ms_total / 1e3), 'library': nat.version(),
     }
-    print(json.dumps(line), flush=True)
+    emit(line)
 
 
 def main():
@@ -645,15 +667,16 @@ def main():
     rank = int(os.environ.get('RANK', '0'))
     local_rank = int(os.environ.get('LOCAL_RANK', '0'))
     world = int(os.environ.get('WORLD_SIZE', '1'))
-    if a.impl == 'reference':
-        run_reference(a, rank, world)
-        return
-    if world == 1 and a.gpus > 1:
-        # launched without torchrun: re-exec under it
+    if world == 1 and a.gpus > 1 and a.impl != 'reference':
+        # launched without torchrun: re-exec under it (the children write the JSON line to this process's stdout)
         import subprocess
         cmd = [sys.executable, '-m', 'torch.distributed.run', '--nnodes=1', f'--nproc-per-node={a.gpus}',
                '--master-addr', '127.0.0.1', '--master-port', os.environ.get('MASTER_PORT', '29517'), *sys.argv]
         sys.exit(subprocess.call(cmd))
+    quiet_stdout()
+    if a.impl == 'reference':
+        run_reference(a, rank, world)
+        return
     if a.workload == 's4':
         if rank == 0:
             run_s4(a)
