@@ -958,7 +958,7 @@ template <bool EXACT>
 __global__ void __launch_bounds__(SGNS_THREADS, 2)
 sgns_negown_kernel(const SgnsArgs a) {
     constexpr int P = 8, SHIFT = 2;
-    __shared__ int own_list[SGNS_THREADS / 32][64];
+    __shared__ int own_list[SGNS_THREADS / 32][128];      // up to 32 drawing lanes x 4 contexts owned at once (world = 1)
     __shared__ double sred[SE_STATS_LEN];
     const int lane = threadIdx.x & 31;
     int *list = own_list[threadIdx.x >> 5];

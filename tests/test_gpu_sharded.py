@@ -224,6 +224,26 @@ def test_owner_computes_negatives_perform_the_same_pair_updates(use_alias, emb):
     s_in.close(); s_out.close()
 
 
+def test_owner_computes_with_every_negative_owned_and_a_long_list():
+    """world = 1 and N*K = 70 > 64: every drawn negative is owned, the per-warp list holds them all; result == the ordinary
+    fused kernel on the same tokens (distinct rows, tiny lr)."""
+    dev = cuda_device()
+    rng = np.random.default_rng(61)
+    emb, radius, k, n_seq, offset, vocab = 128, 5, 7, 4, 1, 2_000_000
+    tokens = rng.permutation(vocab - offset)[:n_seq * 11].reshape(n_seq, 11).astype(np.int32)
+    w = ShardedTable(vocab, emb, dev), ShardedTable(vocab, emb, dev)
+    w[0].fill_uniform(0.3, 1); w[1].fill_uniform(0.3, 2)
+    t_in, t_out = w[0].to_tensor().clone(), w[1].to_tensor().clone()
+    tok = _t(tokens, dev)
+    stats = torch.zeros(nat.STATS_LEN, dtype=torch.float64, device=dev)
+    nat.sgns_update_walks(w[0], w[1], tok, radius, 0, offset, 1e-3, 9, centre_id_base=40, stats=stats)
+    nat.sgns_update_negatives_owned(w[0], w[1], tok, radius, k, offset, 1e-3, 9, centre_id_base=40, stats=stats)
+    assert stats[5].item() == n_seq * 2 * radius * k and stats[4].item() == n_seq * 2 * radius
+    nat.sgns_update_walks(t_in, t_out, tok, radius, k, offset, 1e-3, 9, centre_id_base=40)
+    assert float((w[1].to_tensor() - t_out).abs().max()) < 2e-6 and float((w[0].to_tensor() - t_in).abs().max()) < 2e-6
+    w[0].close(); w[1].close()
+
+
 def test_host_step_on_sharded_tables_matches_device_calls():
     dev = cuda_device()
     from helpers import random_csr
