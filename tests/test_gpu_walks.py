@@ -285,3 +285,20 @@ def test_thread_kernel_chi_square_on_hub_graph():
     walks = nat.walk(csr, starts, 12, 0.5, 2.0, True, 0, seed=77, kernel=nat.WALK_THREAD).cpu().numpy()
     stat, dof = _chi_square_transitions(walks, og, 0.5, 2.0, True)
     assert dof > 20 and stat < chi2.ppf(1 - 1e-6, dof), (stat, dof)
+
+
+@pytest.mark.parametrize('p,q,node2vec,rule', [(0.5, 2.0, True, 0), (1.0, 0.5, True, 0), (4.0, 0.25, True, 1), (0.25, 4.0, True, 1), (1.0, 1.0, False, 0)])
+def test_production_walks_equal_the_python_restatement_bit_for_bit(p, q, node2vec, rule):
+    """Both production kernels == tests/walk_model.py (Philox keys, return-edge split, fp32 acceptance arithmetic) on a random graph
+    and on the degree-400 hub graph: the sampler is pinned bit for bit, on top of the chi-square tests against the reference rule."""
+    import walk_model
+    dev = cuda_device()
+    z = np.load(os.path.join(GOLDEN, 'walks_star_hub.npz'))
+    for rowptr, col in (random_csr(300, 1500, seed=17, sort_rows=True), (z['rowptr'], np.concatenate([np.sort(z['col'][a:b]) for a, b in zip(z['rowptr'][:-1], z['rowptr'][1:])]).astype(np.int32))):
+        csr = CSRGraph.from_arrays(rowptr, col, device=dev)
+        n = len(rowptr) - 1
+        starts = np.random.default_rng(4).integers(0, n, 300).astype(np.int32)
+        want = walk_model.walks(rowptr, csr.col_sorted.cpu().numpy(), starts, 21, p, q, node2vec, rule == 0, seed=1234, walk_id_base=50, walk_id_stride=3)
+        for kern in (nat.WALK_WARP, nat.WALK_THREAD):
+            got = nat.walk(csr, torch.from_numpy(starts).to(dev), 21, p, q, node2vec, rule, seed=1234, walk_id_base=50, walk_id_stride=3, kernel=kern)
+            assert np.array_equal(got.cpu().numpy(), want), (kern, np.argwhere(got.cpu().numpy() != want)[:5])
