@@ -302,3 +302,25 @@ def test_production_walks_equal_the_python_restatement_bit_for_bit(p, q, node2ve
         for kern in (nat.WALK_WARP, nat.WALK_THREAD):
             got = nat.walk(csr, torch.from_numpy(starts).to(dev), 21, p, q, node2vec, rule, seed=1234, walk_id_base=50, walk_id_stride=3, kernel=kern)
             assert np.array_equal(got.cpu().numpy(), want), (kern, np.argwhere(got.cpu().numpy() != want)[:5])
+
+
+@pytest.mark.parametrize('p,q', [(0.5, 2.0), (1.0, 0.5), (2.0, 1.0)])
+def test_weighted_production_walks_equal_the_python_restatement_bit_for_bit(p, q):
+    """Weighted graphs (karate club with its integer weights, a random graph with symmetric weights 1..9): both production kernels ==
+    tests/walk_model.py, including the fp64 weighted neighbour pick and the remembered weight of the return edge."""
+    import walk_model
+    dev = cuda_device()
+    z = np.load(os.path.join(GOLDEN, 'walks_karate_yaml.npz'))
+    rowptr2, col2 = random_csr(200, 900, seed=23, sort_rows=True)
+    src = np.repeat(np.arange(200), np.diff(rowptr2))
+    lo, hi = np.minimum(src, col2).astype(np.int64), np.maximum(src, col2).astype(np.int64)
+    w2 = (1 + (lo * 1000003 + hi * 7919) % 9).astype(np.float64)
+    for rowptr, col, w in ((z['rowptr'], z['col'], z['w']), (rowptr2, col2, w2)):
+        csr = CSRGraph.from_arrays(rowptr, col, w, True, device=dev)
+        n = len(rowptr) - 1
+        starts = np.random.default_rng(6).integers(0, n, 200).astype(np.int32)
+        want = walk_model.walks(csr.rowptr.cpu().numpy(), csr.col_sorted.cpu().numpy(), starts, 17, p, q, True, True, seed=77, walk_id_base=9,
+                                wcdf=csr.wcdf.cpu().numpy())
+        for kern in (nat.WALK_WARP, nat.WALK_THREAD):
+            got = nat.walk(csr, torch.from_numpy(starts).to(dev), 17, p, q, True, 0, seed=77, walk_id_base=9, kernel=kern)
+            assert np.array_equal(got.cpu().numpy(), want), (kern, np.argwhere(got.cpu().numpy() != want)[:5])
