@@ -38,6 +38,9 @@ class CSRGraph:
     def device(self):
         return self.rowptr.device
 
+    def __len__(self) -> int:
+        return self.n_nodes
+
     @property
     def weighted(self) -> bool:
         return self.w is not None

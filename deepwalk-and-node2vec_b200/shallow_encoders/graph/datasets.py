@@ -31,10 +31,17 @@ class RandomWalkDataset:
         self._walk_generator: RandomWalk = random_walk_factory(
             name=method, graph=graph, length=walk_length, additional_params=method_params or {})
         self._walks_per_node = walks_per_node
-        self._order = list(range(len(graph)))       # node ids (lexicographic rank), shuffled per epoch (:45, :87)
-        random.shuffle(self._order)
+        self._order = self._shuffled(len(graph))    # node ids (lexicographic rank), shuffled per epoch (:45, :87)
         self._epoch = 0
         self._pending: Optional[Iterator[str]] = None
+
+    @staticmethod
+    def _shuffled(n: int) -> torch.Tensor:
+        """A fresh permutation of the node ids driven by python's `random` state, like the reference's `random.shuffle(nodes)`
+        (seed `random` to reproduce it); a tensor permutation so that 10 M-node graphs do not shuffle a python list."""
+        gen = torch.Generator()
+        gen.manual_seed(random.getrandbits(62))
+        return torch.randperm(n, generator=gen).to(torch.int32)
 
     # -- reference protocol --------------------------------------------------------------------------------------
     @property
@@ -83,8 +90,7 @@ class RandomWalkDataset:
     def epoch_starts(self) -> torch.Tensor:
         """Start node of every walk of the current epoch: node k of the shuffled order, walks_per_node times in a
         row (`nodes[index // walks_per_node]`, reference :76)."""
-        order = torch.tensor(self._order, dtype=torch.int32)
-        return order.repeat_interleave(self._walks_per_node)
+        return self._order.repeat_interleave(self._walks_per_node)
 
     def epoch_walks(self, seed: Optional[int] = None, rank: int = 0, world: int = 1) -> torch.Tensor:
         """All walks of one epoch, int32 node ids [len(self), walk_length] on the device; reshuffles the node order
@@ -95,7 +101,7 @@ class RandomWalkDataset:
         starts = self.epoch_starts()[rank::world].contiguous().to(gen.csr.device, non_blocking=True)
         walks = gen.walk_batch(starts, seed=seed, walk_id_base=self._epoch * len(self) + rank, walk_id_stride=world)
         self._epoch += 1
-        random.shuffle(self._order)
+        self._order = self._shuffled(len(self._graph))
         return walks
 
 
@@ -181,3 +187,18 @@ class SyntheticCoraDataset(RandomWalkDataset):
         labels = {names[i]: str(int(label[i])) for i in range(n_nodes)}
         super().__init__(graph=graph, walks_per_node=walks_per_node, walk_length=walk_length, method=method,
                          labels=labels, **kwargs)
+
+
+@register_dataset('graph_powerlaw_synthetic')
+class SyntheticPowerLawDataset(RandomWalkDataset):
+    """Large unlabelled power-law graph generated on the device (shallow_encoders/graph/synthetic.py), the shape of
+    BASELINE.json's 10 M-node / 250 M-edge configuration; registered like the reference's graphs (datasets.py:126-221) so that
+    `tools/train.py --config-name=sge_sg_powerlaw_synthetic` drives the walk + SGNS hot path at scale.  The graph lives only as
+    CSR in HBM (`.graph` is the CSRGraph; there is no networkx object), node names are n0000000.. in id order."""
+
+    def __init__(self, walks_per_node: int, walk_length: int, method: str = 'node2vec', n_nodes: int = 1_000_000,
+                 n_edges: int = 25_000_000, seed: int = 0, **kwargs):
+        from shallow_encoders.graph.synthetic import powerlaw_graph_device
+        assert n_nodes <= 10_000_000, 'node names n%07d keep their lexicographic = numeric order up to 10^7 nodes'
+        csr = powerlaw_graph_device(n_nodes, n_edges, seed, 'cuda')
+        super().__init__(graph=csr, walks_per_node=walks_per_node, walk_length=walk_length, method=method, **kwargs)

@@ -147,3 +147,23 @@ def test_train_tool_karate_end_to_end(engine, tmp_path):
     mean_acc, best = node_classification(trainer.model.input_embedding.numpy(), dataset.vocab.get_itos(), dataset.labels,
                                          instantiate(nc['split_algorithm']), 20)
     assert mean_acc >= 0.85, (engine, mean_acc, best)
+
+
+def test_powerlaw_synthetic_dataset_trains_through_the_cli_config(tmp_path):
+    """`graph_powerlaw_synthetic` (registered like the reference's graphs) + configs/sge_sg_powerlaw_synthetic.yaml at a small size:
+    the CSR-only dataset feeds the fused engine, the loss falls, the checkpoint has the reference's keys."""
+    from shallow_encoders.config_parser import load_config
+    from shallow_encoders.word2vec.dataloader.registry import DATASET_REGISTRY
+    from tools.train import train
+    cuda_device()
+    assert 'graph_powerlaw_synthetic' in DATASET_REGISTRY
+    over = ['datamodule.additional_parameters.n_nodes=20000', 'datamodule.additional_parameters.n_edges=200000', 'datamodule.batch_size=16384',
+            'datamodule.additional_parameters.walks_per_node=4', 'datamodule.additional_parameters.walk_length=40', 'train.max_epochs=3',
+            f'train.fused_lr={0.025 * 16384 * 30 * 10}', f'path.output_dir={tmp_path}']
+    cfg = load_config('sge_sg_powerlaw_synthetic', over)
+    trainer, ds = train(cfg, quiet=True)
+    assert len(ds) == 80000 and len(ds.vocab) == 20001 and ds.vocab.get_itos()[1] == 'n0000000'
+    losses = trainer.logged['train-epoch/loss']
+    assert len(losses) == 3 and losses[-1] < losses[0] - 0.3, losses
+    ckpt = torch.load(os.path.join(str(tmp_path), 'graph_powerlaw_synthetic', cfg.train.experiment, 'checkpoints', 'last.ckpt'), map_location='cpu')
+    assert ckpt['state_dict']['_model._input_embedding.weight'].shape == (20001, 128)
