@@ -39,6 +39,16 @@ sample_negatives_kernel(const float *__restrict__ prob, const int32_t *__restric
         out[i] = draw_row(prob, alias, vocab, r.x, r.y);
     }
 }
+__global__ void __launch_bounds__(256)
+check_ids_kernel(const int32_t *__restrict__ ids, int64_t n, int64_t lo, int64_t hi, int32_t *__restrict__ bad_count) {
+    int bad = 0;
+    for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (int64_t)gridDim.x * blockDim.x) {
+        const int64_t v = ids[i];
+        bad += (v < lo) | (v >= hi);
+    }
+    bad = __reduce_add_sync(FULL, bad);
+    if ((threadIdx.x & 31) == 0 && bad) atomicAdd(bad_count, bad);
+}
 }  // namespace
 }  // namespace se
 
@@ -155,4 +165,15 @@ extern "C" int se_host_sgns_update_tokens(const int32_t *tokens_host, int64_t n_
     SE_CUDA(cudaMemcpyAsync(stats_host, stats_dev, sizeof(double) * SE_STATS_LEN, cudaMemcpyDeviceToHost, st));
     SE_CUDA(cudaStreamSynchronize(st));
     return SE_OK;
+}
+
+extern "C" int se_check_ids(const int32_t *ids, int64_t n, int64_t lo, int64_t hi, int32_t *bad_count, void *stream) {
+    SE_REQUIRE(n >= 0 && bad_count && (ids || n == 0), "se_check_ids: bad arguments");
+    if (n == 0) return SE_OK;
+    const int sms = se::sm_count();
+    if (sms <= 0) return SE_ERR_CUDA;
+    int64_t blocks = (n + 255) / 256;
+    if (blocks > (int64_t)sms * 8) blocks = (int64_t)sms * 8;
+    se::check_ids_kernel<<<(int)blocks, 256, 0, (cudaStream_t)stream>>>(ids, n, lo, hi, bad_count);
+    return se::check_cuda(cudaGetLastError(), "check_ids_kernel launch");
 }

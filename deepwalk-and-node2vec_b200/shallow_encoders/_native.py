@@ -78,6 +78,7 @@ _SIGNATURES = {
     'se_edge_features': (c_int, [c_p, c_i64, c_int, c_p, c_p, c_i64, c_int, c_p, c_p]),
     'se_edge_op': (c_int, [c_p, c_p, c_i64, c_int, c_p, c_p]),
     'se_sample_negative_edges': (c_int, [c_p, c_p, c_i64, c_i64, c_u64, c_i64, c_p, c_p, c_p, c_p]),
+    'se_check_ids': (c_int, [c_p, c_i64, c_i64, c_i64, c_p, c_p]),
     'se_table_fill_uniform': (c_int, [c_p, c_i64, c_f32, c_u64, c_i64, c_int, c_int, c_p]),
     'se_table_gather_rows': (c_int, [c_p, c_int, c_p, c_i64, c_p, c_p]),
     'se_table_scatter_rows': (c_int, [c_p, c_int, c_p, c_i64, c_p, c_p]),
@@ -354,16 +355,33 @@ def sgns_step(w_in: torch.Tensor, w_out: torch.Tensor, inputs: torch.Tensor, tar
     return _stats_dict(stats) if own_stats else None
 
 
+def check_ids(ids: torch.Tensor, lo: int, hi: int, what: str = 'ids') -> None:
+    """Raise IndexError (as the reference's nn.Embedding does) if any id is outside [lo, hi); synchronises."""
+    global _launches
+    bad = torch.zeros(1, dtype=torch.int32, device=ids.device)
+    with _on(ids):
+        _check(load().se_check_ids(_ptr(ids, torch.int32, what), ids.numel(), int(lo), int(hi), bad.data_ptr(), _stream()))
+    _launches += 1
+    n_bad = int(bad.item())
+    if n_bad:
+        raise IndexError(f'{n_bad} of {ids.numel()} {what} are outside [{lo}, {hi})')
+
+
 def sgns_update_walks(w_in, w_out, tokens: torch.Tensor, radius: int, n_neg: int,
                       row_offset: int, lr: float, seed: int, centre_id_base: int = 0,
                       alias: Optional[Dict[str, torch.Tensor]] = None, flags: int = SCATTER_RED,
-                      stats: Optional[torch.Tensor] = None, local_negatives: bool = False) -> Optional[Dict[str, float]]:
+                      stats: Optional[torch.Tensor] = None, local_negatives: bool = False,
+                      check_tokens: bool = False) -> Optional[Dict[str, float]]:
     """The fused hot path on tokens int32 [n_seq, L]: windows + negatives + in-place SGNS update.
     w_in / w_out: CUDA float32 tensors, or ShardedTables striped over several GPUs (then `local_negatives` selects
-    negatives among the rows this GPU owns; `alias`, if given, must be built over those local rows)."""
+    negatives among the rows this GPU owns; `alias`, if given, must be built over those local rows).
+    `check_tokens`: validate token + row_offset against the table first (one extra small launch and a sync) -- for tokens
+    that do not come from `walk` (which only emits valid node ids)."""
     global _launches
     n_seq, seq_len = tokens.shape
     p_in, vocab, emb, s_in, dev = _table(w_in, 'w_in')
+    if check_tokens:
+        check_ids(tokens, -row_offset, vocab - row_offset, 'tokens')
     p_out, vocab_o, emb_o, s_out, _ = _table(w_out, 'w_out')
     if (vocab, emb) != (vocab_o, emb_o):
         raise ValueError('w_in and w_out must have the same shape')

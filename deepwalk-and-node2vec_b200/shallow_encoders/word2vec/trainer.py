@@ -142,7 +142,7 @@ class Word2VecTrainer(nn.Module):
 
     def fused_step(self, tokens: torch.Tensor, context_radius: int, lr: float, row_offset: int = 1, seed: int = 0,
                    alias=None, flags: int = nat.SCATTER_RED, stats: Optional[torch.Tensor] = None,
-                   local_negatives: bool = False) -> Optional[Dict[str, float]]:
+                   local_negatives: bool = False, check_tokens: bool = False) -> Optional[Dict[str, float]]:
         """In-place SGNS update from int32 token sequences [n_seq, L] in HBM; `lr` multiplies the un-averaged per-pair
         gradient (for the reference's mean loss over a launch of P pairs pass lr_batch / P)."""
         w_in, w_out = self._model.tables
@@ -150,7 +150,7 @@ class Word2VecTrainer(nn.Module):
         n_cen = tokens.shape[1] - 2 * context_radius
         return nat.sgns_update_walks(w_in, w_out, tokens, context_radius, self._neg_samples, row_offset, lr, seed,
                                      centre_id_base=launch * tokens.shape[0] * max(n_cen, 1), alias=alias, flags=flags, stats=stats,
-                                     local_negatives=local_negatives)
+                                     local_negatives=local_negatives, check_tokens=check_tokens)
 
     # -- checkpoints (state-dict keys `_model._input_embedding.weight`, `_model._output_embedding.weight`) ---------------
     def save_checkpoint(self, path: str) -> None:

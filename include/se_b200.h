@@ -244,6 +244,11 @@ int se_host_walk_sgns_step_sharded(const int64_t *rowptr, const int32_t *col, co
                                    int flags, const se_shard_spec *spec, int32_t *starts_dev, int32_t *walks_dev,
                                    double *stats_dev, int32_t *walks_host, double *stats_host, void *stream);
 
+/* Input hygiene for token / node ids that come from outside the library (the reference's nn.Embedding raises IndexError on an
+ * out-of-range id, word2vec/model.py:22-23; the fused kernels index the tables unchecked): ADDS to bad_count[0] the number of
+ * ids[i] outside [lo, hi).  The Python wrappers run it before a fused update unless told the ids come from se_walk. */
+int se_check_ids(const int32_t *ids, int64_t n, int64_t lo, int64_t hi, int32_t *bad_count, void *stream);
+
 /* Host-buffer step for sequences that are already token ids (the text path after W2VDataset.sentence_pipeline,
  * word2vec/dataloader/torch_dataset.py:124-156, 205-213: one int32 id per token, sentences of equal length): copies
  * tokens_host[n_seq * seq_len] to tokens_dev, runs the fused window / negatives / SGNS update, copies the SE_STATS_LEN

@@ -383,3 +383,21 @@ def test_host_token_step_equals_device_call():
     assert abs((stats_host[0].item() + stats_host[1].item()) / stats_host[4].item() - st['loss']) < 1e-5
     with pytest.raises(RuntimeError):
         nat.host_sgns_update_tokens(torch.from_numpy(tokens), torch.from_numpy(w_in), b_out, radius, k, 1, 0.025, 5, scratch, stats_dev, stats_host)   # no CPU fallback
+
+
+def test_out_of_range_tokens_raise_like_the_reference_embedding():
+    """nn.Embedding raises IndexError on an id >= num_embeddings (word2vec/model.py:22-23); with check_tokens the fused path does too,
+    before any kernel touches the tables."""
+    dev = cuda_device()
+    w_in = torch.zeros((100, 128), device=dev); w_out = torch.zeros((100, 128), device=dev)
+    good = torch.randint(0, 99, (4, 9), dtype=torch.int32, device=dev)
+    nat.sgns_update_walks(w_in, w_out, good, 2, 3, 1, 0.01, 1, check_tokens=True)
+    for bad_value in (99, -2, 10 ** 6):
+        bad = good.clone(); bad[2, 3] = bad_value
+        before = w_out.clone()
+        with pytest.raises(IndexError, match='outside'):
+            nat.sgns_update_walks(w_in, w_out, bad, 2, 3, 1, 0.01, 1, check_tokens=True)
+        assert torch.equal(w_out, before)
+    nat.check_ids(torch.arange(10, dtype=torch.int32, device=dev), 0, 10)
+    with pytest.raises(IndexError):
+        nat.check_ids(torch.arange(11, dtype=torch.int32, device=dev), 0, 10)
