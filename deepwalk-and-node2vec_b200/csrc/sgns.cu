@@ -937,7 +937,9 @@ int launch_win_t(const SgnsArgs &a, cudaStream_t stream) {
 
 // Returns SE_ERR_UNSUPPORTED when the shape is not covered (caller tries the next kernel).
 int launch_win(const SgnsArgs &a, cudaStream_t stream) {
-    if (a.emb % 4 != 0 || a.emb <= 64 || a.emb > 128 || a.n_neg > 7 || a.radius > 8 || a.scatter_store || a.no_window) return SE_ERR_UNSUPPORTED;
+    // rows of 36..128 floats: one float4 per lane, lanes beyond the row idle (still far fewer instructions per pair than the generic
+    // group-per-centre kernel: measured 1.65x at E = 64 on the Zipf stream); shorter rows pack several centres per warp in sgns_kernel
+    if (a.emb % 4 != 0 || a.emb <= 32 || a.emb > 128 || a.n_neg > 7 || a.radius > 8 || a.scatter_store || a.no_window) return SE_ERR_UNSUPPORTED;
     if (((uintptr_t)a.w_in % 16) || ((uintptr_t)a.w_out % 16)) return SE_ERR_UNSUPPORTED;
     return a.emb == 128 ? launch_win_t<true>(a, stream) : launch_win_t<false>(a, stream);
 }
@@ -1126,7 +1128,7 @@ int launch_ctx_t(const SgnsArgs &a, cudaStream_t stream) {
 // Returns SE_ERR_UNSUPPORTED when the shape is not covered (caller tries the next kernel).
 template <int MODE>
 int launch_ctx(const SgnsArgs &a, cudaStream_t stream) {
-    if (a.emb % 4 != 0 || a.emb <= 64 || a.emb > 128 || a.n_neg > 7) return SE_ERR_UNSUPPORTED;
+    if (a.emb % 4 != 0 || a.emb <= 32 || a.emb > 128 || a.n_neg > 7) return SE_ERR_UNSUPPORTED;
     if (((uintptr_t)a.w_in % 16) || ((uintptr_t)a.w_out % 16)) return SE_ERR_UNSUPPORTED;
     return a.emb == 128 ? launch_ctx_t<MODE, true>(a, stream) : launch_ctx_t<MODE, false>(a, stream);
 }
@@ -1455,9 +1457,9 @@ extern "C" int se_sgns_update_negatives_owned(float *w_in, float *w_out, int64_t
     SE_REQUIRE((alias_prob == nullptr) == (alias_idx == nullptr), "se_sgns_update_negatives_owned: pass both alias arrays or neither");
     if (n_neg == 0 || n_seq == 0) return SE_OK;
     const int64_t sr = spec->stripe_rows;
-    if ((sr & (sr - 1)) || emb % 4 != 0 || emb <= 64 || emb > 128 || n_neg > 7 || ((2 * radius + 3) / 4) * n_neg > 32 ||
+    if ((sr & (sr - 1)) || emb % 4 != 0 || emb <= 32 || emb > 128 || n_neg > 7 || ((2 * radius + 3) / 4) * n_neg > 32 ||
         ((uintptr_t)w_in % 16) || ((uintptr_t)w_out % 16)) {
-        se::set_error("se_sgns_update_negatives_owned: needs 64 < emb <= 128 (multiple of 4), n_neg <= 7, ceil(2r/4)*n_neg <= 32, "
+        se::set_error("se_sgns_update_negatives_owned: needs 32 < emb <= 128 (multiple of 4), n_neg <= 7, ceil(2r/4)*n_neg <= 32, "
                       "16-byte aligned tables and a power-of-two stripe_rows (emb %d, n_neg %d, radius %d, stripe_rows %lld)",
                       emb, n_neg, radius, (long long)sr);
         return SE_ERR_UNSUPPORTED;
