@@ -110,6 +110,44 @@ template <bool FAST> __device__ __forceinline__ float logf_(float x) {
     if constexpr (FAST) return __logf(x); else return logf(x);
 }
 
+// Block-level reduction of the loss statistics (layout: SE_STATS_LEN in se_b200.h): every contributing thread adds into shared
+// memory, then one double atomic per statistic per block goes to `stats`.  Must be reached by all threads of the block.
+__device__ __forceinline__ void flush_stats(double *stats, bool contribute, float loss_pos, float loss_neg, unsigned cnt_recall,
+                                            unsigned cnt_fp, unsigned cnt_pairs, double cnt_neg) {
+    __shared__ double sred[SE_STATS_LEN];
+    if (threadIdx.x < SE_STATS_LEN) sred[threadIdx.x] = 0.0;
+    __syncthreads();
+    if (contribute) {
+        atomicAdd(&sred[0], (double)loss_pos);
+        atomicAdd(&sred[1], (double)loss_neg);
+        atomicAdd(&sred[2], (double)cnt_recall);
+        atomicAdd(&sred[3], (double)cnt_fp);
+        atomicAdd(&sred[4], (double)cnt_pairs);
+        atomicAdd(&sred[5], cnt_neg);
+    }
+    __syncthreads();
+    if (threadIdx.x < SE_STATS_LEN && stats && sred[threadIdx.x] != 0.0) atomicAdd(stats + threadIdx.x, sred[threadIdx.x]);
+}
+
+// Persistent launch geometry shared by the SGNS kernels: enough blocks of SGNS_THREADS for `n_units` at `units_per_block`, capped at one
+// resident wave (SMs x occupancy).  Returns 0 blocks on error (message set).
+template <typename Kernel>
+int persistent_blocks(Kernel kern, size_t smem, int64_t n_units, int units_per_block, bool need_resident = false) {
+    int occ = 0;
+    if (check_cuda(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, kern, SGNS_THREADS, smem), "occupancy") != SE_OK) return 0;
+    if (occ < 1) {
+        if (need_resident) return -1;
+        occ = 1;
+    }
+    const int sms = sm_count();
+    if (sms <= 0) return 0;
+    int64_t blocks = (n_units + units_per_block - 1) / units_per_block;
+    const int64_t cap = (int64_t)sms * occ;
+    if (blocks > cap) blocks = cap;
+    if (blocks < 1) blocks = 1;
+    return (int)blocks;
+}
+
 template <int MODE, int VEC, int G, int R>
 __global__ void __launch_bounds__(SGNS_THREADS)
 sgns_kernel(const SgnsArgs a) {
@@ -279,20 +317,7 @@ sgns_kernel(const SgnsArgs a) {
         }
     }
 
-    // block-level reduction of the statistics: one double atomic per block per statistic
-    __shared__ double sred[SE_STATS_LEN];
-    if (threadIdx.x < SE_STATS_LEN) sred[threadIdx.x] = 0.0;
-    __syncthreads();
-    if (lg == 0 && (cnt_pairs != 0)) {
-        atomicAdd(&sred[0], (double)loss_pos);
-        atomicAdd(&sred[1], (double)loss_neg);
-        atomicAdd(&sred[2], (double)cnt_recall);
-        atomicAdd(&sred[3], (double)cnt_fp);
-        atomicAdd(&sred[4], (double)cnt_pairs);
-        atomicAdd(&sred[5], (double)cnt_pairs * (double)K);
-    }
-    __syncthreads();
-    if (threadIdx.x < SE_STATS_LEN && a.stats && sred[threadIdx.x] != 0.0) atomicAdd(a.stats + threadIdx.x, sred[threadIdx.x]);
+    flush_stats(a.stats, lg == 0 && cnt_pairs != 0, loss_pos, loss_neg, cnt_recall, cnt_fp, cnt_pairs, (double)cnt_pairs * (double)K);
 }
 
 
@@ -511,19 +536,8 @@ sgns_fast_kernel(const SgnsArgs a) {
         }
     }
 
-    __shared__ double sred[SE_STATS_LEN];
-    if (threadIdx.x < SE_STATS_LEN) sred[threadIdx.x] = 0.0;
-    __syncthreads();
-    if (loss_pos != 0.f || loss_neg != 0.f || cnt_pairs != 0 || cnt_fp != 0 || cnt_recall != 0) {
-        atomicAdd(&sred[0], (double)loss_pos);
-        atomicAdd(&sred[1], (double)loss_neg);
-        atomicAdd(&sred[2], (double)cnt_recall);
-        atomicAdd(&sred[3], (double)cnt_fp);
-        atomicAdd(&sred[4], (double)cnt_pairs);
-        atomicAdd(&sred[5], (double)cnt_pairs * (double)K);
-    }
-    __syncthreads();
-    if (threadIdx.x < SE_STATS_LEN && a.stats && sred[threadIdx.x] != 0.0) atomicAdd(a.stats + threadIdx.x, sred[threadIdx.x]);
+    flush_stats(a.stats, loss_pos != 0.f || loss_neg != 0.f || cnt_pairs != 0 || cnt_fp != 0 || cnt_recall != 0, loss_pos, loss_neg, cnt_recall,
+                cnt_fp, cnt_pairs, (double)cnt_pairs * (double)K);
 }
 
 
@@ -691,19 +705,8 @@ sgns_ctx_kernel(const SgnsArgs a) {
         }
     }
 
-    __shared__ double sred[SE_STATS_LEN];
-    if (threadIdx.x < SE_STATS_LEN) sred[threadIdx.x] = 0.0;
-    __syncthreads();
-    if (loss_pos != 0.f || loss_neg != 0.f || cnt_pairs != 0 || cnt_fp != 0 || cnt_recall != 0) {
-        atomicAdd(&sred[0], (double)loss_pos);
-        atomicAdd(&sred[1], (double)loss_neg);
-        atomicAdd(&sred[2], (double)cnt_recall);
-        atomicAdd(&sred[3], (double)cnt_fp);
-        atomicAdd(&sred[4], (double)cnt_pairs);
-        atomicAdd(&sred[5], (double)cnt_pairs * (double)K);
-    }
-    __syncthreads();
-    if (threadIdx.x < SE_STATS_LEN && a.stats && sred[threadIdx.x] != 0.0) atomicAdd(a.stats + threadIdx.x, sred[threadIdx.x]);
+    flush_stats(a.stats, loss_pos != 0.f || loss_neg != 0.f || cnt_pairs != 0 || cnt_fp != 0 || cnt_recall != 0, loss_pos, loss_neg, cnt_recall,
+                cnt_fp, cnt_pairs, (double)cnt_pairs * (double)K);
 }
 
 
@@ -886,19 +889,8 @@ sgns_win_kernel(const SgnsArgs a) {
         }
     }
 
-    __shared__ double sred[SE_STATS_LEN];
-    if (threadIdx.x < SE_STATS_LEN) sred[threadIdx.x] = 0.0;
-    __syncthreads();
-    if (loss_pos != 0.f || loss_neg != 0.f || cnt_pairs != 0 || cnt_fp != 0 || cnt_recall != 0) {
-        atomicAdd(&sred[0], (double)loss_pos);
-        atomicAdd(&sred[1], (double)loss_neg);
-        atomicAdd(&sred[2], (double)cnt_recall);
-        atomicAdd(&sred[3], (double)cnt_fp);
-        atomicAdd(&sred[4], (double)cnt_pairs);
-        atomicAdd(&sred[5], (double)cnt_pairs * (double)K);
-    }
-    __syncthreads();
-    if (threadIdx.x < SE_STATS_LEN && a.stats && sred[threadIdx.x] != 0.0) atomicAdd(a.stats + threadIdx.x, sred[threadIdx.x]);
+    flush_stats(a.stats, loss_pos != 0.f || loss_neg != 0.f || cnt_pairs != 0 || cnt_fp != 0 || cnt_recall != 0, loss_pos, loss_neg, cnt_recall,
+                cnt_fp, cnt_pairs, (double)cnt_pairs * (double)K);
 }
 
 template <int T, bool EXACT>
@@ -906,17 +898,10 @@ int launch_win_one(const SgnsArgs &a, cudaStream_t stream) {
     auto kern = sgns_win_kernel<T, EXACT>;
     const size_t smem = (size_t)(SGNS_THREADS / 32) * 2 * (2 * a.radius + 2) * 32 * sizeof(float4);
     if (check_cuda(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem), "cudaFuncSetAttribute") != SE_OK) return SE_ERR_CUDA;
-    int occ = 0;
-    if (check_cuda(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, kern, SGNS_THREADS, smem), "occupancy") != SE_OK) return SE_ERR_CUDA;
-    if (occ < 1) return SE_ERR_UNSUPPORTED;
-    const int sms = sm_count();
-    if (sms <= 0) return SE_ERR_CUDA;
-    constexpr int GPB = SGNS_THREADS / 32;
-    int64_t blocks = (a.n_units + GPB - 1) / GPB;
-    const int64_t cap = (int64_t)sms * occ;
-    if (blocks > cap) blocks = cap;
-    if (blocks < 1) blocks = 1;
-    kern<<<(int)blocks, SGNS_THREADS, smem, stream>>>(a);
+    const int blocks = persistent_blocks(kern, smem, a.n_units, SGNS_THREADS / 32, true);
+    if (blocks < 0) return SE_ERR_UNSUPPORTED;            // the ring does not fit: the caller falls back to the per-context kernel
+    if (blocks == 0) return SE_ERR_CUDA;
+    kern<<<blocks, SGNS_THREADS, smem, stream>>>(a);
     return check_cuda(cudaGetLastError(), "sgns_win_kernel launch");
 }
 
@@ -961,7 +946,6 @@ __global__ void __launch_bounds__(SGNS_THREADS, 2)
 sgns_negown_kernel(const SgnsArgs a) {
     constexpr int P = 8, SHIFT = 2;
     __shared__ int own_list[SGNS_THREADS / 32][128];      // up to 32 drawing lanes x 4 contexts owned at once (world = 1)
-    __shared__ double sred[SE_STATS_LEN];
     const int lane = threadIdx.x & 31;
     int *list = own_list[threadIdx.x >> 5];
     const int64_t gid = (int64_t)blockIdx.x * (SGNS_THREADS / 32) + (threadIdx.x >> 5);
@@ -1065,48 +1049,24 @@ sgns_negown_kernel(const SgnsArgs a) {
         if (ok) red_vec<4>(a.w_in + crow * E + eoff, acc, a.sys_scope);
     }
 
-    if (threadIdx.x < SE_STATS_LEN) sred[threadIdx.x] = 0.0;
-    __syncthreads();
-    if (cnt_neg != 0) {
-        atomicAdd(&sred[1], (double)loss_neg);
-        atomicAdd(&sred[3], (double)cnt_fp);
-        atomicAdd(&sred[5], (double)cnt_neg);
-    }
-    __syncthreads();
-    if (threadIdx.x < SE_STATS_LEN && a.stats && sred[threadIdx.x] != 0.0) atomicAdd(a.stats + threadIdx.x, sred[threadIdx.x]);
+    flush_stats(a.stats, cnt_neg != 0, 0.f, loss_neg, 0u, cnt_fp, 0u, (double)cnt_neg);
 }
 
 template <bool EXACT>
 int launch_negown(const SgnsArgs &a, cudaStream_t stream) {
     auto kern = sgns_negown_kernel<EXACT>;
-    int occ = 0;
-    if (check_cuda(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, kern, SGNS_THREADS, 0), "occupancy") != SE_OK) return SE_ERR_CUDA;
-    if (occ < 1) occ = 1;
-    const int sms = sm_count();
-    if (sms <= 0) return SE_ERR_CUDA;
-    constexpr int GPB = SGNS_THREADS / 32;
-    int64_t blocks = (a.n_units + GPB - 1) / GPB;
-    const int64_t cap = (int64_t)sms * occ;
-    if (blocks > cap) blocks = cap;
-    if (blocks < 1) blocks = 1;
-    kern<<<(int)blocks, SGNS_THREADS, 0, stream>>>(a);
+    const int blocks = persistent_blocks(kern, 0, a.n_units, SGNS_THREADS / 32);
+    if (blocks <= 0) return SE_ERR_CUDA;
+    kern<<<blocks, SGNS_THREADS, 0, stream>>>(a);
     return check_cuda(cudaGetLastError(), "sgns_negown_kernel launch");
 }
 
 template <int MODE, int T, bool EXACT>
 int launch_ctx_one(const SgnsArgs &a, cudaStream_t stream) {
     auto kern = sgns_ctx_kernel<MODE, T, EXACT>;
-    int occ = 0;
-    if (check_cuda(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, kern, SGNS_THREADS, 0), "occupancy") != SE_OK) return SE_ERR_CUDA;
-    if (occ < 1) occ = 1;
-    const int sms = sm_count();
-    if (sms <= 0) return SE_ERR_CUDA;
-    constexpr int GPB = SGNS_THREADS / 32;
-    int64_t blocks = (a.n_units + GPB - 1) / GPB;
-    const int64_t cap = (int64_t)sms * occ;
-    if (blocks > cap) blocks = cap;
-    if (blocks < 1) blocks = 1;
-    kern<<<(int)blocks, SGNS_THREADS, 0, stream>>>(a);
+    const int blocks = persistent_blocks(kern, 0, a.n_units, SGNS_THREADS / 32);
+    if (blocks <= 0) return SE_ERR_CUDA;
+    kern<<<blocks, SGNS_THREADS, 0, stream>>>(a);
     return check_cuda(cudaGetLastError(), "sgns_ctx_kernel launch");
 }
 
@@ -1136,17 +1096,9 @@ int launch_ctx(const SgnsArgs &a, cudaStream_t stream) {
 template <int MODE, int R, bool EXACT>
 int launch_fast_one(const SgnsArgs &a, cudaStream_t stream) {
     auto kern = sgns_fast_kernel<MODE, R, EXACT>;
-    int occ = 0;
-    if (check_cuda(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, kern, SGNS_THREADS, 0), "occupancy") != SE_OK) return SE_ERR_CUDA;
-    if (occ < 1) occ = 1;
-    const int sms = sm_count();
-    if (sms <= 0) return SE_ERR_CUDA;
-    constexpr int GPB = SGNS_THREADS / 32;
-    int64_t blocks = (a.n_units + GPB - 1) / GPB;
-    const int64_t cap = (int64_t)sms * occ;
-    if (blocks > cap) blocks = cap;
-    if (blocks < 1) blocks = 1;
-    kern<<<(int)blocks, SGNS_THREADS, 0, stream>>>(a);
+    const int blocks = persistent_blocks(kern, 0, a.n_units, SGNS_THREADS / 32);
+    if (blocks <= 0) return SE_ERR_CUDA;
+    kern<<<blocks, SGNS_THREADS, 0, stream>>>(a);
     return check_cuda(cudaGetLastError(), "sgns_fast_kernel launch");
 }
 
@@ -1169,17 +1121,9 @@ int launch_fast(const SgnsArgs &a, cudaStream_t stream) {
 template <int MODE, int VEC, int G, int R>
 int launch_one(const SgnsArgs &a, cudaStream_t stream) {
     auto kern = sgns_kernel<MODE, VEC, G, R>;
-    int occ = 0;
-    if (check_cuda(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, kern, SGNS_THREADS, 0), "occupancy") != SE_OK) return SE_ERR_CUDA;
-    if (occ < 1) occ = 1;
-    const int sms = sm_count();
-    if (sms <= 0) return SE_ERR_CUDA;
-    constexpr int GPB = SGNS_THREADS / G;
-    int64_t blocks = (a.n_units + GPB - 1) / GPB;
-    const int64_t cap = (int64_t)sms * occ;          // persistent: exactly one resident wave
-    if (blocks > cap) blocks = cap;
-    if (blocks < 1) blocks = 1;
-    kern<<<(int)blocks, SGNS_THREADS, 0, stream>>>(a);
+    const int blocks = persistent_blocks(kern, 0, a.n_units, SGNS_THREADS / G);      // exactly one resident wave at most
+    if (blocks <= 0) return SE_ERR_CUDA;
+    kern<<<blocks, SGNS_THREADS, 0, stream>>>(a);
     return check_cuda(cudaGetLastError(), "sgns_kernel launch");
 }
 
@@ -1287,16 +1231,7 @@ ns_loss_kernel(const float *__restrict__ pos, const float *__restrict__ neg, int
             fp += sg >= 0.5f;
         }
     }
-    __shared__ double sred[SE_STATS_LEN];
-    if (threadIdx.x < SE_STATS_LEN) sred[threadIdx.x] = 0.0;
-    __syncthreads();
-    if (cnt) {
-        atomicAdd(&sred[0], (double)lp); atomicAdd(&sred[1], (double)ln);
-        atomicAdd(&sred[2], (double)rec); atomicAdd(&sred[3], (double)fp);
-        atomicAdd(&sred[4], (double)cnt); atomicAdd(&sred[5], (double)cnt * n_neg);
-    }
-    __syncthreads();
-    if (threadIdx.x < SE_STATS_LEN && stats && sred[threadIdx.x] != 0.0) atomicAdd(stats + threadIdx.x, sred[threadIdx.x]);
+    flush_stats(stats, cnt != 0, lp, ln, rec, fp, cnt, (double)cnt * n_neg);
 }
 
 int common_checks(const char *fn, const void *w_in, const void *w_out, int64_t vocab, int emb, int n_neg) {
