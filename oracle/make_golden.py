@@ -12,6 +12,9 @@ Everything written here is produced by the reference's own code:
              (word2vec/model.py:79-91, word2vec/loss.py:14-22) and Word2VecTrainer.training_step
              (word2vec/trainer.py:131-152) with `generate_noise_batch` pinned to a recorded tensor
   vocab_*    GraphDataset vocabulary order           (torch_dataset.py:99-110)
+  downstream perform_node_classification / perform_edge_classification of tools/graph_model_downstream_classification.py
+             (:94-148, :227-299) run UNMODIFIED (hydra / omegaconf / matplotlib / tools.utils stubbed: they only serve the CLI and
+             the plots) on a fixed embedding of the karate-club graph: per-experiment accuracies
   edge_ops   the four edge operators                 (graph/edge_operators.py:10-64) applied the way
              create_edge_embeddings does (tools/graph_model_downstream_classification.py:203-224)
 
@@ -298,6 +301,70 @@ def emit_edge_ops():
     print('edge_ops: 4 operators x 4 embedding sizes')
 
 
+def emit_downstream():
+    """The reference's own downstream evaluation on a FIXED embedding (karate club, E = 8): the accuracy yardstick of the north star,
+    pinned so that tools/downstream.py (the restatement the B200 repo uses) can be checked against it."""
+    import logging
+    import types
+    for name in ('hydra', 'omegaconf', 'matplotlib', 'matplotlib.pyplot'):
+        if name not in sys.modules:
+            sys.modules[name] = types.ModuleType(name)
+    sys.modules['hydra'].main = lambda **_kw: (lambda fn: fn)
+    sys.modules['omegaconf'].DictConfig = dict
+    sys.modules['matplotlib'].pyplot = sys.modules['matplotlib.pyplot']
+    fake_utils = types.ModuleType('tools.utils')
+    fake_utils.setup_pipeline = lambda *a, **k: None
+    fake_utils.MATPLOTLIB_COLORS = ['b', 'g', 'r']
+    sys.modules['tools.utils'] = fake_utils
+    import tools.graph_model_downstream_classification as ref_ds            # the reference's module
+    from shallow_encoders.split import TrainTestRatioSplit as RefSplit
+    assert ref_ds.__file__.startswith(ref_import.REFERENCE_ROOT), ref_ds.__file__
+    logging.disable(logging.CRITICAL)
+
+    karate = ref_datasets.KarateClubDataset(walks_per_node=1, walk_length=4)
+    graph, labels = karate.graph, karate.labels
+    itos = ['<unk>'] + sorted(graph.nodes)
+    rng = np.random.default_rng(2024)
+    emb = rng.standard_normal((len(itos), 8)).astype(np.float32)
+    for i, name in enumerate(itos[1:], start=1):                            # weak class signal + weak neighbourhood signal
+        emb[i, 0] += 0.9 if labels[name] == '1' else -0.9
+    adj_mean = np.zeros_like(emb)
+    for i, name in enumerate(itos[1:], start=1):
+        adj_mean[i] = np.mean([emb[itos.index(x)] for x in graph.neighbors(name)], axis=0)
+    emb = (0.6 * emb + 0.8 * adj_mean).astype(np.float32)
+
+    class FakeModel:
+        input_embedding = torch.from_numpy(emb)
+
+    vocab = ref_import._StubVocab(itos)
+    dataset = types.SimpleNamespace(vocab=vocab, labels=labels, has_features=False, graph=graph)
+
+    accs = []
+    real_fit = ref_ds.create_and_fit_classification_model
+
+    def recording_fit(*a, **k):
+        clf, acc = real_fit(*a, **k)
+        accs.append(acc)
+        return clf, acc
+
+    ref_ds.create_and_fit_classification_model = recording_fit
+    ref_ds.perform_node_classification(model=FakeModel, dataset=dataset, output_path='/tmp', split_algorithm=RefSplit(train_ratio=0.5, test_all=True),
+                                       n_experiments=20, visualize=False, classifier_params=None)
+    node_accs = np.array(accs, dtype=np.float64)
+    accs.clear()
+    random.seed(7)
+    ref_ds.perform_edge_classification(model=FakeModel, dataset=dataset, train_ratio=0.5, n_experiments=300, edge_operator_name='hadamard',
+                                       classifier_params=None)
+    edge_accs = np.array(accs, dtype=np.float64)
+    ref_ds.create_and_fit_classification_model = real_fit
+    logging.disable(logging.NOTSET)
+    edges = np.array([(itos.index(a), itos.index(b)) for a, b in graph.edges], dtype=np.int64)
+    np.savez_compressed(os.path.join(GOLDEN, 'downstream_karate.npz'), meta=np.array(META), embedding=emb, itos=np.array(itos),
+                        labels=np.array([labels[v] for v in itos[1:]]), edges=edges, node_accuracies=node_accs,
+                        edge_accuracies=edge_accs, sklearn=np.array(__import__('sklearn').__version__))
+    print(f'downstream: node acc mean {node_accs.mean():.4f} best {node_accs.max():.4f}; edge acc mean {edge_accs.mean():.4f} (+- {edge_accs.std():.4f})')
+
+
 if __name__ == '__main__':
     os.makedirs(GOLDEN, exist_ok=True)
     emit_walks()
@@ -305,4 +372,5 @@ if __name__ == '__main__':
     emit_sgns()
     emit_vocab()
     emit_edge_ops()
+    emit_downstream()
     print('golden fixtures written to', GOLDEN)
