@@ -20,8 +20,9 @@ no inter-GPU barrier inside a step.  `--negatives local` (default when sharded) 
 rows the GPU owns; `--negatives global` keeps the reference's uniform draw over the whole table (5/6 of the rows then
 cross NVLink) and is reported beside it.  `--multi replicas`: per-GPU replicas averaged by an NCCL all-reduce each step.
 
---impl reference: the reference's CPU path (oracle/cpu_port.py: python walks on all host cores + torch CPU
-SkipGram/loss/backward/Adam) on a bounded sample of the same workload; rank 0 only.
+--impl reference: the UNMODIFIED reference's CPU path (oracle/ref_pipeline.py imports it from /root/reference or from
+the git-ignored byte-for-byte copy baseline/_ref/: Node2Vec.walk on all host cores -> tokenize -> collate ->
+Word2VecTrainer.training_step -> backward -> Adam) on a bounded sample of the same workload; rank 0 only.
 """
 import argparse
 import json
@@ -100,7 +101,8 @@ def parse_args():
     ap.add_argument('--no-cpu-baseline', action='store_true')
     ap.add_argument('--cpu-nodes', type=int, default=100_000, help='node count of the CPU sample graph (same mean degree)')
     ap.add_argument('--cpu-walks-per-step', type=int, default=64, help='reference batch_size (walks per step)')
-    ap.add_argument('--cpu-seconds', type=float, default=15.0, help='target CPU time of the cpu_baseline sample')
+    ap.add_argument('--cpu-steps', type=int, default=8, help='timed steps of the cpu_baseline sample (about 10-30 s of CPU work)')
+    ap.add_argument('--cpu-port', action='store_true', help='time oracle/cpu_port.py (the restated pattern) instead of the unmodified reference')
     return ap.parse_args()
 
 
@@ -228,53 +230,64 @@ def recorded_traffic():
 
 
 # --------------------------------------------------------------------------------------------------------------
-def run_reference(a, rank, world):
-    """CPU arm: the reference's path (oracle port) on all host cores, bounded sample of the same workload."""
-    if rank != 0:
-        return
-    from oracle import cpu_port
+def _reference_sample(a, steps, warmup):
+    """The CPU arm on a bounded sample of the S3 workload.  Preferred: the UNMODIFIED reference (oracle/ref_pipeline.py in its own
+    process: /root/reference, or the byte-for-byte copy under baseline/_ref/ that travels to the GPU box), kind "reference".
+    Only if the reference cannot be imported: oracle/cpu_port.py (same pattern restated; faster than the reference because it tests
+    membership on sets), kind "port"."""
     cores = os.cpu_count() or 1
     nodes = min(a.cpu_nodes, a.nodes)
     edges = int(round(a.edges * (nodes / a.nodes)))
+    why = None
+    if not a.cpu_port:
+        from oracle import ref_pipeline
+        r = ref_pipeline.call(nodes=nodes, edges=edges, method='node2vec', p=a.p, q=a.q, walk_len=a.walk_len,
+                              walks_per_node=a.walks_per_node, walks_per_step=a.cpu_walks_per_step, radius=a.radius, emb=a.emb,
+                              neg=a.neg, optimizer='adam', lr=0.1, steps=steps, warmup=warmup, workers=cores, seed=a.seed)
+        if 'unavailable' not in r:
+            what = (f'{steps} steps x {a.cpu_walks_per_step} walks (reference batch_size; {r["seconds"]:.1f} s CPU) on a {r["graph"]["nodes"]}-node / '
+                    f'{r["graph"]["edges"]}-edge power-law sample of S3 (same generator, same mean degree); the UNMODIFIED reference from '
+                    f'{"baseline/_ref (byte-for-byte copy)" if "baseline" in r["reference_root"] else r["reference_root"]}: Node2Vec.walk in {cores} worker '
+                    f'processes -> tokenize -> vocab -> W2VCollateFunctional -> Word2VecTrainer.training_step -> backward -> torch.optim.Adam '
+                    f'({r["torch_threads"]} threads); walk {r["walk_steps_per_s"]:.3g} steps/s, sgns {r["sgns_pairs_per_s"]:.3g} pairs/s')
+            return r, 'reference', what, cores
+        why = r['unavailable']
+    from oracle import cpu_port
     g = cpu_port.powerlaw_graph_host(nodes, edges, a.seed)
-    r = cpu_port.run_reference_pipeline(g, a.cpu_walks_per_step, a.steps, a.warmup, a.walk_len, a.p, a.q, True, a.radius,
+    r = cpu_port.run_reference_pipeline(g, a.cpu_walks_per_step, steps, warmup, a.walk_len, a.p, a.q, True, a.radius,
                                         a.emb, a.neg, cores, optimizer='adam', seed=a.seed)
-    sample = (f'{a.steps} steps x {a.cpu_walks_per_step} walks (reference batch_size) on a {nodes}-node / {edges}-edge power-law '
-              f'sample of S3 (same generator, same mean degree); python walks on {cores} processes + torch CPU '
-              f'SkipGram/loss/backward/dense Adam with {cores} threads; walk {r["walk_steps_per_s"]:.3g} steps/s, '
-              f'sgns {r["sgns_pairs_per_s"]:.3g} pairs/s')
+    what = (f'{steps} steps x {a.cpu_walks_per_step} walks ({r["seconds"]:.1f} s CPU) on a {nodes}-node / {edges}-edge power-law sample of S3; '
+            f'oracle/cpu_port.py = the reference pattern restated (python node2vec walks on {cores} processes, python collate, torch CPU '
+            f'SkipGram + loss + backward + dense Adam, {cores} threads)' + (f'; reference itself unavailable: {why}' if why else ''))
+    return r, 'port', what, cores
+
+
+def run_reference(a, rank, world):
+    """CPU arm (`--impl reference`): the reference's own CPU implementation of the path on all host cores, bounded sample of
+    the same workload; rank 0 only."""
+    if rank != 0:
+        return
+    r, kind, sample, cores = _reference_sample(a, a.steps, a.warmup)
     cfg = workload_config(a, 1)
     cfg['parallelism'] = f'{cores} host cores'
     cfg['optimizer'] = 'torch.optim.Adam on dense tables (as every shipped YAML, e.g. configs/sge_sg_cora.yaml:32-34)'
+    cfg['cpu_sample'] = {'nodes': min(a.cpu_nodes, a.nodes), 'walks_per_step': a.cpu_walks_per_step}
     line = {
         'impl': 'reference', 'metric': METRIC, 'value': r['pairs_per_s'], 'unit': UNIT, 'n_gpus': a.gpus, 'steps': a.steps,
         'warmup': a.warmup, 'ms_per_step': r['ms_per_step'], 'higher_is_better': True, 'scaling': 'weak', 'vs_baseline': None,
         'dtype': 'f32', 'data': 'synthetic', 'config': cfg,
-        'cpu_baseline': {'value': r['pairs_per_s'], 'unit': UNIT, 'cores': cores, 'kind': 'port', 'sample': sample},
+        'cpu_baseline': {'value': r['pairs_per_s'], 'unit': UNIT, 'cores': cores, 'kind': kind, 'sample': sample},
         'e2e': {'value': r['pairs_per_s'], 'unit': UNIT, 'h2d_bytes_per_step': 0, 'd2h_bytes_per_step': 0},
-        'walk_steps_per_s': r['walk_steps_per_s'], 'gpu_launches': 0,
+        'walk_steps_per_s': r['walk_steps_per_s'], 'sgns_pairs_per_s': r['sgns_pairs_per_s'], 'gpu_launches': 0,
     }
     emit(line)
 
 
 def cpu_baseline(a):
-    from oracle import cpu_port
-    cores = os.cpu_count() or 1
-    nodes = min(a.cpu_nodes, a.nodes)
-    edges = int(round(a.edges * (nodes / a.nodes)))
-    g = cpu_port.powerlaw_graph_host(nodes, edges, a.seed)
-    probe = cpu_port.run_reference_pipeline(g, a.cpu_walks_per_step, 2, 1, a.walk_len, a.p, a.q, True, a.radius, a.emb, a.neg,
-                                            cores, optimizer='adam', seed=a.seed)
-    steps = max(3, min(200, int(a.cpu_seconds / max(probe['seconds'] / 2, 1e-3))))
-    r = cpu_port.run_reference_pipeline(g, a.cpu_walks_per_step, steps, 1, a.walk_len, a.p, a.q, True, a.radius, a.emb, a.neg,
-                                        cores, optimizer='adam', seed=a.seed + 1)
-    return {
-        'value': r['pairs_per_s'], 'unit': UNIT, 'cores': cores, 'kind': 'port',
-        'sample': (f'{steps} steps x {a.cpu_walks_per_step} walks ({r["seconds"]:.1f} s CPU) on a {nodes}-node / {edges}-edge '
-                   f'power-law sample of S3; oracle/cpu_port.py = reference pattern: python node2vec walks on {cores} '
-                   f'processes, python collate, torch CPU SkipGram + loss + backward + dense Adam ({cores} threads)'),
-        'walk_steps_per_s': r['walk_steps_per_s'], 'sgns_pairs_per_s': r['sgns_pairs_per_s'],
-    }
+    steps = max(3, int(a.cpu_steps))
+    r, kind, sample, cores = _reference_sample(a, steps, 1)
+    return {'value': r['pairs_per_s'], 'unit': UNIT, 'cores': cores, 'kind': kind, 'sample': sample,
+            'walk_steps_per_s': r['walk_steps_per_s'], 'sgns_pairs_per_s': r['sgns_pairs_per_s']}
 
 
 # --------------------------------------------------------------------------------------------------------------

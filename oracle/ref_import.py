@@ -1,10 +1,11 @@
 """
 TEST INFRASTRUCTURE ONLY -- never imported by the product path.
 
-Import shim for the UNMODIFIED reference at /root/reference (read-only, present only in
-the build container, never on the GPU box).  Used exclusively by `oracle/make_golden.py`
-to (a) validate the oracle restatements against the real reference and (b) generate the
-golden vectors committed under `tests/golden/`.
+Import shim for the UNMODIFIED reference: /root/reference (read-only, present only in the build
+container) or its byte-for-byte, git-ignored copy under baseline/_ref/ (oracle/vendor_ref.py), which
+travels to the GPU box.  Used by `oracle/make_golden.py` to (a) validate the oracle restatements against
+the real reference and (b) generate the golden vectors committed under `tests/golden/`, and by
+`oracle/ref_pipeline.py` (bench.py's `--impl reference` / `cpu_baseline` legs) to TIME the real reference.
 
 Three third-party packages the reference imports are not installable offline, so in-memory
 stubs with the documented behaviour are registered before the reference modules load:
@@ -21,7 +22,19 @@ import sys
 import types
 from collections import Counter
 
-REFERENCE_ROOT = os.environ.get('SE_REFERENCE_ROOT', '/root/reference')
+_REPO = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+VENDORED_ROOT = os.path.join(_REPO, 'baseline', '_ref')      # git-ignored byte-for-byte copy (oracle/vendor_ref.py)
+
+
+def reference_root():
+    """/root/reference where it is mounted (the build container), else the vendored copy that travels to the GPU box."""
+    for cand in (os.environ.get('SE_REFERENCE_ROOT'), '/root/reference', VENDORED_ROOT):
+        if cand and os.path.isdir(os.path.join(cand, 'shallow_encoders')):
+            return cand
+    return None
+
+
+REFERENCE_ROOT = reference_root() or '/root/reference'
 
 
 class _StubVocab:

@@ -45,4 +45,15 @@ def test_reference_arm_prints_one_json_line_on_a_tiny_sample():
     assert out.returncode == 0, out.stderr[-2000:]
     line = json.loads(out.stdout.strip().splitlines()[-1])
     assert line['impl'] == 'reference' and line['metric'] == 'sgns_pairs_per_s' and line['value'] > 0
-    assert line['cpu_baseline']['kind'] == 'port' and line['e2e']['h2d_bytes_per_step'] == 0 and line['gpu_launches'] == 0
+    from oracle import ref_import
+    want = 'reference' if ref_import.reference_root() else 'port'          # the unmodified reference wherever it can be imported
+    assert line['cpu_baseline']['kind'] == want and line['e2e']['h2d_bytes_per_step'] == 0 and line['gpu_launches'] == 0
+    assert ('UNMODIFIED reference' in line['cpu_baseline']['sample']) == (want == 'reference')
+
+
+def test_reference_arm_can_still_time_the_port():
+    out = subprocess.run([sys.executable, os.path.join(ROOT, 'bench.py'), '--impl', 'reference', '--cpu-port', '--steps', '1', '--warmup', '1',
+                          '--cpu-nodes', '2000', '--cpu-walks-per-step', '8', '--walk-len', '12', '--emb', '16'], capture_output=True, text=True, timeout=600)
+    assert out.returncode == 0, out.stderr[-2000:]
+    line = json.loads(out.stdout.strip().splitlines()[-1])
+    assert line['cpu_baseline']['kind'] == 'port' and line['value'] > 0
