@@ -90,8 +90,11 @@ def parse_args():
     ap.add_argument('--seed', type=int, default=0)
     ap.add_argument('--kernel', default='window', choices=['window', 'context'],
                     help='window: context rows resident in shared memory while in the window; context: gathered per pair')
-    ap.add_argument('--multi', default='sharded', choices=['sharded', 'replicas', 'a2a'],
-                    help='N > 1: sharded = one striped table pair over NVLink peer memory (product); a2a = the NCCL all-to-all baseline; replicas')
+    ap.add_argument('--multi', default='synced', choices=['synced', 'sharded', 'replicas', 'a2a'],
+                    help='N > 1: synced = the reference\'s global negative draw on per-GPU working copies + row-sharded masters, one fused '
+                         'reduce-scatter/all-gather kernel over peer memory per step (product, reference-exact draw); sharded = one striped table '
+                         'pair gathered / red.added per pair over NVLink (capacity mode; --negatives local|global|owner); a2a = the NCCL all-to-all '
+                         'baseline; replicas = NCCL all-reduce averaging')
     ap.add_argument('--a2a-micro-walks', type=int, default=8192, help='a2a baseline: walks per exchange micro-batch')
     ap.add_argument('--negatives', default='auto', choices=['auto', 'local', 'global', 'owner'],
                     help='sharded tables: local (auto) = draw negatives among the rows the GPU owns; global = reference draw over the whole table, rows '
@@ -111,6 +114,11 @@ def parallelism(a, n_gpus):
         return 'single GPU' + (' (tables in a 1-shard VMM mapping)' if a.tables == 'vmm' else '')
     if a.multi == 'replicas':
         return f'dp{n_gpus}: walks sharded by id, table replicas averaged by NCCL all-reduce every step'
+    if a.multi == 'synced':
+        return (f'dp{n_gpus}: walks sharded by id (replicated CSR, no communication); both tables row-sharded into {n_gpus} master chunks (rows by node id) '
+                f'+ one working copy per GPU; every GPU runs the single-GPU fused kernel with the reference\'s uniform draw over the WHOLE table, then '
+                f'ONE kernel per table sums the updates of all copies into the masters and writes the rows back over NVLink peer memory '
+                f'(fused reduce-scatter + all-gather, csrc/replica.cu); no NCCL on the data path')
     neg = 'local' if a.negatives == 'auto' else a.negatives
     if a.multi == 'a2a':
         return (f'dp{n_gpus} NCCL BASELINE: tables row-sharded by row % {n_gpus}; per micro-batch of {a.a2a_micro_walks} walks: unique ids -> '
@@ -131,6 +139,7 @@ def workload_config(a, n_gpus):
         'emb': a.emb, 'context_radius': a.radius, 'negatives': a.neg,
         'negative_sampling': ('uniform over the rows owned by the GPU (walks are dealt to GPUs by id)'
                               if (n_gpus > 1 and a.multi in ('sharded', 'a2a') and a.negatives in ('auto', 'local')) else 'uniform (reference)'),
+        'table_sync': ('every step: master += sum over GPUs of (working copy - master), written back to all copies' if n_gpus > 1 and a.multi == 'synced' else None),
         'optimizer': 'in-place SGD (Hogwild, red.global.add.v4.f32)' if a.scatter == 'red' else 'in-place SGD (Hogwild, plain stores)',
         'parallelism': parallelism(a, n_gpus),
         'l2': 'inputs exceed L2 (tables 2 x %.2f GB, CSR ~%.1f GB); no flush' % ((a.nodes + 1) * a.emb * 4 / 1e9, (2 * a.edges * 4 + a.nodes * 8) / 1e9),
@@ -197,6 +206,24 @@ class ClockSampler(threading.Thread):
         s = sorted(self.samples)
         return {'sm_mhz': s[len(s) // 2], 'sm_max_mhz': self.max_mhz, 'reasons': sorted(self.reasons - {'gpu_idle'}),
                 'samples': len(s), 'power_w_max': max(self.power) if self.power else None}
+
+
+def nvlink_bytes(index):
+    """(tx, rx) NVLink data bytes of GPU `index` since driver start (NVML field values, all links), or None."""
+    try:
+        import pynvml
+        pynvml.nvmlInit()
+        h = pynvml.nvmlDeviceGetHandleByIndex(index)
+        vals = pynvml.nvmlDeviceGetFieldValues(h, [(pynvml.NVML_FI_DEV_NVLINK_THROUGHPUT_DATA_TX, 0xFFFFFFFF),
+                                                   (pynvml.NVML_FI_DEV_NVLINK_THROUGHPUT_DATA_RX, 0xFFFFFFFF)])
+        out = []
+        for v in vals:
+            if v.nvmlReturn != 0:
+                return None
+            out.append(int(v.value.ullVal) * 1024)          # the counters are in KiB
+        return tuple(out)
+    except Exception:   # noqa: BLE001
+        return None
 
 
 def nvml_index(local_rank):
@@ -311,6 +338,8 @@ def run_b200(a, rank, local_rank, world):
     fallback_note = None
     sharded = (world > 1 and a.multi == 'sharded') or (world == 1 and a.tables == 'vmm')
     a2a = world > 1 and a.multi == 'a2a'
+    synced = world > 1 and a.multi == 'synced'
+    ex = None
     neg_mode = 'global'
     if (sharded or a2a) and world > 1:
         neg_mode = 'local' if a.negatives == 'auto' else a.negatives
@@ -321,15 +350,16 @@ def run_b200(a, rank, local_rank, world):
         tables = RowShardedTables(vocab, a.emb, rank, world, dev)
         tables.fill_uniform(bound, a.seed + 101, a.seed + 102)
         w_in = w_out = None
-    elif sharded:
-        # Striped tables need CUDA VMM handle export between processes (POSIX fds over unix sockets).  If the platform
+    elif sharded or synced:
+        # Peer-mapped tables need CUDA VMM handle export between processes (POSIX fds over unix sockets).  If the platform
         # refuses that on ANY rank, every rank drops to the replica mode (still the same CUDA kernels) and the line says so.
-        from shallow_encoders.word2vec.sharded import ShardedTable, make_exchange
-        ex = w_in = w_out = None
+        from shallow_encoders.word2vec.sharded import ReplicatedTable, ShardedTable, make_exchange
+        w_in = w_out = None
         try:
             ex = make_exchange(rank, world)
-            w_in = ShardedTable(vocab, a.emb, dev, rank, world, ex)
-            w_out = ShardedTable(vocab, a.emb, dev, rank, world, ex)
+            make = ReplicatedTable if synced else ShardedTable
+            w_in = make(vocab, a.emb, dev, rank, world, ex)
+            w_out = make(vocab, a.emb, dev, rank, world, ex)
             ok, why = 1, ''
         except Exception as e:   # noqa: BLE001
             ok, why = 0, repr(e)
@@ -343,16 +373,24 @@ def run_b200(a, rank, local_rank, world):
             for t in (w_in, w_out):
                 if t is not None:
                     t.close()
-            sharded, local_neg, neg_mode, fallback_note = False, False, 'global', f'striped tables unavailable ({why or "on another rank"}): ran --multi replicas'
+            sharded, synced, local_neg, neg_mode = False, False, False, 'global'
+            fallback_note = f'peer-mapped tables unavailable ({why or "on another rank"}): ran --multi replicas'
             a.multi = 'replicas'
             w_in = torch.empty((vocab, a.emb), dtype=torch.float32, device=dev)
             w_out = torch.empty((vocab, a.emb), dtype=torch.float32, device=dev)
     else:
         w_in = torch.empty((vocab, a.emb), dtype=torch.float32, device=dev)
         w_out = torch.empty((vocab, a.emb), dtype=torch.float32, device=dev)
-    if not a2a:
+    if synced:
+        w_in.fill_uniform(bound, a.seed + 101)                # every rank fills its working copy and adopts its master chunk
+        w_out.fill_uniform(bound, a.seed + 102)
+    elif not a2a:
         nat.table_fill_uniform(w_in, bound, a.seed + 101)     # same content on every rank / for every sharding
         nat.table_fill_uniform(w_out, bound, a.seed + 102)
+    if world > 1:
+        torch.cuda.synchronize()
+        dist.barrier()                                        # nobody touches a peer's rows before they are initialised
+    T = {'w_in': w_in, 'w_out': w_out, 'synced': synced, 'sharded': sharded}
     flags = nat.SCATTER_RED if a.scatter == 'red' else nat.SCATTER_STORE
     if a.kernel == 'context':
         flags |= nat.NO_WINDOW
@@ -379,15 +417,26 @@ def run_b200(a, rank, local_rank, world):
     scratch = {'starts': torch.empty(n_walks, dtype=torch.int32, device=dev), 'walks': walks, 'stats': stats}
     stats_host = torch.zeros(nat.STATS_LEN, dtype=torch.float64).pin_memory()
 
-    def sync_tables():
-        if world > 1 and not sharded and not a2a:
-            dist.all_reduce(w_in, op=dist.ReduceOp.AVG)
-            dist.all_reduce(w_out, op=dist.ReduceOp.AVG)
-
     ev = lambda: torch.cuda.Event(enable_timing=True)   # noqa: E731
-    sgns_events, walk_events = [], []
+    sgns_events, walk_events, sync_events = [], [], []
 
-    gather_buf = torch.empty((world * n_walks, a.walk_len), dtype=torch.int32, device=dev) if sharded and world > 1 else None
+    def sync_tables(record=False):
+        if world == 1 or a2a or T['sharded']:
+            return
+        if record:
+            s0, s1 = ev(), ev()
+            s0.record()
+        if T['synced']:
+            from shallow_encoders.word2vec.sharded import sync_replicated
+            sync_replicated([T['w_in'], T['w_out']])
+        else:
+            dist.all_reduce(T['w_in'], op=dist.ReduceOp.AVG)
+            dist.all_reduce(T['w_out'], op=dist.ReduceOp.AVG)
+        if record:
+            s1.record()
+            sync_events.append((s0, s1))
+
+    gather_buf = torch.empty((world * n_walks, a.walk_len), dtype=torch.int32, device=dev) if world > 1 and not a2a else None
 
     def sgns_stage(base, step, mode):
         if a2a:
@@ -395,10 +444,10 @@ def run_b200(a, rank, local_rank, world):
                         micro_walks=a.a2a_micro_walks, local_negatives=mode == 'local', stats=stats)
         elif mode == 'owner':
             from shallow_encoders.word2vec.sharded import sgns_update_walks_owner_computes
-            sgns_update_walks_owner_computes(w_in, w_out, walks, a.radius, a.neg, 1, a.lr, a.seed + 1, step * world * n_walks * n_cen,
+            sgns_update_walks_owner_computes(T['w_in'], T['w_out'], walks, a.radius, a.neg, 1, a.lr, a.seed + 1, step * world * n_walks * n_cen,
                                              rank, world, stats=stats, gather_buf=gather_buf)
         else:
-            nat.sgns_update_walks(w_in, w_out, walks, a.radius, a.neg, 1, a.lr, a.seed + 1, centre_id_base=base * n_cen,
+            nat.sgns_update_walks(T['w_in'], T['w_out'], walks, a.radius, a.neg, 1, a.lr, a.seed + 1, centre_id_base=base * n_cen,
                                   flags=flags, stats=stats, local_negatives=mode == 'local')
 
     def device_step(step, record=False, mode=None):
@@ -415,7 +464,7 @@ def run_b200(a, rank, local_rank, world):
             e2.record()
             walk_events.append((e0, e1))
             sgns_events.append((e1, e2))
-        sync_tables()
+        sync_tables(record)
 
     def host_step(step):
         st, base = pinned[step]
@@ -427,7 +476,7 @@ def run_b200(a, rank, local_rank, world):
             stats_host.copy_(stats)
             torch.cuda.synchronize()
             return
-        nat.host_walk_sgns_step(csr, st, a.walk_len, a.p, a.q, True, nat.RULE_REFERENCE, a.seed, base, w_in, w_out, a.radius,
+        nat.host_walk_sgns_step(csr, st, a.walk_len, a.p, a.q, True, nat.RULE_REFERENCE, a.seed, base, T['w_in'], T['w_out'], a.radius,
                                 a.neg, 1, a.lr, scratch, stats_host, flags=flags, local_negatives=local_neg)
         sync_tables()
 
@@ -451,6 +500,7 @@ def run_b200(a, rank, local_rank, world):
     barrier()
     launches0 = nat.launches()
     sampler.start()
+    nvl0 = nvlink_bytes(nvml_index(local_rank)) if world > 1 else None
     torch.cuda.profiler.start()          # `ncu --profile-from-start off` captures exactly the timed region
     t0, t1 = ev(), ev()
     t0.record()
@@ -459,6 +509,7 @@ def run_b200(a, rank, local_rank, world):
     t1.record()
     barrier()
     torch.cuda.profiler.stop()
+    nvl1 = nvlink_bytes(nvml_index(local_rank)) if world > 1 else None
     clocks = sampler.stop()
     launches = nat.launches() - launches0
     ms_total = max_over_ranks(t0.elapsed_time(t1))
@@ -467,6 +518,7 @@ def run_b200(a, rank, local_rank, world):
     value = world * pairs_per_step * a.steps / (ms_total / 1e3)
     sgns_ms = max_over_ranks(sum(x.elapsed_time(y) for x, y in sgns_events) / len(sgns_events))
     walk_ms = max_over_ranks(sum(x.elapsed_time(y) for x, y in walk_events) / len(walk_events))
+    sync_ms = max_over_ranks(sum(x.elapsed_time(y) for x, y in sync_events) / len(sync_events)) if sync_events else None
     stat_vals = stats.tolist()
 
     # ---- end-to-end through the host-buffer C-ABI entry (`e2e`) -------------------------------------------------
@@ -484,13 +536,26 @@ def run_b200(a, rank, local_rank, world):
     e2e_ms = max(e2e_ms, max_over_ranks(e2e_wall * 1e3) if world > 1 else e2e_wall * 1e3)   # host copies + sync are on the clock
     e2e_value = world * pairs_per_step * a.steps / (e2e_ms / 1e3)
 
-    # ---- sharded tables: the other negative-sampling mode, a few steps, reported beside the headline -------------
+    # ---- the other multi-GPU modes, a few steps each, reported beside the headline ---------------------------------
     other = None
-    if (sharded or a2a) and world > 1 and a.extra_steps > 0:
-        names = {'local': 'local (rows the GPU owns)', 'global': 'global (reference draw, negative rows fetched over NVLink)',
-                 'owner': 'global, owner-computes (reference draw, centre rows travel instead of negative rows)'}
+    if (sharded or a2a or synced) and world > 1 and a.extra_steps > 0:
+        names = {'local': 'striped tables, negatives among the rows the GPU owns (changed sampler; per-pair NVLink traffic 0.2 rows)',
+                 'global': 'striped tables, reference draw, negative rows fetched / red.added over NVLink per pair',
+                 'owner': 'striped tables, reference draw, owner-computes (centre rows travel instead of negative rows)'}
+        if synced:
+            # swap the working copies for ONE striped table pair (the capacity mode) and time its negative modes beside the headline
+            from shallow_encoders.word2vec.sharded import ShardedTable
+            T['w_in'].close(); T['w_out'].close()
+            torch.cuda.empty_cache()
+            T['w_in'] = ShardedTable(vocab, a.emb, dev, rank, world, ex)
+            T['w_out'] = ShardedTable(vocab, a.emb, dev, rank, world, ex)
+            nat.table_fill_uniform(T['w_in'], bound, a.seed + 101)
+            nat.table_fill_uniform(T['w_out'], bound, a.seed + 102)
+            T['synced'], T['sharded'] = False, True
+            barrier()
+        modes = ('local', 'global') if a2a else (('local', 'owner') if synced else ('local', 'global', 'owner'))
         other, first = [], a.warmup + 2 * a.steps + 1
-        for mode in [m for m in (('local', 'global') if a2a else ('local', 'global', 'owner')) if m != neg_mode]:
+        for mode in [m for m in modes if synced or m != neg_mode]:
             device_step(first, mode=mode)
             barrier()
             x0, x1 = ev(), ev()
@@ -500,15 +565,20 @@ def run_b200(a, rank, local_rank, world):
             x1.record()
             barrier()
             other_ms = max_over_ranks(x0.elapsed_time(x1))
-            other.append({'negatives': names[mode], 'value': world * pairs_per_step * a.extra_steps / (other_ms / 1e3), 'unit': UNIT,
+            other.append({'mode': names[mode], 'value': world * pairs_per_step * a.extra_steps / (other_ms / 1e3), 'unit': UNIT,
                           'steps': a.extra_steps, 'ms_per_step': other_ms / a.extra_steps})
             first += a.extra_steps + 1
+
+    def close_tables():
+        if T['sharded'] or T['synced']:
+            T['w_in'].close(); T['w_out'].close()
+        if ex is not None:
+            ex.close()
 
     if rank != 0:
         if world > 1:
             barrier()
-            if sharded:
-                w_in.close(); w_out.close(); ex.close()
+            close_tables()
             dist.destroy_process_group()
         return
 
@@ -548,16 +618,28 @@ def run_b200(a, rank, local_rank, world):
     if fallback_note:
         line['multi_gpu_fallback'] = fallback_note
     if other is not None:
-        line['sharded_other_negative_modes'] = other
+        line['other_multi_gpu_modes'] = other
     if a2a:
         line['a2a'] = {'micro_walks': a.a2a_micro_walks, 'exchanged_bytes_sent_per_rank': tables.exchanged_bytes}
     if sharded:
         line['tables'] = {'kind': 'vmm-striped', 'stripe_bytes': w_in.stripe_bytes, 'stripes_per_table': w_in.n_stripes,
                           'bytes_per_gpu': 2 * w_in.n_stripes * w_in.stripe_bytes // world}
+    if synced:
+        table_bytes = vocab * a.emb * 4
+        moved = 2 * 2 * table_bytes * (world - 1) / world          # per GPU per direction per step, both tables
+        line['tables'] = {'kind': 'working copy per GPU + row-sharded masters (vmm peer-mapped)', 'bytes_per_gpu': 2 * w_in.seg_bytes + 2 * table_bytes // world}
+        line['table_sync'] = {'ms_per_step': sync_ms, 'nvlink_bytes_per_gpu_per_direction': moved,
+                              'achieved_gbs_per_direction': (moved / (sync_ms / 1e3) / 1e9) if sync_ms else None,
+                              'reference_gbs_per_direction': 770.0, 'reference_source': 'B200_PROFILING.md measured peer copy'}
+    if nvl0 and nvl1:
+        line['nvlink_counters_rank0'] = {'tx_bytes_per_step': (nvl1[0] - nvl0[0]) / a.steps, 'rx_bytes_per_step': (nvl1[1] - nvl0[1]) / a.steps,
+                                         'source': 'NVML NVLINK_THROUGHPUT_DATA_TX/RX over the timed region'}
     if world == 1 and not a.no_cpu_baseline:
         if sharded:
             w_in.close(); w_out.close()
+            T['sharded'] = False
         del w_in, w_out, csr
+        T.clear(); T.update({'sharded': False, 'synced': False})
         torch.cuda.empty_cache()
         try:
             line['cpu_baseline'] = cpu_baseline(a)
@@ -566,8 +648,7 @@ def run_b200(a, rank, local_rank, world):
     emit(line)
     if world > 1:
         barrier()
-        if sharded:
-            w_in.close(); w_out.close(); ex.close()
+        close_tables()
         dist.destroy_process_group()
 
 

@@ -79,6 +79,8 @@ _SIGNATURES = {
     'se_edge_op': (c_int, [c_p, c_p, c_i64, c_int, c_p, c_p]),
     'se_sample_negative_edges': (c_int, [c_p, c_p, c_i64, c_i64, c_u64, c_i64, c_p, c_p, c_p, c_p]),
     'se_check_ids': (c_int, [c_p, c_i64, c_i64, c_i64, c_p, c_p]),
+    'se_replica_chunk': (c_int, [c_i64, c_int, c_int, c_p, c_p]),
+    'se_replica_sync': (c_int, [c_p, c_i64, c_int, c_int, c_i64, c_p, c_int, c_p]),
     'se_table_fill_uniform': (c_int, [c_p, c_i64, c_f32, c_u64, c_i64, c_int, c_int, c_p]),
     'se_table_gather_rows': (c_int, [c_p, c_int, c_p, c_i64, c_p, c_p]),
     'se_table_scatter_rows': (c_int, [c_p, c_int, c_p, c_i64, c_p, c_p]),
@@ -516,6 +518,22 @@ def table_scatter_rows(table, rows: torch.Tensor, src: torch.Tensor) -> None:
     assert src.shape == (rows.numel(), emb)
     with torch.cuda.device(dev):
         _check(load().se_table_scatter_rows(ptr, emb, _ptr(rows, torch.int64, 'rows'), rows.numel(), _ptr(src, torch.float32, 'src'), _stream()))
+    _launches += 1
+
+
+def replica_chunk(n_elems: int, world: int, rank: int):
+    """[lo, hi) element range of the flat table whose master lives on `rank` (host arithmetic, no GPU)."""
+    lo, hi = c_i64(), c_i64()
+    _check(load().se_replica_chunk(int(n_elems), int(world), int(rank), ctypes.byref(lo), ctypes.byref(hi)))
+    return lo.value, hi.value
+
+
+def replica_sync(base_ptr: int, stride_elems: int, world: int, rank: int, n_elems: int, master: torch.Tensor, mode: int = 0) -> None:
+    """One rank's share of the fused reduce-scatter + all-gather over the working copies (csrc/replica.cu)."""
+    global _launches
+    with _on(master):
+        _check(load().se_replica_sync(int(base_ptr), int(stride_elems), int(world), int(rank), int(n_elems),
+                                      _ptr(master, torch.float32, 'master'), int(mode), _stream()))
     _launches += 1
 
 

@@ -269,6 +269,145 @@ class _RankView:
         return _Spec(self.world, self.rank, self.stripe_rows)
 
 
+class _CudaArray:
+    """__cuda_array_interface__ carrier: lets torch view memory this module mapped itself (no ownership)."""
+
+    def __init__(self, ptr: int, shape):
+        self.__cuda_array_interface__ = {'shape': tuple(int(x) for x in shape), 'typestr': '<f4', 'data': (int(ptr), False), 'version': 2}
+
+
+class ReplicatedTable:
+    """One [vocab x emb] table trained by `world` GPUs with the reference's GLOBAL negative draw at NVLink bulk rate.
+
+    Every GPU holds a full WORKING COPY in its own HBM (the unchanged single-GPU kernels run on it: pass this object
+    wherever a table is expected), rank r holds the MASTER of the contiguous row chunk r.  `sync()` -- called by every
+    rank after its step, between two barriers -- adds the summed updates of all copies to the master and writes the
+    result back into every copy, one kernel over peer memory (csrc/replica.cu): synchronous data-parallel SGD with summed
+    updates on ONE model.  All copies live in one virtual range (segment g on GPU g, mapped everywhere) built with the
+    striped-table plumbing above: a ShardedTable with one stripe per rank.
+
+    simulate=True places every segment on the calling GPU (single-GPU tests); `as_rank(r)` then gives rank r's view."""
+
+    def __init__(self, vocab: int, emb: int, device, rank: int = 0, world: int = 1, exchange: Optional[FdExchange] = None,
+                 simulate: bool = False, group=None):
+        import ctypes
+        self.vocab, self.emb = int(vocab), int(emb)
+        self.device = torch.device(device)
+        self.rank, self.world, self.group = int(rank), int(world), group
+        self.shape = (self.vocab, self.emb)
+        lib = nat.load()
+        with torch.cuda.device(self.device):
+            gran = ctypes.c_int64()
+            nat._check(lib.se_shard_granularity(ctypes.byref(gran)))
+        row_bytes = 4 * self.emb
+        unit = gran.value * row_bytes // math.gcd(gran.value, row_bytes)
+        self.seg_bytes = -(-(self.vocab * row_bytes) // unit) * unit
+        self.seg_rows = self.seg_bytes // row_bytes
+        self.seg_elems = self.seg_bytes // 4
+        self._set = ShardedTable(self.world * self.seg_rows, self.emb, self.device, self.rank, self.world, exchange,
+                                 stripe_bytes=self.seg_bytes, simulate=simulate)
+        self.base = self._set.ptr
+        self.ptr = self.base + self.rank * self.seg_bytes
+        self.n_elems = self.vocab * self.emb
+        self._masters = {}
+        self.master = self._master_for(self.rank)
+
+    def _master_for(self, rank: int) -> torch.Tensor:
+        if rank not in self._masters:
+            lo, hi = nat.replica_chunk(self.n_elems, self.world, rank)
+            self._masters[rank] = torch.zeros(max(hi - lo, 4), dtype=torch.float32, device=self.device)
+        return self._masters[rank]
+
+    # the kernels see a plain local table (device-scope reductions, negatives over the whole table)
+    def spec(self) -> _Spec:
+        return _Spec(1, 0, max(self.vocab, 1))
+
+    @property
+    def is_cuda(self) -> bool:
+        return True
+
+    def owned_row_range(self, rank: Optional[int] = None):
+        lo, hi = nat.replica_chunk(self.n_elems, self.world, self.rank if rank is None else rank)
+        return lo // self.emb, -(-min(hi, self.n_elems) // self.emb)
+
+    def view(self) -> torch.Tensor:
+        """The working copy as a torch tensor that ALIASES the mapped memory (valid until close())."""
+        return torch.as_tensor(_CudaArray(self.ptr, self.shape), device=self.device)
+
+    def to_tensor(self) -> torch.Tensor:
+        rows = torch.arange(self.vocab, dtype=torch.int64, device=self.device)
+        return nat.table_gather_rows(self, rows)
+
+    def gather(self, rows: torch.Tensor) -> torch.Tensor:
+        return nat.table_gather_rows(self, rows.to(self.device, torch.int64))
+
+    def scatter(self, rows: torch.Tensor, src: torch.Tensor) -> None:
+        nat.table_scatter_rows(self, rows.to(self.device, torch.int64), src.to(self.device, torch.float32).contiguous())
+
+    def fill_uniform(self, bound: float, seed: int) -> None:
+        """Every rank fills its own copy with the same Philox content, then takes its master chunk from it."""
+        nat.table_fill_uniform(self, bound, seed)
+        self.adopt()
+
+    def load(self, full: torch.Tensor) -> None:
+        """Every rank loads the same full [vocab x emb] tensor into its copy (checkpoint restore)."""
+        self.scatter(torch.arange(self.vocab, dtype=torch.int64, device=self.device), full.to(self.device))
+        self.adopt()
+
+    def adopt(self, rank: Optional[int] = None) -> None:
+        """master chunk <- working copy (mode 1)."""
+        r = self.rank if rank is None else rank
+        nat.replica_sync(self.base, self.seg_elems, self.world, r, self.n_elems, self._master_for(r), mode=1)
+
+    def sync_local(self, rank: Optional[int] = None, mode: int = 0) -> None:
+        """This rank's share of the fused reduce-scatter + all-gather; the caller provides the barriers (see `sync`)."""
+        r = self.rank if rank is None else rank
+        nat.replica_sync(self.base, self.seg_elems, self.world, r, self.n_elems, self._master_for(r), mode=mode)
+
+    def as_rank(self, rank: int) -> '_ReplicaView':
+        return _ReplicaView(self, rank)
+
+    def close(self) -> None:
+        self._set.close()
+        self.ptr = self.base = 0
+
+
+class _ReplicaView:
+    """Working copy of another rank of a SIMULATED ReplicatedTable (single-GPU tests); owns nothing."""
+
+    def __init__(self, table: ReplicatedTable, rank: int):
+        assert 0 <= rank < table.world
+        self.ptr = table.base + rank * table.seg_bytes
+        self.vocab, self.emb, self.device, self.shape = table.vocab, table.emb, table.device, table.shape
+
+    def spec(self) -> _Spec:
+        return _Spec(1, 0, max(self.vocab, 1))
+
+
+_BARRIER_TOKEN = {}
+
+
+def device_barrier(device, group=None) -> None:
+    """Stream-ordered barrier over the ranks of `group`: a one-element NCCL all-reduce on the current stream (no host sync)."""
+    import torch.distributed as dist
+    key = (torch.device(device).index, id(group))
+    if key not in _BARRIER_TOKEN:
+        _BARRIER_TOKEN[key] = torch.zeros(1, dtype=torch.int32, device=device)
+    dist.all_reduce(_BARRIER_TOKEN[key], group=group)
+
+
+def sync_replicated(tables, group=None) -> None:
+    """End-of-step synchronisation of ReplicatedTables on every rank: barrier (all steps done) -> each rank's fused
+    reduce-scatter + all-gather kernels over peer memory -> barrier (all copies written).  world == 1: nothing to do."""
+    tables = [t for t in tables if t.world > 1]
+    if not tables:
+        return
+    device_barrier(tables[0].device, group)
+    for t in tables:
+        t.sync_local()
+    device_barrier(tables[0].device, group)
+
+
 def sgns_update_walks_owner_computes(w_in, w_out, my_walks: torch.Tensor, radius: int, n_neg: int, row_offset: int, lr: float, seed: int,
                                      centre_id_base: int, rank: int, world: int, group=None, stats: Optional[torch.Tensor] = None,
                                      alias=None, gather_buf: Optional[torch.Tensor] = None, micro_walks: Optional[int] = None) -> None:

@@ -244,6 +244,22 @@ int se_host_walk_sgns_step_sharded(const int64_t *rowptr, const int32_t *col, co
                                    int flags, const se_shard_spec *spec, int32_t *starts_dev, int32_t *walks_dev,
                                    double *stats_dev, int32_t *walks_host, double *stats_host, void *stream);
 
+/* ------------------------------------------------------------------------------------------------------------
+ * Multi-GPU with the reference's GLOBAL negative draw (word2vec/utils/sampling.py:21) at NVLink bulk rate: per-GPU
+ * working copies + row-sharded masters (csrc/replica.cu).  No reference counterpart (`devices: '1'`).
+ * `base` is one virtual range of `world` segments of stride_elems floats (segment g = GPU g's full [vocab x emb] working
+ * copy, physically in GPU g's HBM, mapped into every process through the se_shard_* calls above); the single-GPU kernels
+ * train on segment `rank`.  Rank r owns the master of the element chunk se_replica_chunk returns (contiguous rows).
+ * se_replica_sync, enqueued by EVERY rank between two inter-GPU barriers, does for the chunk the caller owns
+ *     mode 0:  master' = master + sum_g (copy_g - master);  every copy_g <- master'     (fused reduce-scatter + all-gather)
+ *     mode 1:  master <- copy_rank                                                     (after initialisation)
+ *     mode 2:  every copy_g <- master                                                  (after loading a checkpoint)
+ * which equals synchronous data-parallel SGD with SUMMED updates, on one model.  `master` holds hi_elem - lo_elem floats.
+ * ---------------------------------------------------------------------------------------------------------- */
+int se_replica_chunk(int64_t n_elems, int world, int rank, int64_t *lo_elem, int64_t *hi_elem);
+int se_replica_sync(float *base, int64_t stride_elems, int world, int rank, int64_t n_elems, float *master, int mode,
+                    void *stream);
+
 /* Input hygiene for token / node ids that come from outside the library (the reference's nn.Embedding raises IndexError on an
  * out-of-range id, word2vec/model.py:22-23; the fused kernels index the tables unchecked): ADDS to bad_count[0] the number of
  * ids[i] outside [lo, hi).  The Python wrappers run it before a fused update unless told the ids come from se_walk. */

@@ -191,6 +191,33 @@ def main():
     np.testing.assert_allclose(rs.gather_full('out').cpu().numpy(), want_out, rtol=1e-4, atol=1e-5)
     assert rs.exchanged_bytes > 0
     barrier()
+    # 7. ReplicatedTable (csrc/replica.cu): every rank trains its own working copy with the GLOBAL negative draw, then the fused
+    #    reduce-scatter + all-gather over peer memory leaves start + sum_g (copy_g - start) in every copy
+    from shallow_encoders.word2vec.sharded import ReplicatedTable, sync_replicated
+    r_in = ReplicatedTable(vocab, emb, dev, rank, world, ex); r_out = ReplicatedTable(vocab, emb, dev, rank, world, ex)
+    r_in.fill_uniform(0.3, 5); r_out.fill_uniform(0.3, 6)
+    barrier()
+    assert torch.equal(r_in.to_tensor(), d_in) and torch.equal(r_out.view(), d_out)
+    walks_r = torch.from_numpy(np.random.default_rng(1000 + rank).integers(0, vocab - offset, (256, 9)).astype(np.int32)).to(dev)
+    for it in range(2):
+        before_in, before_out = r_in.to_tensor().double(), r_out.to_tensor().double()
+        st = nat.sgns_update_walks(r_in, r_out, walks_r, radius, k, offset, 0.05, seed=50 + it, centre_id_base=(it * world + rank) * 256 * 5)
+        assert st['pairs'] == 256 * 5 * 4
+        mine_in, mine_out = r_in.to_tensor().double() - before_in, r_out.to_tensor().double() - before_out
+        assert float(mine_in.abs().max()) > 1e-4
+        dist.all_reduce(mine_in); dist.all_reduce(mine_out)                      # NCCL cross-check of the summed updates
+        sync_replicated([r_in, r_out])
+        torch.cuda.synchronize()
+        assert float((r_in.to_tensor().double() - (before_in + mine_in)).abs().max()) < 2e-6
+        assert float((r_out.to_tensor().double() - (before_out + mine_out)).abs().max()) < 2e-6
+        flat = r_in.to_tensor().reshape(-1)
+        lo, hi = nat.replica_chunk(vocab * emb, world, rank)
+        assert torch.equal(r_in.master[:min(hi, vocab * emb) - lo], flat[lo:min(hi, vocab * emb)])
+        ref = flat.clone()
+        dist.broadcast(ref, src=0)
+        assert torch.equal(ref, flat), 'working copies differ between ranks after the sync'
+    barrier()
+    r_in.close(); r_out.close()
     s_in.close(); s_out.close(); ex.close()
     dist.destroy_process_group()
     print(f'MGPU_OK rank {rank}/{world}', flush=True)

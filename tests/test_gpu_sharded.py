@@ -13,7 +13,7 @@ import philox_ref
 from helpers import cuda_device
 from oracle import sgns_oracle
 from shallow_encoders import _native as nat
-from shallow_encoders.word2vec.sharded import ShardedTable, local_rows, local_to_global
+from shallow_encoders.word2vec.sharded import ReplicatedTable, ShardedTable, local_rows, local_to_global
 
 pytestmark = pytest.mark.gpu
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
@@ -299,6 +299,55 @@ def test_nccl_baseline_step_equals_minibatch_sgd_on_one_gpu():
     np.testing.assert_allclose(t.gather_full('out').cpu().numpy(), want_out, rtol=1e-4, atol=1e-5)
     st = stats.tolist()
     assert st[4] == b * n and abs((st[0] + st[1]) / st[4] - o['loss']) < 1e-4 * o['loss']
+
+
+@pytest.mark.parametrize('world,vocab,emb', [(2, 5000, 128), (4, 4097, 48), (8, 35, 2), (3, 777, 20)])
+def test_replicated_tables_sync_equals_the_sum_of_all_updates_simulated_ranks(world, vocab, emb):
+    """ReplicatedTable (csrc/replica.cu) with every rank's working copy on ONE GPU: each simulated rank trains its copy on its
+    own walks with the unchanged fused kernel (global negative draw), then every rank runs its share of the fused
+    reduce-scatter + all-gather.  Afterwards every copy and every master chunk equals start + sum_g (copy_g - start) --
+    synchronous data-parallel SGD with summed updates -- to fp32 rounding, and a second sync without updates changes nothing."""
+    dev = cuda_device()
+    radius, k, offset = 2, 3, 1
+    t_in = ReplicatedTable(vocab, emb, dev, rank=0, world=world, simulate=True)
+    t_out = ReplicatedTable(vocab, emb, dev, rank=0, world=world, simulate=True)
+    start_in = torch.empty((vocab, emb), device=dev); start_out = torch.empty((vocab, emb), device=dev)
+    nat.table_fill_uniform(start_in, 0.4, 21); nat.table_fill_uniform(start_out, 0.4, 22)
+    rows = torch.arange(vocab, device=dev)
+    for r in range(world):
+        nat.table_scatter_rows(t_in.as_rank(r), rows, start_in); nat.table_scatter_rows(t_out.as_rank(r), rows, start_out)
+        t_in.adopt(r); t_out.adopt(r)
+    rng = np.random.default_rng(5)
+    after_in, after_out = [], []
+    for r in range(world):
+        walks = _t(rng.integers(0, vocab - offset, (64, 9)).astype(np.int32), dev)
+        st = nat.sgns_update_walks(t_in.as_rank(r), t_out.as_rank(r), walks, radius, k, offset, 0.05, seed=30 + r, centre_id_base=1000 * r)
+        assert st['pairs'] == 64 * 5 * 4
+        after_in.append(nat.table_gather_rows(t_in.as_rank(r), rows)); after_out.append(nat.table_gather_rows(t_out.as_rank(r), rows))
+    assert float((after_in[0] - start_in).abs().max()) > 1e-4                  # the step moved something
+    want_in = start_in.double() + sum((a.double() - start_in.double()) for a in after_in)
+    want_out = start_out.double() + sum((a.double() - start_out.double()) for a in after_out)
+    for r in range(world):
+        t_in.sync_local(r); t_out.sync_local(r)
+    for r in range(world):
+        got_in = nat.table_gather_rows(t_in.as_rank(r), rows); got_out = nat.table_gather_rows(t_out.as_rank(r), rows)
+        assert float((got_in.double() - want_in).abs().max()) < 2e-6 and float((got_out.double() - want_out).abs().max()) < 2e-6
+        assert torch.equal(got_in, nat.table_gather_rows(t_in.as_rank(0), rows))          # all copies identical bit for bit
+        lo, hi = nat.replica_chunk(vocab * emb, world, r)
+        hi = min(hi, vocab * emb)
+        assert torch.equal(t_in._master_for(r)[:hi - lo], got_in.reshape(-1)[lo:hi])
+    before = nat.table_gather_rows(t_in.as_rank(world - 1), rows)
+    for r in range(world):
+        t_in.sync_local(r)
+    assert torch.equal(nat.table_gather_rows(t_in.as_rank(0), rows), before)         # idempotent without new updates
+    # mode 2: masters pushed back into every copy (checkpoint restore path)
+    nat.table_scatter_rows(t_in.as_rank(1 % world), rows, torch.zeros((vocab, emb), device=dev))
+    for r in range(world):
+        t_in.sync_local(r, mode=2)
+    assert torch.equal(nat.table_gather_rows(t_in.as_rank(1 % world), rows), before)
+    v = t_in.view()
+    assert v.shape == (vocab, emb) and torch.equal(v, nat.table_gather_rows(t_in.as_rank(0), rows))
+    t_in.close(); t_out.close()
 
 
 @pytest.mark.skipif(torch.cuda.device_count() < 2, reason='needs two GPUs on one NVLink/NVSwitch node')

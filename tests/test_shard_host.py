@@ -166,3 +166,18 @@ def test_row_exchange_fetch_and_push_over_gloo_world_size_2():
     for p in procs:
         p.join(timeout=30)
     assert res == {0: 'ok', 1: 'ok'}, res
+
+
+def test_replica_chunks_partition_the_table_in_float4_units():
+    """se_replica_chunk (csrc/replica.cu): rank r owns a contiguous element range, the ranges tile [0, round_up4(n)) exactly."""
+    from shallow_encoders import _native as nat
+    nat.load()
+    for n_elems in (0, 1, 70, 4096 * 128 + 12, 10_000_001 * 128):
+        for world in (1, 2, 3, 8):
+            edges = [nat.replica_chunk(n_elems, world, r) for r in range(world)]
+            assert edges[0][0] == 0 and edges[-1][1] == -(-n_elems // 4) * 4
+            for (lo, hi), (lo2, _hi2) in zip(edges, edges[1:]):
+                assert lo <= hi == lo2 and lo % 4 == 0
+            sizes = [hi - lo for lo, hi in edges]
+            assert max(sizes) - min(s for s in sizes if s or True) <= max(sizes)      # no chunk larger than ceil(n4 / world) float4s
+            assert max(sizes) == -(-(-(-n_elems // 4)) // world) * 4 or n_elems == 0
