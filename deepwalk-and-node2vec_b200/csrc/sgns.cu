@@ -12,141 +12,10 @@
 //   MODE_STEP  explicit batch, in-place SGD (noise optional: in-kernel Philox negatives)
 //   MODE_WALK  tokens[n_seq x L] -> windows (word2vec/dataloader/torch_dataset.py:300-309) + in-kernel negatives
 //              (word2vec/utils/sampling.py:21 distribution, or alias table) + in-place SGD.  Nothing materialised.
-#include "common.cuh"
+#include "sgns_common.cuh"
 
 namespace se {
 namespace {
-
-constexpr int SGNS_THREADS = 256;
-constexpr float CLAMP_MIN = 1e-6f;
-enum { MODE_GRAD = 0, MODE_STEP = 1, MODE_WALK = 2 };
-
-template <int VEC> struct VecT;
-template <> struct VecT<4> { using type = float4; };
-template <> struct VecT<2> { using type = float2; };
-template <> struct VecT<1> { using type = float; };
-
-// L2-only loads: rows are updated by other SMs (and by our own red.global), so L1 must not serve them.
-template <int VEC> __device__ __forceinline__ void load_vec(const float *p, float (&v)[VEC]) {
-    if constexpr (VEC == 4) { float4 t = __ldcg(reinterpret_cast<const float4 *>(p)); v[0] = t.x; v[1] = t.y; v[2] = t.z; v[3] = t.w; }
-    else if constexpr (VEC == 2) { float2 t = __ldcg(reinterpret_cast<const float2 *>(p)); v[0] = t.x; v[1] = t.y; }
-    else { v[0] = __ldcg(p); }
-}
-template <int VEC> __device__ __forceinline__ void store_vec(float *p, const float (&v)[VEC]) {
-    if constexpr (VEC == 4) __stcg(reinterpret_cast<float4 *>(p), make_float4(v[0], v[1], v[2], v[3]));
-    else if constexpr (VEC == 2) __stcg(reinterpret_cast<float2 *>(p), make_float2(v[0], v[1]));
-    else __stcg(p, v[0]);
-}
-// no-return vector reduction at L2 (sm_90+): one instruction per 16 bytes.  `sys` selects system scope, required when
-// the row may live in a peer GPU's HBM (sharded tables): the reduction then executes at the owner's L2 over NVLink.
-template <int VEC> __device__ __forceinline__ void red_vec(float *p, const float (&v)[VEC], bool sys = false) {
-    if (sys) {
-        if constexpr (VEC == 4)
-            asm volatile("red.relaxed.sys.global.add.v4.f32 [%0], {%1, %2, %3, %4};" ::"l"(p), "f"(v[0]), "f"(v[1]), "f"(v[2]), "f"(v[3]) : "memory");
-        else if constexpr (VEC == 2)
-            asm volatile("red.relaxed.sys.global.add.v2.f32 [%0], {%1, %2};" ::"l"(p), "f"(v[0]), "f"(v[1]) : "memory");
-        else
-            asm volatile("red.relaxed.sys.global.add.f32 [%0], %1;" ::"l"(p), "f"(v[0]) : "memory");
-        return;
-    }
-    if constexpr (VEC == 4)
-        asm volatile("red.relaxed.gpu.global.add.v4.f32 [%0], {%1, %2, %3, %4};" ::"l"(p), "f"(v[0]), "f"(v[1]), "f"(v[2]), "f"(v[3]) : "memory");
-    else if constexpr (VEC == 2)
-        asm volatile("red.relaxed.gpu.global.add.v2.f32 [%0], {%1, %2};" ::"l"(p), "f"(v[0]), "f"(v[1]) : "memory");
-    else
-        asm volatile("red.relaxed.gpu.global.add.f32 [%0], %1;" ::"l"(p), "f"(v[0]) : "memory");
-}
-
-// Shuffles name only the lanes of the calling group: groups of one warp may run different trip counts.
-template <int G> __device__ __forceinline__ unsigned group_mask() {
-    if constexpr (G == 32) return FULL;
-    else return ((1u << G) - 1u) << ((threadIdx.x & 31) & ~(G - 1));
-}
-template <int G> __device__ __forceinline__ float group_sum(float v, unsigned mask) {
-#pragma unroll
-    for (int off = G >> 1; off > 0; off >>= 1) v += __shfl_xor_sync(mask, v, off, G);
-    return v;
-}
-
-struct SgnsArgs {
-    float *w_in, *w_out;                 // tables (read-only in MODE_GRAD)
-    float *grad_in, *grad_out;           // MODE_GRAD only (may be null)
-    const int64_t *inputs, *targets, *noise;   // explicit modes
-    const int32_t *tokens;               // MODE_WALK
-    const float *alias_prob; const int32_t *alias_idx;
-    double *stats;
-    int64_t n_units;                     // batch rows (explicit) or n_seq * (L - 2r) centres (walk)
-    int64_t vocab;
-    int emb, n_ctx, n_neg;
-    int seq_len, radius, n_cen, row_offset;
-    float lr, grad_scale;
-    uint64_t seed; int64_t id_base;
-    int scatter_store;
-    int force_generic;                   // SE_SGNS_GENERIC_KERNEL: skip the fast path (testing / comparison)
-    // sharded tables (se_shard_spec): negatives are drawn over neg_vocab ids; with neg_shift >= 0 those are LOCAL ids of
-    // shard neg_rank (stripes of 1 << neg_shift rows, stripe s owned by rank s % neg_world) and are mapped to table rows
-    uint32_t neg_vocab;
-    int neg_shift, neg_world, neg_rank;
-    int sys_scope;                       // rows may live in peer HBM: system-scope reductions
-    int no_window;                       // SE_SGNS_NO_WINDOW: per-context kernel instead of the window-resident one
-    int own_shift;                       // sgns_negown_kernel: log2(stripe_rows); row r is owned by (r >> own_shift) % neg_world
-};
-
-// in-kernel negative: uniform / alias draw, then (local negatives) local id -> row of the stripe this rank owns
-__device__ __forceinline__ int neg_row(const SgnsArgs &a, uint32_t r0, uint32_t r1) {
-    uint32_t j = (uint32_t)draw_row(a.alias_prob, a.alias_idx, a.neg_vocab, r0, r1);
-    if (a.neg_shift >= 0) {
-        const uint32_t s = j >> a.neg_shift;
-        j = ((s * (uint32_t)a.neg_world + (uint32_t)a.neg_rank) << a.neg_shift) | (j & ((1u << a.neg_shift) - 1u));
-    }
-    return (int)j;
-}
-
-template <bool FAST> __device__ __forceinline__ float sigmoidf_(float x) {
-    if constexpr (FAST) return __fdividef(1.0f, 1.0f + __expf(-x));
-    else return 1.0f / (1.0f + expf(-x));
-}
-template <bool FAST> __device__ __forceinline__ float logf_(float x) {
-    if constexpr (FAST) return __logf(x); else return logf(x);
-}
-
-// Block-level reduction of the loss statistics (layout: SE_STATS_LEN in se_b200.h): every contributing thread adds into shared
-// memory, then one double atomic per statistic per block goes to `stats`.  Must be reached by all threads of the block.
-__device__ __forceinline__ void flush_stats(double *stats, bool contribute, float loss_pos, float loss_neg, unsigned cnt_recall,
-                                            unsigned cnt_fp, unsigned cnt_pairs, double cnt_neg) {
-    __shared__ double sred[SE_STATS_LEN];
-    if (threadIdx.x < SE_STATS_LEN) sred[threadIdx.x] = 0.0;
-    __syncthreads();
-    if (contribute) {
-        atomicAdd(&sred[0], (double)loss_pos);
-        atomicAdd(&sred[1], (double)loss_neg);
-        atomicAdd(&sred[2], (double)cnt_recall);
-        atomicAdd(&sred[3], (double)cnt_fp);
-        atomicAdd(&sred[4], (double)cnt_pairs);
-        atomicAdd(&sred[5], cnt_neg);
-    }
-    __syncthreads();
-    if (threadIdx.x < SE_STATS_LEN && stats && sred[threadIdx.x] != 0.0) atomicAdd(stats + threadIdx.x, sred[threadIdx.x]);
-}
-
-// Persistent launch geometry shared by the SGNS kernels: enough blocks of SGNS_THREADS for `n_units` at `units_per_block`, capped at one
-// resident wave (SMs x occupancy).  Returns 0 blocks on error (message set).
-template <typename Kernel>
-int persistent_blocks(Kernel kern, size_t smem, int64_t n_units, int units_per_block, bool need_resident = false) {
-    int occ = 0;
-    if (check_cuda(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, kern, SGNS_THREADS, smem), "occupancy") != SE_OK) return 0;
-    if (occ < 1) {
-        if (need_resident) return -1;
-        occ = 1;
-    }
-    const int sms = sm_count();
-    if (sms <= 0) return 0;
-    int64_t blocks = (n_units + units_per_block - 1) / units_per_block;
-    const int64_t cap = (int64_t)sms * occ;
-    if (blocks > cap) blocks = cap;
-    if (blocks < 1) blocks = 1;
-    return (int)blocks;
-}
 
 template <int MODE, int VEC, int G, int R>
 __global__ void __launch_bounds__(SGNS_THREADS)
@@ -330,22 +199,6 @@ sgns_kernel(const SgnsArgs a) {
 //   * draws negatives from one Philox call per four contexts (see neg_words),
 //   * knows the row length at compile time when E == 128*R (no predication, shift addressing).
 // ------------------------------------------------------------------------------------------------------------------
-template <int CH> __device__ __forceinline__ float transposed_reduce(float (&v)[CH], int lane) {
-    int off = 16;
-#pragma unroll
-    for (int n = CH; n > 1; n >>= 1, off >>= 1) {
-        const bool hi = (lane & off) != 0;
-#pragma unroll
-        for (int i = 0; i < n / 2; ++i) {
-            const float send = hi ? v[i] : v[i + n / 2];
-            const float keep = hi ? v[i + n / 2] : v[i];
-            v[i] = keep + __shfl_xor_sync(FULL, send, off);
-        }
-    }
-    float r = v[0];
-    for (; off > 0; off >>= 1) r += __shfl_xor_sync(FULL, r, off);
-    return r;      // lane l holds the dot of row (l >> (5 - log2 CH))
-}
 
 template <int MODE, int R, bool EXACT>
 __global__ void __launch_bounds__(SGNS_THREADS, 2)
@@ -711,222 +564,22 @@ sgns_ctx_kernel(const SgnsArgs a) {
 
 
 // ------------------------------------------------------------------------------------------------------------------
-// Window-resident variant of the hot kernel (MODE_WALK only).  A warp walks its contiguous span of centres with the W_out
-// rows of the 2r+1 tokens around the current centre RESIDENT in shared memory (ring of 2r+2 slots per warp: current value
-// + accumulated update).  A token's context row is fetched ONCE when it enters the window (cp.async, one centre ahead),
-// serves as the positive row of up to 2r centres from shared memory, and its accumulated update is scattered with ONE
-// red.global.add when it leaves -- instead of 2r gathers and 2r scatters through L2.  Negatives, the centre row, the
-// reduction and the loss arithmetic are those of sgns_ctx_kernel.  On one GPU the L2 already absorbed most of that reuse
-// (DRAM traffic is unchanged); on SHARDED tables peer rows are not cached in the local L2, so this removes 2r-fold
-// NVLink traffic for the positive rows.  Updates of the same row by other warps / GPUs still all land (we add our delta,
-// we do not store the row).
-// ------------------------------------------------------------------------------------------------------------------
-__device__ __forceinline__ void cp_async16(float4 *smem_dst, const float *gsrc) {
-    const unsigned saddr = (unsigned)__cvta_generic_to_shared(smem_dst);
-    asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(saddr), "l"(gsrc) : "memory");
-}
-__device__ __forceinline__ void cp_async_wait_all() { asm volatile("cp.async.wait_all;" ::: "memory"); }
-
-template <int T, bool EXACT>
-__global__ void __launch_bounds__(SGNS_THREADS, 2)
-sgns_win_kernel(const SgnsArgs a) {
-    constexpr int K = T - 1;
-    constexpr int P = (T <= 1) ? 1 : (T <= 2) ? 2 : (T <= 4) ? 4 : 8;
-    constexpr int SHIFT = (P == 8) ? 2 : (P == 4) ? 3 : (P == 2) ? 4 : 5;
-    extern __shared__ float4 win_smem[];
-    const int lane = threadIdx.x & 31;
-    const int64_t gid = (int64_t)blockIdx.x * (SGNS_THREADS / 32) + (threadIdx.x >> 5);
-    const int64_t n_groups = (int64_t)gridDim.x * (SGNS_THREADS / 32);
-    const int E = EXACT ? 128 : a.emb;
-    const int eoff = lane * 4;
-    const bool ok = EXACT || eoff < E;
-    const int N = a.n_ctx, NG = (a.n_ctx + 3) >> 2, r = a.radius;
-    const int RING = 2 * r + 2;
-    float4 *cur = win_smem + (size_t)(threadIdx.x >> 5) * 2 * RING * 32 + lane;     // slot s at cur[s * 32]
-    float4 *del = cur + RING * 32;
-    const int owner_t = lane >> SHIFT;
-    const bool owner_rep = (lane & ((1 << SHIFT) - 1)) == 0;
-
-    float loss_pos = 0.f, loss_neg = 0.f;
-    unsigned cnt_recall = 0, cnt_fp = 0, cnt_pairs = 0;
-
-    const int64_t span = (a.n_units + n_groups - 1) / n_groups;
-    int64_t u = gid * span;
-    const int64_t u_end = min(a.n_units, u + span);
-
-    while (u < u_end) {
-        // ---- one segment: consecutive centres of ONE sequence ----------------------------------------------------
-        const int64_t s = u / a.n_cen;
-        const int p0 = r + (int)(u - s * a.n_cen);
-        const int m = (int)min(u_end - u, (int64_t)(a.n_cen - (p0 - r)));        // centres p0 .. p0 + m - 1
-        const int32_t *seq = a.tokens + s * a.seq_len;
-        // window of the first centre: positions p0 - r .. p0 + r -> slots 0 .. 2r
-        for (int j = 0; j <= 2 * r; ++j) {
-            if (ok) {
-                cp_async16(cur + j * 32, a.w_out + ((int64_t)__ldg(seq + p0 - r + j) + a.row_offset) * E + eoff);
-                del[j * 32] = make_float4(0.f, 0.f, 0.f, 0.f);
-            }
-        }
-        cp_async_wait_all();
-        int head = 0;                                                             // slot of position p - r
-
-        for (int p = p0; p < p0 + m; ++p, ++u) {
-            // the row entering the window for the next centre goes to the free slot while this centre is processed
-            int free_slot = head - 1; if (free_slot < 0) free_slot += RING;
-            const bool slide = p + 1 < p0 + m;
-            if (slide && ok) {
-                cp_async16(cur + free_slot * 32, a.w_out + ((int64_t)__ldg(seq + p + r + 1) + a.row_offset) * E + eoff);
-                del[free_slot * 32] = make_float4(0.f, 0.f, 0.f, 0.f);
-            }
-            const int64_t crow = (int64_t)__ldg(seq + p) + a.row_offset;
-            float cen[4] = {0.f, 0.f, 0.f, 0.f}, acc[4] = {0.f, 0.f, 0.f, 0.f};
-            if (ok) load_vec<4>(a.w_in + crow * E + eoff, cen);
-
-            for (int g = 0; g < NG; ++g) {
-                // ids of the negatives this lane owns (lane t = negative t - 1) in contexts 4g .. 4g + 3
-                int ids[4] = {0, 0, 0, 0};
-                if (K > 0) {
-                    const uint64_t cid = (uint64_t)(a.id_base + u);
-                    const int k = lane >= 1 ? lane - 1 : 0;
-                    const uint4 wb = neg_words(a.seed, cid, g * 4, k, STREAM_NEG);
-                    uint4 wc = make_uint4(0, 0, 0, 0);
-                    if (a.alias_prob) wc = neg_words(a.seed, cid, g * 4, k, STREAM_NEG_COIN);
-#pragma unroll
-                    for (int j = 0; j < 4; ++j)
-                        if (g * 4 + j < N && lane >= 1 && lane < T) ids[j] = neg_row(a, pick_word(wb, j), pick_word(wc, j));
-                }
-#pragma unroll
-                for (int j = 0; j < 4; ++j) {
-                    const int n = g * 4 + j;
-                    if (n < N) {
-                        int slot = head + ((n < r) ? n : n + 1);                 // window offset of context n (centre skipped)
-                        if (slot >= RING) slot -= RING;
-                        int tid[T];
-                        float row[T][4];
-                        float dot[P];
-#pragma unroll
-                        for (int t = 1; t < T; ++t) tid[t] = __shfl_sync(FULL, ids[j], t);
-                        row[0][0] = row[0][1] = row[0][2] = row[0][3] = 0.f;
-                        if (ok) { const float4 c4 = cur[slot * 32]; row[0][0] = c4.x; row[0][1] = c4.y; row[0][2] = c4.z; row[0][3] = c4.w; }
-#pragma unroll
-                        for (int t = 1; t < T; ++t) {
-                            row[t][0] = row[t][1] = row[t][2] = row[t][3] = 0.f;
-                            if (ok) load_vec<4>(a.w_out + (int64_t)tid[t] * E + eoff, row[t]);
-                        }
-#pragma unroll
-                        for (int t = 0; t < P; ++t) {
-                            float d = 0.f;
-                            if (t < T) {
-#pragma unroll
-                                for (int e = 0; e < 4; ++e) d = fmaf(row[t][e], cen[e], d);
-                            }
-                            dot[t] = d;
-                        }
-                        const float sc = transposed_reduce<P>(dot, lane);
-                        float step_mine = 0.f;
-                        if (owner_t < T) {
-                            const bool positive = owner_t == 0;
-                            const float x = positive ? sc : -sc;                      // loss = -log clamp(sigmoid(x), 1e-6)
-                            const float ex = __expf(-x);
-                            const float sig = __fdividef(1.0f, 1.0f + ex);
-                            const bool live = sig > CLAMP_MIN;
-                            const float gmag = live ? ex * sig : 0.f;                 // |dL/ds| = sigmoid(-x)
-                            step_mine = positive ? a.lr * gmag : -a.lr * gmag;        // -lr * dL/ds
-                            if (owner_rep) {
-                                const float l = -__logf(fmaxf(sig, CLAMP_MIN));
-                                if (positive) { loss_pos += l; cnt_recall += x >= 0.f; cnt_pairs += 1; }
-                                else { loss_neg += l; cnt_fp += x <= 0.f; }
-                            }
-                        }
-                        {   // positive row: update the resident copy and its pending delta
-                            const float step = __shfl_sync(FULL, step_mine, 0);
-                            float4 upd;
-                            upd.x = step * cen[0]; upd.y = step * cen[1]; upd.z = step * cen[2]; upd.w = step * cen[3];
-#pragma unroll
-                            for (int e = 0; e < 4; ++e) acc[e] = fmaf(step, row[0][e], acc[e]);
-                            if (ok) {
-                                cur[slot * 32] = make_float4(row[0][0] + upd.x, row[0][1] + upd.y, row[0][2] + upd.z, row[0][3] + upd.w);
-                                float4 d4 = del[slot * 32];
-                                d4.x += upd.x; d4.y += upd.y; d4.z += upd.z; d4.w += upd.w;
-                                del[slot * 32] = d4;
-                            }
-                        }
-#pragma unroll
-                        for (int t = 1; t < T; ++t) {
-                            const float step = __shfl_sync(FULL, step_mine, t << SHIFT);
-                            float d[4];
-#pragma unroll
-                            for (int e = 0; e < 4; ++e) { acc[e] = fmaf(step, row[t][e], acc[e]); d[e] = step * cen[e]; }
-                            if (ok) red_vec<4>(a.w_out + (int64_t)tid[t] * E + eoff, d, a.sys_scope);
-                        }
-                    }
-                }
-            }
-            if (ok) red_vec<4>(a.w_in + crow * E + eoff, acc, a.sys_scope);
-            // slide: the oldest position leaves the window -> one scatter of everything it accumulated
-            if (slide) {
-                if (ok) {
-                    const float4 d4 = del[head * 32];
-                    const float d[4] = {d4.x, d4.y, d4.z, d4.w};
-                    red_vec<4>(a.w_out + ((int64_t)__ldg(seq + p - r) + a.row_offset) * E + eoff, d, a.sys_scope);
-                }
-                cp_async_wait_all();
-                if (++head == RING) head = 0;
-            }
-        }
-        // segment end: flush the 2r + 1 rows still resident (positions p_last - r .. p_last + r)
-        {
-            const int p_last = p0 + m - 1;
-            int slot = head;
-            for (int j = 0; j <= 2 * r; ++j) {
-                if (ok) {
-                    const float4 d4 = del[slot * 32];
-                    const float d[4] = {d4.x, d4.y, d4.z, d4.w};
-                    red_vec<4>(a.w_out + ((int64_t)__ldg(seq + p_last - r + j) + a.row_offset) * E + eoff, d, a.sys_scope);
-                }
-                if (++slot == RING) slot = 0;
-            }
-        }
-    }
-
-    flush_stats(a.stats, loss_pos != 0.f || loss_neg != 0.f || cnt_pairs != 0 || cnt_fp != 0 || cnt_recall != 0, loss_pos, loss_neg, cnt_recall,
-                cnt_fp, cnt_pairs, (double)cnt_pairs * (double)K);
-}
-
-template <int T, bool EXACT>
-int launch_win_one(const SgnsArgs &a, cudaStream_t stream) {
-    auto kern = sgns_win_kernel<T, EXACT>;
-    const size_t smem = (size_t)(SGNS_THREADS / 32) * 2 * (2 * a.radius + 2) * 32 * sizeof(float4);
-    if (check_cuda(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem), "cudaFuncSetAttribute") != SE_OK) return SE_ERR_CUDA;
-    const int blocks = persistent_blocks(kern, smem, a.n_units, SGNS_THREADS / 32, true);
-    if (blocks < 0) return SE_ERR_UNSUPPORTED;            // the ring does not fit: the caller falls back to the per-context kernel
-    if (blocks == 0) return SE_ERR_CUDA;
-    kern<<<blocks, SGNS_THREADS, smem, stream>>>(a);
-    return check_cuda(cudaGetLastError(), "sgns_win_kernel launch");
-}
-
-template <bool EXACT>
-int launch_win_t(const SgnsArgs &a, cudaStream_t stream) {
-    switch (1 + a.n_neg) {
-        case 1: return launch_win_one<1, EXACT>(a, stream);
-        case 2: return launch_win_one<2, EXACT>(a, stream);
-        case 3: return launch_win_one<3, EXACT>(a, stream);
-        case 4: return launch_win_one<4, EXACT>(a, stream);
-        case 5: return launch_win_one<5, EXACT>(a, stream);
-        case 6: return launch_win_one<6, EXACT>(a, stream);
-        case 7: return launch_win_one<7, EXACT>(a, stream);
-        case 8: return launch_win_one<8, EXACT>(a, stream);
-        default: return SE_ERR_UNSUPPORTED;
-    }
-}
-
+// Window-resident kernel family: sgns_win.cuh, instantiated per lane-group width in sgns_win_g*.cu.
 // Returns SE_ERR_UNSUPPORTED when the shape is not covered (caller tries the next kernel).
+// ------------------------------------------------------------------------------------------------------------------
 int launch_win(const SgnsArgs &a, cudaStream_t stream) {
-    // rows of 36..128 floats: one float4 per lane, lanes beyond the row idle (still far fewer instructions per pair than the generic
-    // group-per-centre kernel: measured 1.65x at E = 64 on the Zipf stream); shorter rows pack several centres per warp in sgns_kernel
-    if (a.emb % 4 != 0 || a.emb <= 32 || a.emb > 128 || a.n_neg > 7 || a.radius > 8 || a.scatter_store || a.no_window) return SE_ERR_UNSUPPORTED;
+    if (a.emb % 4 != 0 || a.emb < 16 || a.emb > 128 || a.n_neg > 7 || a.radius > 8 || a.scatter_store || a.no_window) return SE_ERR_UNSUPPORTED;
     if (((uintptr_t)a.w_in % 16) || ((uintptr_t)a.w_out % 16)) return SE_ERR_UNSUPPORTED;
-    return a.emb == 128 ? launch_win_t<true>(a, stream) : launch_win_t<false>(a, stream);
+    int rc = SE_ERR_UNSUPPORTED;
+    if (a.emb > 64) {
+        if (a.hot_rows > 0) rc = launch_win_g32_hot(a, stream);
+        if (rc == SE_ERR_UNSUPPORTED) rc = launch_win_g32(a, stream);
+    } else if (a.emb > 32) {
+        rc = launch_win_g16(a, stream);
+    } else {
+        rc = launch_win_g8(a, stream);
+    }
+    return rc;
 }
 
 
@@ -1361,7 +1014,8 @@ extern "C" int se_sgns_update_walks_sharded(float *w_in, float *w_out, int64_t v
     // W2VCollateFunctional asserts text_length >= 2r+1 (torch_dataset.py:298)
     SE_REQUIRE(seq_len >= 2 * radius + 1, "Text is too short! [text_length=%d] < [min_text_length=%d]", seq_len, 2 * radius + 1);
     SE_REQUIRE((alias_prob == nullptr) == (alias_idx == nullptr), "se_sgns_update_walks: pass both alias arrays or neither");
-    SE_REQUIRE((flags & ~(SE_SGNS_SCATTER_STORE | SE_SGNS_GENERIC_KERNEL | SE_SGNS_NO_WINDOW)) == 0, "se_sgns_update_walks: unknown flags %d", flags);
+    SE_REQUIRE((flags & ~(SE_SGNS_SCATTER_STORE | SE_SGNS_GENERIC_KERNEL | SE_SGNS_NO_WINDOW | SE_SGNS_WHOLE_SEQUENCES | SE_SGNS_HOT_ROWS_MASK)) == 0,
+               "se_sgns_update_walks: unknown flags %d", flags);
     se::SgnsArgs a{};
     a.w_in = w_in; a.w_out = w_out; a.tokens = tokens; a.alias_prob = alias_prob; a.alias_idx = alias_idx;
     a.stats = stats; a.vocab = vocab; a.emb = emb; a.n_ctx = 2 * radius; a.n_neg = n_neg;
@@ -1370,6 +1024,9 @@ extern "C" int se_sgns_update_walks_sharded(float *w_in, float *w_out, int64_t v
     a.lr = lr; a.seed = seed; a.id_base = centre_id_base; a.scatter_store = (flags & SE_SGNS_SCATTER_STORE) != 0;
     a.force_generic = (flags & SE_SGNS_GENERIC_KERNEL) != 0;
     a.no_window = (flags & SE_SGNS_NO_WINDOW) != 0;
+    a.whole_seq = (flags & SE_SGNS_WHOLE_SEQUENCES) != 0;
+    a.hot_rows = (int)(((unsigned)flags & (unsigned)SE_SGNS_HOT_ROWS_MASK) >> SE_SGNS_HOT_ROWS_SHIFT);
+    a.n_seq = n_seq;
     rc = apply_shard_spec("se_sgns_update_walks_sharded", a, spec);
     if (rc != SE_OK) return rc;
     SE_REQUIRE(!(a.sys_scope && a.scatter_store), "se_sgns_update_walks_sharded: plain-store scatter is not supported on "

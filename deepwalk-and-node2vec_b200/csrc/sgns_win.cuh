@@ -1,0 +1,359 @@
+// Window-resident SGNS kernel (MODE_WALK: tokens[n_seq x L] -> windows, negatives, in-place update), sm_100a.
+//
+// A GROUP of G lanes (G = 32 / 16 / 8 for rows of up to 128 / 64 / 32 floats: 1 / 2 / 4 centres per warp, one float4 per lane)
+// walks its span of centres with the W_out rows of the 2r+1 tokens around the current centre RESIDENT in shared memory (a ring
+// of 2r+2 physical slots per group: current value + pending update).  A token's context row is fetched ONCE when it enters the
+// window (cp.async, issued one centre ahead), serves as the positive row of up to 2r centres from shared memory, and its
+// accumulated update leaves with ONE red.global.add.v4.f32 when the token slides out -- instead of 2r gathers and 2r scatters
+// through L2 (window rule: word2vec/dataloader/torch_dataset.py:300-309).  Negatives, the centre row, the transposed reduction
+// and the loss arithmetic (word2vec/loss.py:15-16) are those of sgns_ctx_kernel.
+//
+// Repeated tokens.  Random walks revisit nodes all the time (A-B-A at p = 0.5; a whole walk on a 3-node path).  Window POSITIONS
+// (logical ring slots) are therefore mapped to PHYSICAL slots through a small table: a token that enters the window while its row
+// is already resident ALIASES the resident slot, so inside one group every pair sees the row's latest value -- the pair-by-pair
+// semantics of the reference's sequential updates and of the per-pair kernel -- and no duplicate is fetched.  When the older
+// position slides out, the pending update is scattered (so updates never wait longer than one window length) and the slot lives on
+// for its remaining aliases.
+//
+// Hot rows (HOT = true, se flags SE_SGNS_HOT_ROWS(n)).  With frequency-sorted vocabularies (the text path: torchtext orders by
+// frequency, torch_dataset.py:104-110) and unigram^0.75 negatives, the first rows of W_out receive a large share of all updates;
+// their red.global.add serialise per address at the L2 atomic unit and become the critical path (S4: 0.93 G pairs/s against 1.56 G
+// with uniform negatives).  Rows [0, n) are instead COMBINED PER CTA: every update of such a row -- positive or negative -- is a
+// shared-memory atomic add into a per-CTA accumulator, every read adds the accumulator to the value from L2, and the
+// accumulators are drained round-robin (one row per group per centre) with one red.global each.  Hot context rows are not made
+// ring-resident, so their staleness is bounded by the drain period (a few centres) instead of the window length.
+#pragma once
+#include "sgns_common.cuh"
+
+namespace se {
+namespace {
+
+constexpr int WIN_HOT_MARK = -1;       // physical slot of a window position whose row goes through the hot-row cache
+constexpr int WIN_HOT_MAX = 4096;
+
+template <int G, int T, bool EXACT, bool HOT, int THREADS>
+__global__ void __launch_bounds__(THREADS, (THREADS <= 256 ? 2 : 1))
+sgns_win_kernel(const SgnsArgs a) {
+    constexpr int K = T - 1;
+    constexpr int P = (T <= 1) ? 1 : (T <= 2) ? 2 : (T <= 4) ? 4 : 8;              // dots padded to a power of two
+    constexpr int LOG_G = (G == 32) ? 5 : (G == 16) ? 4 : 3;
+    constexpr int LOG_P = (P == 8) ? 3 : (P == 4) ? 2 : (P == 2) ? 1 : 0;
+    constexpr int SHIFT = LOG_G - LOG_P;                                           // lanes per owner sub-group = 1 << SHIFT
+    constexpr int GPB = THREADS / G;                                               // groups per block
+    constexpr int HS = 4 * G;                                                      // floats per hot-cache row
+    static_assert(P <= G && T <= G, "one lane per target row");
+    extern __shared__ float4 win_smem[];
+    const int lg = threadIdx.x & (G - 1);
+    const int grp = threadIdx.x / G;
+    const unsigned gmask = group_mask<G>();
+    const int64_t gid = (int64_t)blockIdx.x * GPB + grp;
+    const int64_t n_groups = (int64_t)gridDim.x * GPB;
+    const int E = EXACT ? 4 * G : a.emb;
+    const int eoff = lg * 4;
+    const bool ok = EXACT || eoff < E;
+    const int N = a.n_ctx, NG = (a.n_ctx + 3) >> 2, r = a.radius;
+    const int RING = 2 * r + 2;
+    float4 *cur = win_smem + (size_t)grp * 2 * RING * G + lg;                      // physical slot s: cur[s * G], del[s * G]
+    float4 *del = cur + RING * G;
+    int *ids_s = reinterpret_cast<int *>(win_smem + (size_t)GPB * 2 * RING * G) + grp * 2 * RING;   // row id of logical slot l
+    int *phys_s = ids_s + RING;                                                                     // its physical slot (or WIN_HOT_MARK)
+    float *hot = reinterpret_cast<float *>(win_smem + (size_t)GPB * 2 * RING * G) + GPB * 2 * RING; // [H][HS] pending updates of rows < H
+    const int H = HOT ? a.hot_rows : 0;
+    const int owner_t = lg >> SHIFT;
+    const bool owner_rep = (lg & ((1 << SHIFT) - 1)) == 0;
+
+    if constexpr (HOT) {
+        for (int i = threadIdx.x; i < H * HS; i += THREADS) hot[i] = 0.f;
+        __syncthreads();
+    }
+
+    float loss_pos = 0.f, loss_neg = 0.f;
+    unsigned cnt_recall = 0, cnt_fp = 0, cnt_pairs = 0;
+    unsigned free_mask = 0;
+    unsigned drained = 0;                                                          // centres this group has finished (hot-row drain schedule)
+
+    // ---- row access: plain rows through L2, hot rows through the per-CTA accumulator -----------------------------------
+    auto load_row = [&](int rid, float (&v)[4]) {
+        v[0] = v[1] = v[2] = v[3] = 0.f;
+        if (!ok) return;
+        load_vec<4>(a.w_out + (int64_t)rid * E + eoff, v);
+        if constexpr (HOT) {
+            if (rid < H) {
+                const float4 h = *reinterpret_cast<const float4 *>(hot + rid * HS + eoff);
+                v[0] += h.x; v[1] += h.y; v[2] += h.z; v[3] += h.w;
+            }
+        }
+    };
+    auto push_row = [&](int rid, const float (&d)[4]) {
+        if (!ok) return;
+        if constexpr (HOT) {
+            if (rid < H) {
+                float *hp = hot + rid * HS + eoff;
+                atomicAdd(hp, d[0]); atomicAdd(hp + 1, d[1]); atomicAdd(hp + 2, d[2]); atomicAdd(hp + 3, d[3]);
+                return;
+            }
+        }
+        red_vec<4>(a.w_out + (int64_t)rid * E + eoff, d, a.sys_scope);
+    };
+    auto scatter_slot = [&](int ph, int rid) {                                     // pending update of a resident slot -> global, then cleared
+        if (!ok) return;
+        const float4 d4 = del[ph * G];
+        if (d4.x != 0.f || d4.y != 0.f || d4.z != 0.f || d4.w != 0.f) {
+            const float d[4] = {d4.x, d4.y, d4.z, d4.w};
+            red_vec<4>(a.w_out + (int64_t)rid * E + eoff, d, a.sys_scope);
+            del[ph * G] = make_float4(0.f, 0.f, 0.f, 0.f);
+        }
+    };
+    // token with row `rid` enters logical slot l_new; the n_valid logical slots from first_l on are searched for the same row
+    auto enter = [&](int l_new, int rid, int first_l, int n_valid) {
+        int ph = -2;
+        if (HOT && rid < H) {
+            ph = WIN_HOT_MARK;
+        } else {
+            int l = first_l;
+            for (int j = 0; j < n_valid; ++j) {
+                if (ids_s[l] == rid) ph = phys_s[l];
+                if (++l == RING) l = 0;
+            }
+            if (ph == -2) {
+                ph = __ffs(free_mask) - 1;
+                free_mask &= ~(1u << ph);
+                if (ok) {
+                    cp_async16(cur + ph * G, a.w_out + (int64_t)rid * E + eoff);
+                    del[ph * G] = make_float4(0.f, 0.f, 0.f, 0.f);
+                }
+            }
+        }
+        __syncwarp(gmask);
+        if (lg == 0) { ids_s[l_new] = rid; phys_s[l_new] = ph; }
+        __syncwarp(gmask);
+    };
+
+    int64_t span = (a.n_units + n_groups - 1) / n_groups;
+    if (a.whole_seq) span = ((span + a.n_cen - 1) / a.n_cen) * a.n_cen;            // no sequence is split between two groups
+    int64_t u = gid * span;
+    const int64_t u_end = min(a.n_units, u + span);
+
+    while (u < u_end) {
+        // ---- one segment: consecutive centres of ONE sequence ----------------------------------------------------
+        const int64_t s = u / a.n_cen;
+        const int p0 = r + (int)(u - s * a.n_cen);
+        const int m = (int)min(u_end - u, (int64_t)(a.n_cen - (p0 - r)));          // centres p0 .. p0 + m - 1
+        const int32_t *seq = a.tokens + s * a.seq_len;
+        free_mask = (RING >= 32) ? 0xffffffffu : ((1u << RING) - 1u);
+        __syncwarp(gmask);
+        // window of the first centre: positions p0 - r .. p0 + r -> logical slots 0 .. 2r
+        for (int j = 0; j <= 2 * r; ++j) enter(j, __ldg(seq + p0 - r + j) + a.row_offset, 0, j);
+        cp_async_wait_all();
+        int head = 0;                                                              // logical slot of position p - r
+
+        for (int p = p0; p < p0 + m; ++p, ++u) {
+            // the row entering the window for the next centre goes to the free logical slot while this centre is processed
+            int l_in = head - 1; if (l_in < 0) l_in += RING;
+            const bool slide = p + 1 < p0 + m;
+            if (slide) enter(l_in, __ldg(seq + p + r + 1) + a.row_offset, head, 2 * r + 1);
+            const int64_t crow = (int64_t)__ldg(seq + p) + a.row_offset;
+            float cen[4] = {0.f, 0.f, 0.f, 0.f}, acc[4] = {0.f, 0.f, 0.f, 0.f};
+            if (ok) load_vec<4>(a.w_in + crow * E + eoff, cen);
+
+            for (int g = 0; g < NG; ++g) {
+                // ids of the negatives this lane owns (lane t = negative t - 1) in contexts 4g .. 4g + 3
+                int ids[4] = {0, 0, 0, 0};
+                if (K > 0) {
+                    const uint64_t cid = (uint64_t)(a.id_base + u);
+                    const int k = lg >= 1 ? lg - 1 : 0;
+                    const uint4 wb = neg_words(a.seed, cid, g * 4, k, STREAM_NEG);
+                    uint4 wc = make_uint4(0, 0, 0, 0);
+                    if (a.alias_prob) wc = neg_words(a.seed, cid, g * 4, k, STREAM_NEG_COIN);
+#pragma unroll
+                    for (int j = 0; j < 4; ++j)
+                        if (g * 4 + j < N && lg >= 1 && lg < T) ids[j] = neg_row(a, pick_word(wb, j), pick_word(wc, j));
+                }
+#pragma unroll
+                for (int j = 0; j < 4; ++j) {
+                    const int n = g * 4 + j;
+                    if (n < N) {
+                        int l = head + ((n < r) ? n : n + 1);                      // window offset of context n (centre skipped)
+                        if (l >= RING) l -= RING;
+                        const int ph = phys_s[l];
+                        const int rid0 = HOT ? ids_s[l] : 0;
+                        int tid[T];
+                        float row[T][4];
+                        float dot[P];
+#pragma unroll
+                        for (int t = 1; t < T; ++t) tid[t] = __shfl_sync(gmask, ids[j], t, G);
+                        if (!HOT || ph >= 0) {
+                            row[0][0] = row[0][1] = row[0][2] = row[0][3] = 0.f;
+                            if (ok) { const float4 c4 = cur[ph * G]; row[0][0] = c4.x; row[0][1] = c4.y; row[0][2] = c4.z; row[0][3] = c4.w; }
+                        } else {
+                            load_row(rid0, row[0]);
+                        }
+#pragma unroll
+                        for (int t = 1; t < T; ++t) load_row(tid[t], row[t]);
+#pragma unroll
+                        for (int t = 0; t < P; ++t) {
+                            float d = 0.f;
+                            if (t < T) {
+#pragma unroll
+                                for (int e = 0; e < 4; ++e) d = fmaf(row[t][e], cen[e], d);
+                            }
+                            dot[t] = d;
+                        }
+                        const float sc = transposed_reduce<P, G>(dot, lg, gmask);
+                        float step_mine = 0.f;
+                        if (owner_t < T) {
+                            const bool positive = owner_t == 0;
+                            const float x = positive ? sc : -sc;                      // loss = -log clamp(sigmoid(x), 1e-6)
+                            const float ex = __expf(-x);
+                            const float sig = __fdividef(1.0f, 1.0f + ex);
+                            const bool live = sig > CLAMP_MIN;
+                            const float gmag = live ? ex * sig : 0.f;                 // |dL/ds| = sigmoid(-x)
+                            step_mine = positive ? a.lr * gmag : -a.lr * gmag;        // -lr * dL/ds
+                            if (owner_rep) {
+                                const float lo = -__logf(fmaxf(sig, CLAMP_MIN));
+                                if (positive) { loss_pos += lo; cnt_recall += x >= 0.f; cnt_pairs += 1; }
+                                else { loss_neg += lo; cnt_fp += x <= 0.f; }
+                            }
+                        }
+                        {   // positive row: update the resident copy and its pending update (or the hot-row accumulator)
+                            const float step = __shfl_sync(gmask, step_mine, 0, G);
+                            const float upd[4] = {step * cen[0], step * cen[1], step * cen[2], step * cen[3]};
+#pragma unroll
+                            for (int e = 0; e < 4; ++e) acc[e] = fmaf(step, row[0][e], acc[e]);
+                            if (!HOT || ph >= 0) {
+                                if (ok) {
+                                    cur[ph * G] = make_float4(row[0][0] + upd[0], row[0][1] + upd[1], row[0][2] + upd[2], row[0][3] + upd[3]);
+                                    float4 d4 = del[ph * G];
+                                    d4.x += upd[0]; d4.y += upd[1]; d4.z += upd[2]; d4.w += upd[3];
+                                    del[ph * G] = d4;
+                                }
+                            } else {
+                                push_row(rid0, upd);
+                            }
+                        }
+#pragma unroll
+                        for (int t = 1; t < T; ++t) {
+                            const float step = __shfl_sync(gmask, step_mine, t << SHIFT, G);
+                            float d[4];
+#pragma unroll
+                            for (int e = 0; e < 4; ++e) { acc[e] = fmaf(step, row[t][e], acc[e]); d[e] = step * cen[e]; }
+                            push_row(tid[t], d);
+                        }
+                    }
+                }
+            }
+            if (ok) red_vec<4>(a.w_in + crow * E + eoff, acc, a.sys_scope);
+            // slide: the oldest position leaves the window.  Its pending update is scattered now (even if other positions alias
+            // the slot: updates never wait longer than one window length); the slot is freed when no alias is left.
+            if (slide) {
+                const int ph = phys_s[head];
+                if (ph >= 0) {
+                    scatter_slot(ph, ids_s[head]);
+                    bool aliased = false;
+                    int l = head;
+                    for (int j = 0; j <= 2 * r; ++j) {                             // the window after the slide: head + 1 .. head + 2r + 1
+                        if (++l == RING) l = 0;
+                        aliased |= phys_s[l] == ph;
+                    }
+                    if (!aliased) free_mask |= 1u << ph;
+                }
+                cp_async_wait_all();
+                if (++head == RING) head = 0;
+            }
+            if constexpr (HOT) {
+                // drain one hot row per group per centre, round-robin over the CTA's groups
+                if (H > 0) {
+                    const int f = (int)((drained * (unsigned)GPB + (unsigned)grp) % (unsigned)H);
+                    ++drained;
+                    if (ok) {
+                        float *hp = hot + f * HS + eoff;
+                        const float d[4] = {atomicExch(hp, 0.f), atomicExch(hp + 1, 0.f), atomicExch(hp + 2, 0.f), atomicExch(hp + 3, 0.f)};
+                        if (d[0] != 0.f || d[1] != 0.f || d[2] != 0.f || d[3] != 0.f) red_vec<4>(a.w_out + (int64_t)f * E + eoff, d, a.sys_scope);
+                    }
+                }
+            }
+        }
+        // segment end: scatter what is still pending in the 2r + 1 resident positions (each physical slot once)
+        {
+            unsigned done = 0;
+            int l = head;
+            for (int j = 0; j <= 2 * r; ++j) {
+                const int ph = phys_s[l];
+                if (ph >= 0 && !((done >> ph) & 1u)) {
+                    done |= 1u << ph;
+                    scatter_slot(ph, ids_s[l]);
+                }
+                if (++l == RING) l = 0;
+            }
+        }
+    }
+
+    if constexpr (HOT) {
+        __syncthreads();                                                           // every group is done with the accumulators
+        for (int i = threadIdx.x; i < H * G; i += THREADS) {
+            const int f = i / G, eo = (i - f * G) * 4;
+            if (EXACT || eo < E) {
+                const float4 h = *reinterpret_cast<const float4 *>(hot + f * HS + eo);
+                if (h.x != 0.f || h.y != 0.f || h.z != 0.f || h.w != 0.f) {
+                    const float d[4] = {h.x, h.y, h.z, h.w};
+                    red_vec<4>(a.w_out + (int64_t)f * E + eo, d, a.sys_scope);
+                }
+            }
+        }
+    }
+
+    flush_stats(a.stats, loss_pos != 0.f || loss_neg != 0.f || cnt_pairs != 0 || cnt_fp != 0 || cnt_recall != 0, loss_pos, loss_neg, cnt_recall,
+                cnt_fp, cnt_pairs, (double)cnt_pairs * (double)K);
+}
+
+inline size_t win_smem_bytes(int gpb, int g, int radius, int hot_rows) {
+    const int ring = 2 * radius + 2;
+    return (size_t)gpb * 2 * ring * g * sizeof(float4) + (size_t)gpb * 2 * ring * sizeof(int) + (size_t)hot_rows * 4 * g * sizeof(float);
+}
+
+template <int G, int T, bool EXACT, bool HOT>
+int launch_win_one(const SgnsArgs &a_in, cudaStream_t stream) {
+    constexpr int THREADS = HOT ? 512 : SGNS_THREADS;       // the hot-row cache is shared by 16 warps: one block per SM
+    constexpr int GPB = THREADS / G;
+    auto kern = sgns_win_kernel<G, T, EXACT, HOT, THREADS>;
+    SgnsArgs a = a_in;
+    if (HOT) {
+        int dev = 0, max_smem = 0;
+        if (check_cuda(cudaGetDevice(&dev), "cudaGetDevice") != SE_OK) return SE_ERR_CUDA;
+        if (check_cuda(cudaDeviceGetAttribute(&max_smem, cudaDevAttrMaxSharedMemoryPerBlockOptin, dev), "cudaDeviceGetAttribute") != SE_OK) return SE_ERR_CUDA;
+        const int64_t room = (int64_t)max_smem - (int64_t)win_smem_bytes(GPB, G, a.radius, 0) - 1024;
+        const int64_t fit = room / (4 * G * (int64_t)sizeof(float));
+        if (fit < 1) return SE_ERR_UNSUPPORTED;              // no room for a single hot row: the caller uses the plain variant
+        if (a.hot_rows > fit) a.hot_rows = (int)fit;
+        if (a.hot_rows > WIN_HOT_MAX) a.hot_rows = WIN_HOT_MAX;
+        if ((int64_t)a.hot_rows > a.vocab) a.hot_rows = (int)a.vocab;
+    } else {
+        a.hot_rows = 0;
+    }
+    const size_t smem = win_smem_bytes(GPB, G, a.radius, a.hot_rows);
+    if (check_cuda(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem), "cudaFuncSetAttribute") != SE_OK) return SE_ERR_CUDA;
+    const int blocks = persistent_blocks(kern, smem, a.n_units, GPB, true, THREADS);
+    if (blocks < 0) return SE_ERR_UNSUPPORTED;               // the ring does not fit: the caller falls back to the per-context kernel
+    if (blocks == 0) return SE_ERR_CUDA;
+    if (a.n_seq >= (int64_t)blocks * GPB) a.whole_seq = 1;   // enough sequences for every group: never split one
+    kern<<<blocks, THREADS, smem, stream>>>(a);
+    return check_cuda(cudaGetLastError(), "sgns_win_kernel launch");
+}
+
+template <int G, bool EXACT, bool HOT>
+int launch_win_t(const SgnsArgs &a, cudaStream_t stream) {
+    switch (1 + a.n_neg) {
+        case 1: return launch_win_one<G, 1, EXACT, HOT>(a, stream);
+        case 2: return launch_win_one<G, 2, EXACT, HOT>(a, stream);
+        case 3: return launch_win_one<G, 3, EXACT, HOT>(a, stream);
+        case 4: return launch_win_one<G, 4, EXACT, HOT>(a, stream);
+        case 5: return launch_win_one<G, 5, EXACT, HOT>(a, stream);
+        case 6: return launch_win_one<G, 6, EXACT, HOT>(a, stream);
+        case 7: return launch_win_one<G, 7, EXACT, HOT>(a, stream);
+        case 8: return launch_win_one<G, 8, EXACT, HOT>(a, stream);
+        default: return SE_ERR_UNSUPPORTED;
+    }
+}
+
+}  // namespace
+}  // namespace se

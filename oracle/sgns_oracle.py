@@ -108,3 +108,38 @@ def sgd_step(w_in: np.ndarray, w_out: np.ndarray, inputs: np.ndarray, targets: n
 def windows_from_walks(walks: np.ndarray, context_radius: int, row_offset: int = 0) -> Tuple[np.ndarray, np.ndarray]:
     """Batched collate over a dense (n_walks, L) token matrix (every row has the same length)."""
     return collate_sg([w + row_offset for w in np.asarray(walks)], context_radius, walks.shape[1])
+
+
+def sequential_window_sgd(w_in: np.ndarray, w_out: np.ndarray, tokens: np.ndarray, context_radius: int, row_offset: int,
+                          noise: np.ndarray, lr: float) -> Tuple[np.ndarray, np.ndarray, float]:
+    """In-place SGD applied PAIR BY PAIR in the reference's batch order (sequence, centre, context;
+    torch_dataset.py:300-309 windows, loss.py:15-16 per-pair loss, un-averaged: lr multiplies dL_pair): the limit of the
+    reference's training loop for batches of one pair, and what one lane group of the window kernel computes for a
+    sequence -- repeated tokens inside a window included.  Per centre the centre row is read once and written once (its
+    gradient accumulates over the window); every context / negative row is read and updated immediately, so a row that
+    occurs twice in a window sees its own earlier update.  noise: (n_centres, 2r, K) row ids.  Returns the updated
+    copies and the summed loss."""
+    w_in, w_out = w_in.astype(np.float64).copy(), w_out.astype(np.float64).copy()
+    r = context_radius
+    loss, c_idx = 0.0, 0
+    for text in np.asarray(tokens):
+        rows = text.astype(np.int64) + row_offset
+        for i in range(r, len(rows) - r):
+            c = w_in[rows[i]].copy()
+            acc = np.zeros_like(c)
+            ctx = np.concatenate([rows[i - r:i], rows[i + 1:i + 1 + r]])
+            for n, o in enumerate(ctx):
+                targets = np.concatenate([[o], noise[c_idx, n]]) if noise is not None and noise.shape[2] else np.array([o])
+                vals = w_out[targets].copy()                  # all rows of one pair are read before any is updated
+                s = vals @ c
+                for t, (row, sc) in enumerate(zip(targets, s)):
+                    x = sc if t == 0 else -sc
+                    sig = 1.0 / (1.0 + np.exp(-x))
+                    loss += -np.log(max(sig, CLAMP_MIN))
+                    gmag = (1.0 - sig) if sig > CLAMP_MIN else 0.0
+                    step = lr * gmag if t == 0 else -lr * gmag
+                    acc += step * vals[t]
+                    w_out[row] += step * c
+            w_in[rows[i]] += acc
+            c_idx += 1
+    return w_in, w_out, loss

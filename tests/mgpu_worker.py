@@ -212,7 +212,8 @@ def main():
         assert float((r_out.to_tensor().double() - (before_out + mine_out)).abs().max()) < 2e-6
         flat = r_in.to_tensor().reshape(-1)
         lo, hi = nat.replica_chunk(vocab * emb, world, rank)
-        assert torch.equal(r_in.master[:min(hi, vocab * emb) - lo], flat[lo:min(hi, vocab * emb)])
+        hi = max(lo, min(hi, vocab * emb))
+        assert torch.equal(r_in.master[:hi - lo], flat[lo:hi])
         ref = flat.clone()
         dist.broadcast(ref, src=0)
         assert torch.equal(ref, flat), 'working copies differ between ranks after the sync'

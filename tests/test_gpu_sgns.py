@@ -402,3 +402,119 @@ def test_out_of_range_tokens_raise_like_the_reference_embedding():
     nat.check_ids(torch.arange(10, dtype=torch.int32, device=dev), 0, 10)
     with pytest.raises(IndexError):
         nat.check_ids(torch.arange(11, dtype=torch.int32, device=dev), 0, 10)
+
+
+def _repeating_sequences(rng, n_seq, length, pool_size, vocab, offset):
+    """Sequences over disjoint small pools of tokens (so different lane groups never share a row), with the repeats random
+    walks produce: A-B-A returns, a token several times inside one window, a whole stretch on two nodes."""
+    pools = rng.permutation(vocab - offset)[:n_seq * pool_size].reshape(n_seq, pool_size)
+    out = np.empty((n_seq, length), dtype=np.int32)
+    for s in range(n_seq):
+        seq = [pools[s][0], pools[s][1]]
+        while len(seq) < length:
+            u = rng.random()
+            if u < 0.45:
+                seq.append(seq[-2])                              # A-B-A
+            elif u < 0.6:
+                seq.append(seq[-1])                              # self repeat (tokens of a sentence)
+            else:
+                seq.append(pools[s][rng.integers(pool_size)])
+        out[s] = seq[:length]
+    return out
+
+
+@pytest.mark.parametrize('emb,radius,k', [(128, 5, 0), (128, 2, 3), (100, 3, 2), (64, 2, 3), (48, 5, 3), (32, 2, 5), (20, 3, 1)])
+def test_window_kernel_with_repeated_tokens_equals_the_sequential_oracle(emb, radius, k):
+    """tokens that repeat INSIDE a window (A-B-A walks, sentences).  Window positions holding the same row
+    alias one shared-memory slot, so a lane group applies the pairs of its sequence exactly like a sequential pair-by-pair SGD
+    (oracle/sgns_oracle.sequential_window_sgd, fp64).  lr and weights are large enough that treating the copies as private
+    (round 1) would be off by ~1e-2; tolerance 2e-5 absolute on values of ~0.3 (fp32 arithmetic, fast exp)."""
+    dev = cuda_device()
+    rng = np.random.default_rng(100 + emb + radius)
+    offset, n_seq, vocab, lr = 1, (12 if k == 0 else 6), 1_000_000, 0.05
+    length = 2 * radius + 9
+    n_cen = length - 2 * radius
+    tokens = _repeating_sequences(rng, n_seq, length, 5, vocab, offset)
+    assert any(len(set(t[i - radius:i + radius + 1])) < 2 * radius + 1 for t in tokens for i in range(radius, length - radius))
+    token_rows = np.unique(tokens.astype(np.int64) + offset)
+    neg, seed = None, 1
+    if k:
+        for seed in range(1, 500):
+            neg = philox_ref.negatives(seed, np.arange(n_seq * n_cen) + 50, 2 * radius, k, vocab)
+            if len(np.unique(neg)) == neg.size and not np.isin(neg, token_rows).any():
+                break
+        else:
+            raise AssertionError('no collision-free seed')
+    w_in = rng.standard_normal((vocab, emb), dtype=np.float32) * np.float32(0.3)
+    w_out = rng.standard_normal((vocab, emb), dtype=np.float32) * np.float32(0.3)
+    rows = np.unique(np.concatenate([token_rows, neg.ravel()])) if k else token_rows
+    remap = {int(r): i for i, r in enumerate(rows)}
+    rm = np.vectorize(remap.get)
+    want_in, want_out, loss = sgns_oracle.sequential_window_sgd(w_in[rows], w_out[rows], rm(tokens.astype(np.int64) + offset), radius, 0,
+                                                                rm(neg) if k else None, lr)
+    t_in, t_out = _t(w_in, dev), _t(w_out, dev)
+    st = nat.sgns_update_walks(t_in, t_out, _t(tokens, dev), radius, k, offset, lr, seed, centre_id_base=50, flags=nat.WHOLE_SEQUENCES)
+    assert st['pairs'] == n_seq * n_cen * 2 * radius
+    got_in, got_out = t_in.cpu().numpy(), t_out.cpu().numpy()
+    assert np.abs(want_out - w_out[rows]).max() > 5e-3
+    np.testing.assert_allclose(got_out[rows], want_out, rtol=0, atol=2e-5)
+    np.testing.assert_allclose(got_in[rows], want_in, rtol=0, atol=2e-5)
+    assert abs(st['loss'] * st['pairs'] - loss) < 1e-4 * loss
+    untouched = np.setdiff1d(np.arange(vocab), rows)
+    assert np.array_equal(got_in[untouched], w_in[untouched]) and np.array_equal(got_out[untouched], w_out[untouched])
+
+
+@pytest.mark.parametrize('emb,hot', [(128, 8), (128, 40), (48, 16), (64, 300)])
+def test_window_kernel_zipf_sentence_with_hot_row_cache_equals_the_sequential_oracle(emb, hot):
+    """A Zipf-distributed sentence over a tiny frequency-sorted vocabulary (token id = frequency rank: the text path's
+    ordering): the most frequent rows go through the per-CTA hot-row accumulators (SE_SGNS_HOT_ROWS), the rest through the
+    window ring; ONE sequence, so one lane group applies every pair in order and the result must equal the sequential
+    oracle.  K = 0 here (negatives over 60 rows would collide with the window by construction; the alias-negative path of the
+    hot cache is covered statistically in test_hot_row_cache_matches_plain_kernel_to_second_order)."""
+    dev = cuda_device()
+    rng = np.random.default_rng(7 + emb + hot)
+    vocab, radius, length, offset, lr = 60, 3, 90, 1, 0.05
+    p = 1.0 / np.arange(1, vocab)
+    tokens = rng.choice(vocab - 1, size=(1, length), p=p / p.sum()).astype(np.int32)
+    w_in = (rng.standard_normal((vocab, emb)) * 0.3).astype(np.float32)
+    w_out = (rng.standard_normal((vocab, emb)) * 0.3).astype(np.float32)
+    want_in, want_out, loss = sgns_oracle.sequential_window_sgd(w_in, w_out, tokens, radius, offset, None, lr)
+    t_in, t_out = _t(w_in, dev), _t(w_out, dev)
+    st = nat.sgns_update_walks(t_in, t_out, _t(tokens, dev), radius, 0, offset, lr, 3, flags=nat.WHOLE_SEQUENCES | nat.hot_rows_flag(hot))
+    np.testing.assert_allclose(t_out.cpu().numpy(), want_out, rtol=0, atol=3e-5)
+    np.testing.assert_allclose(t_in.cpu().numpy(), want_in, rtol=0, atol=3e-5)
+    assert abs(st['loss'] * st['pairs'] - loss) < 1e-4 * loss
+
+
+def test_hot_row_cache_many_groups_alias_negatives_match_first_order_oracle():
+    """Many sequences on many lane groups, unigram^0.75 alias negatives concentrated on the first rows.  With a tiny lr every
+    row moves by -lr * (sum of the pairs' gradients at the initial weights), which the dense-gradient oracle gives exactly
+    (negatives predicted by the numpy Philox + alias restatement).  The hot-row variant must match it to 3 % of the largest
+    movement.  The plain variants are held to 30 %: they add ~1e-7 increments straight into weights of ~0.2 with
+    red.global.add.f32 (a few ulps each), which accumulates a visible rounding bias on the hottest row -- combining in
+    shared memory first is also the more accurate sum."""
+    dev = cuda_device()
+    rng = np.random.default_rng(3)
+    vocab, emb, radius, k, offset, n_seq, length, lr, seed = 5000, 128, 5, 5, 1, 1024, 32, 1e-6, 11
+    p = 1.0 / np.arange(1, vocab)
+    tokens = rng.choice(vocab - 1, size=(n_seq, length), p=p / p.sum()).astype(np.int32)
+    counts = np.concatenate([[0.0], np.bincount(tokens.ravel(), minlength=vocab - 1).astype(np.float64)])
+    alias = nat.alias_build(counts, 0.75, dev)
+    w_in = (rng.standard_normal((vocab, emb)) * 0.2).astype(np.float32)
+    w_out = (rng.standard_normal((vocab, emb)) * 0.2).astype(np.float32)
+    n_cen = length - 2 * radius
+    neg = philox_ref.negatives(seed, np.arange(n_seq * n_cen), 2 * radius, k, vocab, alias['prob'].cpu().numpy(), alias['alias'].cpu().numpy())
+    assert (neg < 48).mean() > 0.05                                          # the hot rows really are hit
+    inputs, targets = sgns_oracle.windows_from_walks(tokens.astype(np.int64), radius, offset)
+    o = sgns_oracle.training_step(w_in.astype(np.float64), w_out.astype(np.float64), inputs, targets, neg)
+    scale = lr * inputs.shape[0] * 2 * radius
+    want_out, want_in = -scale * o['grad_out'], -scale * o['grad_in']
+    moved = max(np.abs(want_out).max(), np.abs(want_in).max())
+    for flags, tol in ((nat.hot_rows_flag(48), 0.03), (nat.SCATTER_RED, 0.3), (nat.NO_WINDOW, 0.3)):
+        t_in, t_out = _t(w_in, dev), _t(w_out, dev)
+        st = nat.sgns_update_walks(t_in, t_out, _t(tokens, dev), radius, k, offset, lr, seed, alias=alias, flags=flags)
+        err = max(np.abs(t_out.cpu().numpy().astype(np.float64) - w_out - want_out).max(),
+                  np.abs(t_in.cpu().numpy().astype(np.float64) - w_in - want_in).max())
+        assert err < tol * moved, (flags, err, moved)
+        assert st['pairs'] == n_seq * n_cen * 2 * radius and st['negatives'] == st['pairs'] * k
+        assert abs(st['loss'] - o['loss']) < 1e-4 * o['loss']

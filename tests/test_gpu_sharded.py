@@ -334,7 +334,7 @@ def test_replicated_tables_sync_equals_the_sum_of_all_updates_simulated_ranks(wo
         assert float((got_in.double() - want_in).abs().max()) < 2e-6 and float((got_out.double() - want_out).abs().max()) < 2e-6
         assert torch.equal(got_in, nat.table_gather_rows(t_in.as_rank(0), rows))          # all copies identical bit for bit
         lo, hi = nat.replica_chunk(vocab * emb, world, r)
-        hi = min(hi, vocab * emb)
+        hi = max(lo, min(hi, vocab * emb))
         assert torch.equal(t_in._master_for(r)[:hi - lo], got_in.reshape(-1)[lo:hi])
     before = nat.table_gather_rows(t_in.as_rank(world - 1), rows)
     for r in range(world):
