@@ -75,6 +75,8 @@ def parse_args():
     ap.add_argument('--s4-sentence-len', type=int, default=128)
     ap.add_argument('--s4-zipf', type=float, default=1.0)
     ap.add_argument('--s4-power', type=float, default=0.75, help='negative-sampling exponent (0 = the reference\'s uniform draw)')
+    ap.add_argument('--window-refresh', type=int, default=None, help='S4: SE_SGNS_WINDOW_REFRESH (default on for the token stream)')
+    ap.add_argument('--s4-force-alias', action='store_true', help='dev: with --s4-power 0, still draw through an alias table (isolates its cost)')
     ap.add_argument('--nodes', type=int, default=10_000_000)
     ap.add_argument('--edges', type=int, default=250_000_000)
     ap.add_argument('--walks-per-step', type=int, default=262_144)
@@ -144,6 +146,19 @@ def workload_config(a, n_gpus):
         'parallelism': parallelism(a, n_gpus),
         'l2': 'inputs exceed L2 (tables 2 x %.2f GB, CSR ~%.1f GB); no flush' % ((a.nodes + 1) * a.emb * 4 / 1e9, (2 * a.edges * 4 + a.nodes * 8) / 1e9),
     }
+
+
+def sgns_kernel_label(emb, neg, window):
+    """Name of the kernel `se_sgns_update_walks` dispatches to for this shape (csrc/sgns.cu::launch, launch_win)."""
+    t = 1 + neg
+    if window and emb % 4 == 0 and 16 <= emb <= 128 and neg <= 7:
+        g = 32 if emb > 64 else (16 if emb > 32 else 8)
+        return f'sgns_win_kernel<G={g}, T={t}, EXACT={"true" if emb == 128 else "false"}> (E={emb})'
+    if emb % 4 == 0 and 32 < emb <= 128 and neg <= 7:
+        return f'sgns_ctx_kernel<MODE_WALK, T={t}> (E={emb})'
+    if emb % 4 == 0 and 64 < emb <= 1024:
+        return f'sgns_fast_kernel<MODE_WALK, R={-(-emb // 128)}> (E={emb})'
+    return f'sgns_kernel<MODE_WALK> generic (E={emb})'
 
 
 def bytes_per_pair(emb, neg, radius, window=False):
@@ -597,7 +612,7 @@ def run_b200(a, rank, local_rank, world):
         'kernel_ms': {'walk_kernel': walk_ms, 'sgns_kernel': sgns_ms},
         'roofline': {
             'bound': 'hbm', 'kernel': 'se_sgns_grad inside the NCCL row exchange (baseline)' if a2a else (
-                ('sgns_win_kernel<T=1+K, E=128>' if a.kernel == 'window' else 'sgns_ctx_kernel<MODE_WALK, T=1+K, E=128>') + ' (se_sgns_update_walks)'), 'achieved': achieved, 'peak': peak,
+                sgns_kernel_label(a.emb, a.neg, a.kernel == 'window') + ' via se_sgns_update_walks'), 'achieved': achieved, 'peak': peak,
             'unit': 'GB/s', 'frac': achieved / peak, 'peak_source': peak_src,
             'algorithmic_bytes_per_pair': bpp, 'pairs_per_launch': pairs_per_step,
             'bytes_per_pair_formula': '2*4E*(K + 2/N): context rows resident per window' if window else '2*4E*(1 + K + 1/N) (SURVEY 8d)',
@@ -670,7 +685,7 @@ def run_s4(a):
     weights = 1.0 / np.arange(1, a.s4_vocab + 1, dtype=np.float64) ** a.s4_zipf
     cdf = torch.from_numpy(np.cumsum(weights) / weights.sum()).to(dev)
     counts = np.concatenate([[0.0], weights / weights.sum() * 100e6])          # expected counts over 100 M tokens; '<unk>' never drawn
-    alias = nat.alias_build(counts, a.s4_power, dev) if a.s4_power != 0 else None
+    alias = nat.alias_build(counts, a.s4_power, dev) if (a.s4_power != 0 or a.s4_force_alias) else None
     gen = torch.Generator(device=dev)
     gen.manual_seed(a.seed)
     total_steps = a.warmup + 2 * a.steps + 2
@@ -686,7 +701,8 @@ def run_s4(a):
     w_out = torch.empty((vocab, a.emb), dtype=torch.float32, device=dev)
     nat.table_fill_uniform(w_in, bound, a.seed + 101)
     nat.table_fill_uniform(w_out, bound, a.seed + 102)
-    flags = nat.SCATTER_RED | (nat.NO_WINDOW if a.kernel == 'context' else 0)
+    refresh = (bool(a.window_refresh) if a.window_refresh is not None else True) and a.kernel == 'window'
+    flags = nat.SCATTER_RED | (nat.NO_WINDOW if a.kernel == 'context' else 0) | (nat.WINDOW_REFRESH if refresh else 0)
     stats = torch.zeros(nat.STATS_LEN, dtype=torch.float64, device=dev)
     stats_host = torch.zeros(nat.STATS_LEN, dtype=torch.float64).pin_memory()
     tok_scratch = torch.empty((n_seq, L), dtype=torch.int32, device=dev)
@@ -737,10 +753,10 @@ def run_s4(a):
         'config': {'workload': 'S4 synthetic Zipf token stream of the wiki-103 shape: windows -> alias negatives -> SGNS update',
                    'vocab': a.s4_vocab, 'zipf_s': a.s4_zipf, 'sentence_len': L, 'sentences_per_step': n_seq, 'tokens_per_step': n_seq * L,
                    'emb': a.emb, 'context_radius': a.radius, 'negatives': a.neg,
-                   'negative_sampling': f'alias table, unigram^{a.s4_power}' if alias else 'uniform (reference)',
+                   'negative_sampling': f'alias table, unigram^{a.s4_power}' if alias else 'uniform (reference)', 'window_refresh': refresh,
                    'optimizer': f'in-place SGD lr {a.lr} (Hogwild, red.global.add.v4.f32)', 'parallelism': 'single GPU',
                    'l2': 'tables 2 x %.0f MB vs 126 MB L2: largely L2-resident, no flush (hot set is the point of this workload)' % (vocab * a.emb * 4 / 1e6)},
-        'roofline': {'bound': 'hbm', 'kernel': ('sgns_win_kernel' if window else 'sgns_ctx_kernel') + '<T=1+K, E=128> (se_sgns_update_walks)',
+        'roofline': {'bound': 'hbm', 'kernel': sgns_kernel_label(a.emb, a.neg, window) + ' via se_sgns_update_walks',
                      'achieved': achieved, 'peak': peak, 'unit': 'GB/s', 'frac': achieved / peak, 'peak_source': peak_src,
                      'algorithmic_bytes_per_pair': bpp, 'pairs_per_launch': pairs_per_step, 'traffic': None,
                      'note': 'L2-assisted: algorithmic bytes are served mostly from L2 on this workload'},

@@ -572,8 +572,7 @@ int launch_win(const SgnsArgs &a, cudaStream_t stream) {
     if (((uintptr_t)a.w_in % 16) || ((uintptr_t)a.w_out % 16)) return SE_ERR_UNSUPPORTED;
     int rc = SE_ERR_UNSUPPORTED;
     if (a.emb > 64) {
-        if (a.hot_rows > 0) rc = launch_win_g32_hot(a, stream);
-        if (rc == SE_ERR_UNSUPPORTED) rc = launch_win_g32(a, stream);
+        rc = launch_win_g32(a, stream);
     } else if (a.emb > 32) {
         rc = launch_win_g16(a, stream);
     } else {
@@ -1014,7 +1013,7 @@ extern "C" int se_sgns_update_walks_sharded(float *w_in, float *w_out, int64_t v
     // W2VCollateFunctional asserts text_length >= 2r+1 (torch_dataset.py:298)
     SE_REQUIRE(seq_len >= 2 * radius + 1, "Text is too short! [text_length=%d] < [min_text_length=%d]", seq_len, 2 * radius + 1);
     SE_REQUIRE((alias_prob == nullptr) == (alias_idx == nullptr), "se_sgns_update_walks: pass both alias arrays or neither");
-    SE_REQUIRE((flags & ~(SE_SGNS_SCATTER_STORE | SE_SGNS_GENERIC_KERNEL | SE_SGNS_NO_WINDOW | SE_SGNS_WHOLE_SEQUENCES | SE_SGNS_HOT_ROWS_MASK)) == 0,
+    SE_REQUIRE((flags & ~(SE_SGNS_SCATTER_STORE | SE_SGNS_GENERIC_KERNEL | SE_SGNS_NO_WINDOW | SE_SGNS_WHOLE_SEQUENCES | SE_SGNS_WINDOW_REFRESH)) == 0,
                "se_sgns_update_walks: unknown flags %d", flags);
     se::SgnsArgs a{};
     a.w_in = w_in; a.w_out = w_out; a.tokens = tokens; a.alias_prob = alias_prob; a.alias_idx = alias_idx;
@@ -1025,7 +1024,7 @@ extern "C" int se_sgns_update_walks_sharded(float *w_in, float *w_out, int64_t v
     a.force_generic = (flags & SE_SGNS_GENERIC_KERNEL) != 0;
     a.no_window = (flags & SE_SGNS_NO_WINDOW) != 0;
     a.whole_seq = (flags & SE_SGNS_WHOLE_SEQUENCES) != 0;
-    a.hot_rows = (int)(((unsigned)flags & (unsigned)SE_SGNS_HOT_ROWS_MASK) >> SE_SGNS_HOT_ROWS_SHIFT);
+    a.win_refresh = (flags & SE_SGNS_WINDOW_REFRESH) != 0;
     a.n_seq = n_seq;
     rc = apply_shard_spec("se_sgns_update_walks_sharded", a, spec);
     if (rc != SE_OK) return rc;

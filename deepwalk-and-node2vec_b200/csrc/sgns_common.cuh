@@ -28,9 +28,9 @@ struct SgnsArgs {
     int sys_scope;                       // rows may live in peer HBM: system-scope reductions
     int no_window;                       // SE_SGNS_NO_WINDOW: per-context kernel instead of the window-resident one
     int own_shift;                       // sgns_negown_kernel: log2(stripe_rows); row r is owned by (r >> own_shift) % neg_world
-    int hot_rows;                        // window kernel: rows [0, hot_rows) of W_out are combined per CTA in shared memory (SE_SGNS_HOT_ROWS)
     int whole_seq;                       // window kernel: a group's span is rounded up to whole sequences (SE_SGNS_WHOLE_SEQUENCES)
     int64_t n_seq;                       // MODE_WALK: number of sequences
+    int win_refresh;                     // window kernel: re-fetch a resident row when its token is the centre (SE_SGNS_WINDOW_REFRESH)
     // row-sparse Adam (se_sgns_adam_step): first / second moments and per-row step counts of both tables
     float *m_in, *v_in, *m_out, *v_out;
     int32_t *t_in, *t_out;
@@ -40,8 +40,7 @@ struct SgnsArgs {
 // window-resident kernel family (sgns_win.cuh), one translation unit per lane-group width so they compile in parallel;
 // each returns SE_ERR_UNSUPPORTED when the shape is not covered
 int launch_win_g32(const SgnsArgs &a, cudaStream_t stream);        // 64 < emb <= 128: one centre per warp
-int launch_win_g32_hot(const SgnsArgs &a, cudaStream_t stream);    //   ... with the per-CTA hot-row cache
-int launch_win_g16(const SgnsArgs &a, cudaStream_t stream);        // 32 < emb <= 64: two centres per warp (hot-row cache optional)
+int launch_win_g16(const SgnsArgs &a, cudaStream_t stream);        // 32 < emb <= 64: two centres per warp
 int launch_win_g8(const SgnsArgs &a, cudaStream_t stream);         // 16 <= emb <= 32: four centres per warp
 
 namespace {

@@ -15,24 +15,23 @@
 // position slides out, the pending update is scattered (so updates never wait longer than one window length) and the slot lives on
 // for its remaining aliases.
 //
-// Hot rows (HOT = true, se flags SE_SGNS_HOT_ROWS(n)).  With frequency-sorted vocabularies (the text path: torchtext orders by
-// frequency, torch_dataset.py:104-110) and unigram^0.75 negatives, the first rows of W_out receive a large share of all updates;
-// their red.global.add serialise per address at the L2 atomic unit and become the critical path (S4: 0.93 G pairs/s against 1.56 G
-// with uniform negatives).  Rows [0, n) are instead COMBINED PER CTA: every update of such a row -- positive or negative -- is a
-// shared-memory atomic add into a per-CTA accumulator, every read adds the accumulator to the value from L2, and the
-// accumulators are drained round-robin (one row per group per centre) with one red.global each.  Hot context rows are not made
-// ring-resident, so their staleness is bounded by the drain period (a few centres) instead of the window length.
+// Mid-life refresh (SE_SGNS_WINDOW_REFRESH).  On token streams whose frequent tokens sit in thousands of windows at once (a Zipf
+// text corpus) a resident copy misses the other groups' updates for a whole window length; the flag scatters and re-fetches a
+// token's row when the token is the centre (it is not a context then, so nothing in use is touched): S4 mean loss 2.78 -> 2.44
+// (per-pair kernel: 2.45) for 6 % throughput.
+//
+// Tried and dropped (profiles/r02_s4_matrix.md): combining the most frequent rows per CTA in shared memory (fixed-point integer
+// atomics; fp32 shared atomics compile to CAS loops).  It removes the hottest rows' red.global traffic (the busiest L2 slice's
+// atomic unit is 68 % active against 23 % on average with unigram^0.75 negatives) but gains 3 % at best and delays the hot rows'
+// updates, which costs optimisation progress -- the alias-negative slowdown is not an atomic-throughput limit.
 #pragma once
 #include "sgns_common.cuh"
 
 namespace se {
 namespace {
 
-constexpr int WIN_HOT_MARK = -1;       // physical slot of a window position whose row goes through the hot-row cache
-constexpr int WIN_HOT_MAX = 4096;
-
-template <int G, int T, bool EXACT, bool HOT, int THREADS>
-__global__ void __launch_bounds__(THREADS, (THREADS <= 256 ? 2 : 1))
+template <int G, int T, bool EXACT, int THREADS>
+__global__ void __launch_bounds__(THREADS, 2)
 sgns_win_kernel(const SgnsArgs a) {
     constexpr int K = T - 1;
     constexpr int P = (T <= 1) ? 1 : (T <= 2) ? 2 : (T <= 4) ? 4 : 8;              // dots padded to a power of two
@@ -40,7 +39,6 @@ sgns_win_kernel(const SgnsArgs a) {
     constexpr int LOG_P = (P == 8) ? 3 : (P == 4) ? 2 : (P == 2) ? 1 : 0;
     constexpr int SHIFT = LOG_G - LOG_P;                                           // lanes per owner sub-group = 1 << SHIFT
     constexpr int GPB = THREADS / G;                                               // groups per block
-    constexpr int HS = 4 * G;                                                      // floats per hot-cache row
     static_assert(P <= G && T <= G, "one lane per target row");
     extern __shared__ float4 win_smem[];
     const int lg = threadIdx.x & (G - 1);
@@ -56,44 +54,20 @@ sgns_win_kernel(const SgnsArgs a) {
     float4 *cur = win_smem + (size_t)grp * 2 * RING * G + lg;                      // physical slot s: cur[s * G], del[s * G]
     float4 *del = cur + RING * G;
     int *ids_s = reinterpret_cast<int *>(win_smem + (size_t)GPB * 2 * RING * G) + grp * 2 * RING;   // row id of logical slot l
-    int *phys_s = ids_s + RING;                                                                     // its physical slot (or WIN_HOT_MARK)
-    float *hot = reinterpret_cast<float *>(win_smem + (size_t)GPB * 2 * RING * G) + GPB * 2 * RING; // [H][HS] pending updates of rows < H
-    const int H = HOT ? a.hot_rows : 0;
+    int *phys_s = ids_s + RING;                                                                     // its physical slot
     const int owner_t = lg >> SHIFT;
     const bool owner_rep = (lg & ((1 << SHIFT) - 1)) == 0;
-
-    if constexpr (HOT) {
-        for (int i = threadIdx.x; i < H * HS; i += THREADS) hot[i] = 0.f;
-        __syncthreads();
-    }
 
     float loss_pos = 0.f, loss_neg = 0.f;
     unsigned cnt_recall = 0, cnt_fp = 0, cnt_pairs = 0;
     unsigned free_mask = 0;
-    unsigned drained = 0;                                                          // centres this group has finished (hot-row drain schedule)
 
-    // ---- row access: plain rows through L2, hot rows through the per-CTA accumulator -----------------------------------
     auto load_row = [&](int rid, float (&v)[4]) {
         v[0] = v[1] = v[2] = v[3] = 0.f;
-        if (!ok) return;
-        load_vec<4>(a.w_out + (int64_t)rid * E + eoff, v);
-        if constexpr (HOT) {
-            if (rid < H) {
-                const float4 h = *reinterpret_cast<const float4 *>(hot + rid * HS + eoff);
-                v[0] += h.x; v[1] += h.y; v[2] += h.z; v[3] += h.w;
-            }
-        }
+        if (ok) load_vec<4>(a.w_out + (int64_t)rid * E + eoff, v);
     };
     auto push_row = [&](int rid, const float (&d)[4]) {
-        if (!ok) return;
-        if constexpr (HOT) {
-            if (rid < H) {
-                float *hp = hot + rid * HS + eoff;
-                atomicAdd(hp, d[0]); atomicAdd(hp + 1, d[1]); atomicAdd(hp + 2, d[2]); atomicAdd(hp + 3, d[3]);
-                return;
-            }
-        }
-        red_vec<4>(a.w_out + (int64_t)rid * E + eoff, d, a.sys_scope);
+        if (ok) red_vec<4>(a.w_out + (int64_t)rid * E + eoff, d, a.sys_scope);
     };
     auto scatter_slot = [&](int ph, int rid) {                                     // pending update of a resident slot -> global, then cleared
         if (!ok) return;
@@ -106,28 +80,40 @@ sgns_win_kernel(const SgnsArgs a) {
     };
     // token with row `rid` enters logical slot l_new; the n_valid logical slots from first_l on are searched for the same row
     auto enter = [&](int l_new, int rid, int first_l, int n_valid) {
-        int ph = -2;
-        if (HOT && rid < H) {
-            ph = WIN_HOT_MARK;
-        } else {
-            int l = first_l;
-            for (int j = 0; j < n_valid; ++j) {
-                if (ids_s[l] == rid) ph = phys_s[l];
-                if (++l == RING) l = 0;
-            }
-            if (ph == -2) {
-                ph = __ffs(free_mask) - 1;
-                free_mask &= ~(1u << ph);
-                if (ok) {
-                    cp_async16(cur + ph * G, a.w_out + (int64_t)rid * E + eoff);
-                    del[ph * G] = make_float4(0.f, 0.f, 0.f, 0.f);
-                }
+        int ph = -1;
+        int l = first_l;
+        for (int j = 0; j < n_valid; ++j) {
+            if (ids_s[l] == rid) ph = phys_s[l];
+            if (++l == RING) l = 0;
+        }
+        if (ph < 0) {
+            ph = __ffs(free_mask) - 1;
+            free_mask &= ~(1u << ph);
+            if (ok) {
+                cp_async16(cur + ph * G, a.w_out + (int64_t)rid * E + eoff);
+                del[ph * G] = make_float4(0.f, 0.f, 0.f, 0.f);
             }
         }
         __syncwarp(gmask);
         if (lg == 0) { ids_s[l_new] = rid; phys_s[l_new] = ph; }
         __syncwarp(gmask);
     };
+
+    // ids of the negatives this lane owns (lane t = negative t - 1) in contexts 4g .. 4g + 3 of centre uu
+    auto draw_group = [&](int64_t uu, int g, int (&out)[4]) {
+        out[0] = out[1] = out[2] = out[3] = 0;
+        if (K > 0) {
+            const uint64_t cid = (uint64_t)(a.id_base + uu);
+            const int k = lg >= 1 ? lg - 1 : 0;
+            const uint4 wb = neg_words(a.seed, cid, g * 4, k, STREAM_NEG);
+            uint4 wc = make_uint4(0, 0, 0, 0);
+            if (a.alias_prob) wc = neg_words(a.seed, cid, g * 4, k, STREAM_NEG_COIN);
+#pragma unroll
+            for (int j = 0; j < 4; ++j)
+                if (g * 4 + j < N && lg >= 1 && lg < T) out[j] = neg_row(a, pick_word(wb, j), pick_word(wc, j));
+        }
+    };
+    int nxt[4] = {0, 0, 0, 0};
 
     int64_t span = (a.n_units + n_groups - 1) / n_groups;
     if (a.whole_seq) span = ((span + a.n_cen - 1) / a.n_cen) * a.n_cen;            // no sequence is split between two groups
@@ -146,6 +132,7 @@ sgns_win_kernel(const SgnsArgs a) {
         for (int j = 0; j <= 2 * r; ++j) enter(j, __ldg(seq + p0 - r + j) + a.row_offset, 0, j);
         cp_async_wait_all();
         int head = 0;                                                              // logical slot of position p - r
+        draw_group(u, 0, nxt);
 
         for (int p = p0; p < p0 + m; ++p, ++u) {
             // the row entering the window for the next centre goes to the free logical slot while this centre is processed
@@ -155,20 +142,30 @@ sgns_win_kernel(const SgnsArgs a) {
             const int64_t crow = (int64_t)__ldg(seq + p) + a.row_offset;
             float cen[4] = {0.f, 0.f, 0.f, 0.f}, acc[4] = {0.f, 0.f, 0.f, 0.f};
             if (ok) load_vec<4>(a.w_in + crow * E + eoff, cen);
+            // mid-life refresh: the token that is the centre right now is not a context of this centre, so its resident W_out row can
+            // be scattered and re-fetched asynchronously without touching anything in use -- halves how stale a resident copy gets
+            // relative to the other groups (matters for frequent tokens, which sit in thousands of windows at once)
+            if (a.win_refresh && slide) {
+                int lc = head + r; if (lc >= RING) lc -= RING;
+                const int phc = phys_s[lc];
+                bool aliased = false;
+                int l = head;
+                for (int j = 0; j <= 2 * r; ++j) {
+                    aliased |= (l != lc) && phys_s[l] == phc;
+                    if (++l == RING) l = 0;
+                }
+                if (!aliased) {
+                    scatter_slot(phc, ids_s[lc]);
+                    if (ok) cp_async16(cur + phc * G, a.w_out + (int64_t)ids_s[lc] * E + eoff);
+                }
+            }
 
             for (int g = 0; g < NG; ++g) {
-                // ids of the negatives this lane owns (lane t = negative t - 1) in contexts 4g .. 4g + 3
-                int ids[4] = {0, 0, 0, 0};
-                if (K > 0) {
-                    const uint64_t cid = (uint64_t)(a.id_base + u);
-                    const int k = lg >= 1 ? lg - 1 : 0;
-                    const uint4 wb = neg_words(a.seed, cid, g * 4, k, STREAM_NEG);
-                    uint4 wc = make_uint4(0, 0, 0, 0);
-                    if (a.alias_prob) wc = neg_words(a.seed, cid, g * 4, k, STREAM_NEG_COIN);
-#pragma unroll
-                    for (int j = 0; j < 4; ++j)
-                        if (g * 4 + j < N && lg >= 1 && lg < T) ids[j] = neg_row(a, pick_word(wb, j), pick_word(wc, j));
-                }
+                // ids of the negatives this lane owns (lane t = negative t - 1) in contexts 4g .. 4g + 3 were resolved one group ago;
+                // resolve the next group's now (Philox + alias-table loads), off the critical path of this group's row gathers
+                int ids[4] = {nxt[0], nxt[1], nxt[2], nxt[3]};
+                if (g + 1 < NG) draw_group(u, g + 1, nxt);
+                else if (p + 1 < p0 + m) draw_group(u + 1, 0, nxt);
 #pragma unroll
                 for (int j = 0; j < 4; ++j) {
                     const int n = g * 4 + j;
@@ -176,18 +173,13 @@ sgns_win_kernel(const SgnsArgs a) {
                         int l = head + ((n < r) ? n : n + 1);                      // window offset of context n (centre skipped)
                         if (l >= RING) l -= RING;
                         const int ph = phys_s[l];
-                        const int rid0 = HOT ? ids_s[l] : 0;
                         int tid[T];
                         float row[T][4];
                         float dot[P];
 #pragma unroll
                         for (int t = 1; t < T; ++t) tid[t] = __shfl_sync(gmask, ids[j], t, G);
-                        if (!HOT || ph >= 0) {
-                            row[0][0] = row[0][1] = row[0][2] = row[0][3] = 0.f;
-                            if (ok) { const float4 c4 = cur[ph * G]; row[0][0] = c4.x; row[0][1] = c4.y; row[0][2] = c4.z; row[0][3] = c4.w; }
-                        } else {
-                            load_row(rid0, row[0]);
-                        }
+                        row[0][0] = row[0][1] = row[0][2] = row[0][3] = 0.f;
+                        if (ok) { const float4 c4 = cur[ph * G]; row[0][0] = c4.x; row[0][1] = c4.y; row[0][2] = c4.z; row[0][3] = c4.w; }
 #pragma unroll
                         for (int t = 1; t < T; ++t) load_row(tid[t], row[t]);
 #pragma unroll
@@ -215,20 +207,16 @@ sgns_win_kernel(const SgnsArgs a) {
                                 else { loss_neg += lo; cnt_fp += x <= 0.f; }
                             }
                         }
-                        {   // positive row: update the resident copy and its pending update (or the hot-row accumulator)
+                        {   // positive row: update the resident copy and its pending update
                             const float step = __shfl_sync(gmask, step_mine, 0, G);
                             const float upd[4] = {step * cen[0], step * cen[1], step * cen[2], step * cen[3]};
 #pragma unroll
                             for (int e = 0; e < 4; ++e) acc[e] = fmaf(step, row[0][e], acc[e]);
-                            if (!HOT || ph >= 0) {
-                                if (ok) {
-                                    cur[ph * G] = make_float4(row[0][0] + upd[0], row[0][1] + upd[1], row[0][2] + upd[2], row[0][3] + upd[3]);
-                                    float4 d4 = del[ph * G];
-                                    d4.x += upd[0]; d4.y += upd[1]; d4.z += upd[2]; d4.w += upd[3];
-                                    del[ph * G] = d4;
-                                }
-                            } else {
-                                push_row(rid0, upd);
+                            if (ok) {
+                                cur[ph * G] = make_float4(row[0][0] + upd[0], row[0][1] + upd[1], row[0][2] + upd[2], row[0][3] + upd[3]);
+                                float4 d4 = del[ph * G];
+                                d4.x += upd[0]; d4.y += upd[1]; d4.z += upd[2]; d4.w += upd[3];
+                                del[ph * G] = d4;
                             }
                         }
 #pragma unroll
@@ -247,30 +235,16 @@ sgns_win_kernel(const SgnsArgs a) {
             // the slot: updates never wait longer than one window length); the slot is freed when no alias is left.
             if (slide) {
                 const int ph = phys_s[head];
-                if (ph >= 0) {
-                    scatter_slot(ph, ids_s[head]);
-                    bool aliased = false;
-                    int l = head;
-                    for (int j = 0; j <= 2 * r; ++j) {                             // the window after the slide: head + 1 .. head + 2r + 1
-                        if (++l == RING) l = 0;
-                        aliased |= phys_s[l] == ph;
-                    }
-                    if (!aliased) free_mask |= 1u << ph;
+                scatter_slot(ph, ids_s[head]);
+                bool aliased = false;
+                int l = head;
+                for (int j = 0; j <= 2 * r; ++j) {                                 // the window after the slide: head + 1 .. head + 2r + 1
+                    if (++l == RING) l = 0;
+                    aliased |= phys_s[l] == ph;
                 }
+                if (!aliased) free_mask |= 1u << ph;
                 cp_async_wait_all();
                 if (++head == RING) head = 0;
-            }
-            if constexpr (HOT) {
-                // drain one hot row per group per centre, round-robin over the CTA's groups
-                if (H > 0) {
-                    const int f = (int)((drained * (unsigned)GPB + (unsigned)grp) % (unsigned)H);
-                    ++drained;
-                    if (ok) {
-                        float *hp = hot + f * HS + eoff;
-                        const float d[4] = {atomicExch(hp, 0.f), atomicExch(hp + 1, 0.f), atomicExch(hp + 2, 0.f), atomicExch(hp + 3, 0.f)};
-                        if (d[0] != 0.f || d[1] != 0.f || d[2] != 0.f || d[3] != 0.f) red_vec<4>(a.w_out + (int64_t)f * E + eoff, d, a.sys_scope);
-                    }
-                }
             }
         }
         // segment end: scatter what is still pending in the 2r + 1 resident positions (each physical slot once)
@@ -279,7 +253,7 @@ sgns_win_kernel(const SgnsArgs a) {
             int l = head;
             for (int j = 0; j <= 2 * r; ++j) {
                 const int ph = phys_s[l];
-                if (ph >= 0 && !((done >> ph) & 1u)) {
+                if (!((done >> ph) & 1u)) {
                     done |= 1u << ph;
                     scatter_slot(ph, ids_s[l]);
                 }
@@ -288,49 +262,22 @@ sgns_win_kernel(const SgnsArgs a) {
         }
     }
 
-    if constexpr (HOT) {
-        __syncthreads();                                                           // every group is done with the accumulators
-        for (int i = threadIdx.x; i < H * G; i += THREADS) {
-            const int f = i / G, eo = (i - f * G) * 4;
-            if (EXACT || eo < E) {
-                const float4 h = *reinterpret_cast<const float4 *>(hot + f * HS + eo);
-                if (h.x != 0.f || h.y != 0.f || h.z != 0.f || h.w != 0.f) {
-                    const float d[4] = {h.x, h.y, h.z, h.w};
-                    red_vec<4>(a.w_out + (int64_t)f * E + eo, d, a.sys_scope);
-                }
-            }
-        }
-    }
-
     flush_stats(a.stats, loss_pos != 0.f || loss_neg != 0.f || cnt_pairs != 0 || cnt_fp != 0 || cnt_recall != 0, loss_pos, loss_neg, cnt_recall,
                 cnt_fp, cnt_pairs, (double)cnt_pairs * (double)K);
 }
 
-inline size_t win_smem_bytes(int gpb, int g, int radius, int hot_rows) {
+inline size_t win_smem_bytes(int gpb, int g, int radius) {
     const int ring = 2 * radius + 2;
-    return (size_t)gpb * 2 * ring * g * sizeof(float4) + (size_t)gpb * 2 * ring * sizeof(int) + (size_t)hot_rows * 4 * g * sizeof(float);
+    return (size_t)gpb * 2 * ring * g * sizeof(float4) + (size_t)gpb * 2 * ring * sizeof(int);
 }
 
-template <int G, int T, bool EXACT, bool HOT>
+template <int G, int T, bool EXACT>
 int launch_win_one(const SgnsArgs &a_in, cudaStream_t stream) {
-    constexpr int THREADS = HOT ? 512 : SGNS_THREADS;       // the hot-row cache is shared by 16 warps: one block per SM
+    constexpr int THREADS = SGNS_THREADS;
     constexpr int GPB = THREADS / G;
-    auto kern = sgns_win_kernel<G, T, EXACT, HOT, THREADS>;
+    auto kern = sgns_win_kernel<G, T, EXACT, THREADS>;
     SgnsArgs a = a_in;
-    if (HOT) {
-        int dev = 0, max_smem = 0;
-        if (check_cuda(cudaGetDevice(&dev), "cudaGetDevice") != SE_OK) return SE_ERR_CUDA;
-        if (check_cuda(cudaDeviceGetAttribute(&max_smem, cudaDevAttrMaxSharedMemoryPerBlockOptin, dev), "cudaDeviceGetAttribute") != SE_OK) return SE_ERR_CUDA;
-        const int64_t room = (int64_t)max_smem - (int64_t)win_smem_bytes(GPB, G, a.radius, 0) - 1024;
-        const int64_t fit = room / (4 * G * (int64_t)sizeof(float));
-        if (fit < 1) return SE_ERR_UNSUPPORTED;              // no room for a single hot row: the caller uses the plain variant
-        if (a.hot_rows > fit) a.hot_rows = (int)fit;
-        if (a.hot_rows > WIN_HOT_MAX) a.hot_rows = WIN_HOT_MAX;
-        if ((int64_t)a.hot_rows > a.vocab) a.hot_rows = (int)a.vocab;
-    } else {
-        a.hot_rows = 0;
-    }
-    const size_t smem = win_smem_bytes(GPB, G, a.radius, a.hot_rows);
+    const size_t smem = win_smem_bytes(GPB, G, a.radius);
     if (check_cuda(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem), "cudaFuncSetAttribute") != SE_OK) return SE_ERR_CUDA;
     const int blocks = persistent_blocks(kern, smem, a.n_units, GPB, true, THREADS);
     if (blocks < 0) return SE_ERR_UNSUPPORTED;               // the ring does not fit: the caller falls back to the per-context kernel
@@ -340,17 +287,17 @@ int launch_win_one(const SgnsArgs &a_in, cudaStream_t stream) {
     return check_cuda(cudaGetLastError(), "sgns_win_kernel launch");
 }
 
-template <int G, bool EXACT, bool HOT>
+template <int G, bool EXACT>
 int launch_win_t(const SgnsArgs &a, cudaStream_t stream) {
     switch (1 + a.n_neg) {
-        case 1: return launch_win_one<G, 1, EXACT, HOT>(a, stream);
-        case 2: return launch_win_one<G, 2, EXACT, HOT>(a, stream);
-        case 3: return launch_win_one<G, 3, EXACT, HOT>(a, stream);
-        case 4: return launch_win_one<G, 4, EXACT, HOT>(a, stream);
-        case 5: return launch_win_one<G, 5, EXACT, HOT>(a, stream);
-        case 6: return launch_win_one<G, 6, EXACT, HOT>(a, stream);
-        case 7: return launch_win_one<G, 7, EXACT, HOT>(a, stream);
-        case 8: return launch_win_one<G, 8, EXACT, HOT>(a, stream);
+        case 1: return launch_win_one<G, 1, EXACT>(a, stream);
+        case 2: return launch_win_one<G, 2, EXACT>(a, stream);
+        case 3: return launch_win_one<G, 3, EXACT>(a, stream);
+        case 4: return launch_win_one<G, 4, EXACT>(a, stream);
+        case 5: return launch_win_one<G, 5, EXACT>(a, stream);
+        case 6: return launch_win_one<G, 6, EXACT>(a, stream);
+        case 7: return launch_win_one<G, 7, EXACT>(a, stream);
+        case 8: return launch_win_one<G, 8, EXACT>(a, stream);
         default: return SE_ERR_UNSUPPORTED;
     }
 }

@@ -2,5 +2,5 @@
 #include "sgns_win.cuh"
 
 namespace se {
-int launch_win_g8(const SgnsArgs &a, cudaStream_t stream) { return launch_win_t<8, false, false>(a, stream); }
+int launch_win_g8(const SgnsArgs &a, cudaStream_t stream) { return launch_win_t<8, false>(a, stream); }
 }  // namespace se

@@ -25,13 +25,7 @@ SCATTER_STORE = 1
 GENERIC_KERNEL = 2
 NO_WINDOW = 4
 WHOLE_SEQUENCES = 8
-
-
-def hot_rows_flag(n: int) -> int:
-    """SE_SGNS_HOT_ROWS(n): rows [0, n) of W_out are combined per CTA in shared memory (window kernel)."""
-    return (int(n) << 8) & 0x00ffff00
-
-
+WINDOW_REFRESH = 16
 STATS_LEN = 6
 WALK_AUTO, WALK_WARP, WALK_THREAD = 0, 1, 2
 EDGE_OPS = {'average': 0, 'hadamard': 1, 'weighted_l1': 2, 'weighted_l2': 3}

@@ -51,14 +51,9 @@ extern "C" {
 #define SE_SGNS_WHOLE_SEQUENCES 8 /* bit flag (se_sgns_update_walks*): the window kernel gives every lane group whole sequences
                                      (a group's span is rounded up to a multiple of L - 2r centres), so all pairs of a sequence are
                                      applied in order by one group.  Always on when there are at least as many sequences as groups */
-/* se_sgns_update_walks*: rows [0, n) of W_out (the most frequent tokens of a frequency-sorted vocabulary, torchtext order,
- * word2vec/dataloader/torch_dataset.py:104-110) are combined per CTA in shared memory instead of updated with one global
- * reduction per pair: removes the per-address serialisation of hot rows under unigram^0.75 negatives.  n is clamped to what fits
- * in shared memory beside the window ring (n <= 4096); 0 = off.  Window kernel only (32 < emb <= 128). */
-#define SE_SGNS_HOT_ROWS_SHIFT 8
-#define SE_SGNS_HOT_ROWS_MASK 0x00ffff00
-#define SE_SGNS_HOT_ROWS(n) (((n) << SE_SGNS_HOT_ROWS_SHIFT) & SE_SGNS_HOT_ROWS_MASK)
-
+#define SE_SGNS_WINDOW_REFRESH 16 /* bit flag (se_sgns_update_walks*): the window kernel scatters and re-fetches a token's resident
+                                     W_out row when the token is the centre (it is not a context then), so a resident copy is at most r
+                                     centres old instead of 2r: for token streams whose frequent tokens sit in many windows at once */
 /* stats layout written by the SGNS kernels (double[SE_STATS_LEN], ACCUMULATED into, caller zeroes):
  *   [0] sum over pairs of positive loss   -log clamp(sigmoid(s+), 1e-6)          (word2vec/loss.py:15)
  *   [1] sum over pairs of negative loss   -sum_k log clamp(sigmoid(-s-), 1e-6)   (word2vec/loss.py:16)

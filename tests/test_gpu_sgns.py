@@ -453,7 +453,9 @@ def test_window_kernel_with_repeated_tokens_equals_the_sequential_oracle(emb, ra
     want_in, want_out, loss = sgns_oracle.sequential_window_sgd(w_in[rows], w_out[rows], rm(tokens.astype(np.int64) + offset), radius, 0,
                                                                 rm(neg) if k else None, lr)
     t_in, t_out = _t(w_in, dev), _t(w_out, dev)
-    st = nat.sgns_update_walks(t_in, t_out, _t(tokens, dev), radius, k, offset, lr, seed, centre_id_base=50, flags=nat.WHOLE_SEQUENCES)
+    # (the mid-life refresh of resident rows must not change the arithmetic: a scatter followed by a re-fetch of the same row)
+    st = nat.sgns_update_walks(t_in, t_out, _t(tokens, dev), radius, k, offset, lr, seed, centre_id_base=50,
+                               flags=nat.WHOLE_SEQUENCES | (nat.WINDOW_REFRESH if radius != 2 else 0))
     assert st['pairs'] == n_seq * n_cen * 2 * radius
     got_in, got_out = t_in.cpu().numpy(), t_out.cpu().numpy()
     assert np.abs(want_out - w_out[rows]).max() > 5e-3
@@ -464,35 +466,34 @@ def test_window_kernel_with_repeated_tokens_equals_the_sequential_oracle(emb, ra
     assert np.array_equal(got_in[untouched], w_in[untouched]) and np.array_equal(got_out[untouched], w_out[untouched])
 
 
-@pytest.mark.parametrize('emb,hot', [(128, 8), (128, 40), (48, 16), (64, 300)])
-def test_window_kernel_zipf_sentence_with_hot_row_cache_equals_the_sequential_oracle(emb, hot):
-    """A Zipf-distributed sentence over a tiny frequency-sorted vocabulary (token id = frequency rank: the text path's
-    ordering): the most frequent rows go through the per-CTA hot-row accumulators (SE_SGNS_HOT_ROWS), the rest through the
-    window ring; ONE sequence, so one lane group applies every pair in order and the result must equal the sequential
-    oracle.  K = 0 here (negatives over 60 rows would collide with the window by construction; the alias-negative path of the
-    hot cache is covered statistically in test_hot_row_cache_matches_plain_kernel_to_second_order)."""
+@pytest.mark.parametrize('emb', [128, 48, 64])
+def test_window_kernel_zipf_sentence_equals_the_sequential_oracle(emb):
+    """A Zipf-distributed sentence over a tiny vocabulary: most windows hold the same token several times.  ONE sequence, so one
+    lane group applies every pair in order (with and without the mid-life refresh) and the result must equal the sequential
+    oracle.  K = 0 (negatives over 60 rows would collide with the window by construction)."""
     dev = cuda_device()
-    rng = np.random.default_rng(7 + emb + hot)
+    rng = np.random.default_rng(7 + emb)
     vocab, radius, length, offset, lr = 60, 3, 90, 1, 0.05
     p = 1.0 / np.arange(1, vocab)
     tokens = rng.choice(vocab - 1, size=(1, length), p=p / p.sum()).astype(np.int32)
     w_in = (rng.standard_normal((vocab, emb)) * 0.3).astype(np.float32)
     w_out = (rng.standard_normal((vocab, emb)) * 0.3).astype(np.float32)
     want_in, want_out, loss = sgns_oracle.sequential_window_sgd(w_in, w_out, tokens, radius, offset, None, lr)
-    t_in, t_out = _t(w_in, dev), _t(w_out, dev)
-    st = nat.sgns_update_walks(t_in, t_out, _t(tokens, dev), radius, 0, offset, lr, 3, flags=nat.WHOLE_SEQUENCES | nat.hot_rows_flag(hot))
-    np.testing.assert_allclose(t_out.cpu().numpy(), want_out, rtol=0, atol=3e-5)
-    np.testing.assert_allclose(t_in.cpu().numpy(), want_in, rtol=0, atol=3e-5)
-    assert abs(st['loss'] * st['pairs'] - loss) < 1e-4 * loss
+    for flags in (nat.WHOLE_SEQUENCES, nat.WHOLE_SEQUENCES | nat.WINDOW_REFRESH):
+        t_in, t_out = _t(w_in, dev), _t(w_out, dev)
+        st = nat.sgns_update_walks(t_in, t_out, _t(tokens, dev), radius, 0, offset, lr, 3, flags=flags)
+        np.testing.assert_allclose(t_out.cpu().numpy(), want_out, rtol=0, atol=3e-5)
+        np.testing.assert_allclose(t_in.cpu().numpy(), want_in, rtol=0, atol=3e-5)
+        assert abs(st['loss'] * st['pairs'] - loss) < 1e-4 * loss
 
 
-def test_hot_row_cache_many_groups_alias_negatives_match_first_order_oracle():
+def test_many_groups_alias_negatives_match_first_order_oracle():
     """Many sequences on many lane groups, unigram^0.75 alias negatives concentrated on the first rows.  With a tiny lr every
     row moves by -lr * (sum of the pairs' gradients at the initial weights), which the dense-gradient oracle gives exactly
-    (negatives predicted by the numpy Philox + alias restatement).  The hot-row variant must match it to 3 % of the largest
-    movement.  The plain variants are held to 30 %: they add ~1e-7 increments straight into weights of ~0.2 with
-    red.global.add.f32 (a few ulps each), which accumulates a visible rounding bias on the hottest row -- combining in
-    shared memory first is also the more accurate sum."""
+    (negatives predicted by the numpy Philox + alias restatement).  Tolerance 30 % of the largest movement: at this lr the
+    kernels add ~1e-7 increments straight into weights of ~0.2 with red.global.add.f32 (a few ulps each), which accumulates a
+    visible rounding bias on the hottest row (measured 16-26 %; rows with fewer updates agree to ~1 %); at a working lr the
+    increments are four orders of magnitude above an ulp."""
     dev = cuda_device()
     rng = np.random.default_rng(3)
     vocab, emb, radius, k, offset, n_seq, length, lr, seed = 5000, 128, 5, 5, 1, 1024, 32, 1e-6, 11
@@ -510,7 +511,7 @@ def test_hot_row_cache_many_groups_alias_negatives_match_first_order_oracle():
     scale = lr * inputs.shape[0] * 2 * radius
     want_out, want_in = -scale * o['grad_out'], -scale * o['grad_in']
     moved = max(np.abs(want_out).max(), np.abs(want_in).max())
-    for flags, tol in ((nat.hot_rows_flag(48), 0.03), (nat.SCATTER_RED, 0.3), (nat.NO_WINDOW, 0.3)):
+    for flags, tol in ((nat.SCATTER_RED, 0.3), (nat.WINDOW_REFRESH, 0.3), (nat.NO_WINDOW, 0.3)):
         t_in, t_out = _t(w_in, dev), _t(w_out, dev)
         st = nat.sgns_update_walks(t_in, t_out, _t(tokens, dev), radius, k, offset, lr, seed, alias=alias, flags=flags)
         err = max(np.abs(t_out.cpu().numpy().astype(np.float64) - w_out - want_out).max(),
