@@ -140,6 +140,7 @@ sgns_kernel(const SgnsArgs a) {
                                 for (int e = 0; e < VEC; ++e) { acc[j][e] = fmaf(gs, row[c][j][e], acc[j][e]); d[e] = gs * cen[j][e]; }
                                 if (a.grad_out && ok[j]) red_vec<VEC>(a.grad_out + (int64_t)tid[c] * E + eoff[j], d);
                             }
+                            if (a.touch_out && lg == 0) mark_row(a.touch_out, a.list_out, a.touch_counts + 1, tid[c]);
                         } else {
                             const float step = -a.lr * g;
                             float *rp = a.w_out + (int64_t)tid[c] * E;
@@ -172,6 +173,7 @@ sgns_kernel(const SgnsArgs a) {
             if (!ok[j]) continue;
             if constexpr (MODE == MODE_GRAD) {
                 if (a.grad_in) red_vec<VEC>(a.grad_in + crow * E + eoff[j], acc[j]);
+                if (j == 0 && a.touch_in && lg == 0) mark_row(a.touch_in, a.list_in, a.touch_counts, crow);
             } else {
                 float *cp = a.w_in + crow * E + eoff[j];
                 if (a.scatter_store) {
@@ -934,6 +936,38 @@ extern "C" int se_sgns_grad(const float *w_in, const float *w_out, int64_t vocab
     a.grad_scale = batch > 0 ? 1.0f / (float)(batch * n_ctx) : 0.f;
     a.neg_vocab = (uint32_t)vocab; a.neg_shift = -1; a.neg_world = 1;
     return se::launch<se::MODE_GRAD>(a, (cudaStream_t)stream);
+}
+
+extern "C" int se_sgns_adam_step(float *w_in, float *w_out, int64_t vocab, int emb, const int64_t *inputs, const int64_t *targets,
+                                 const int64_t *noise, int64_t batch, int n_ctx, int n_neg, const se_adam_state *st, float lr,
+                                 float beta1, float beta2, float eps, double *stats, void *stream) {
+    int rc = se::common_checks("se_sgns_adam_step", w_in, w_out, vocab, emb, n_neg);
+    if (rc != SE_OK) return rc;
+    SE_REQUIRE(batch >= 0 && n_ctx >= 1, "se_sgns_adam_step: bad batch shape");
+    if (batch == 0) return SE_OK;
+    SE_REQUIRE(inputs && targets && (noise || n_neg == 0), "se_sgns_adam_step: null index tensor");
+    SE_REQUIRE(st && st->m_in && st->v_in && st->m_out && st->v_out && st->g_in && st->g_out && st->t_in && st->t_out && st->touched_in &&
+               st->touched_out && st->list_in && st->list_out && st->counts, "se_sgns_adam_step: incomplete optimiser state");
+    const int64_t need_in = batch < vocab ? batch : vocab;
+    const int64_t tgt = batch * n_ctx * (int64_t)(1 + n_neg);
+    const int64_t need_out = tgt < vocab ? tgt : vocab;
+    SE_REQUIRE(st->list_in_capacity >= need_in && st->list_out_capacity >= need_out,
+               "se_sgns_adam_step: row lists too small (need %lld / %lld entries)", (long long)need_in, (long long)need_out);
+    SE_REQUIRE(beta1 >= 0.f && beta1 < 1.f && beta2 >= 0.f && beta2 < 1.f && eps >= 0.f, "se_sgns_adam_step: bad hyper-parameters");
+    se::SgnsArgs a{};
+    a.w_in = w_in; a.w_out = w_out; a.grad_in = st->g_in; a.grad_out = st->g_out;
+    a.inputs = inputs; a.targets = targets; a.noise = noise;
+    a.stats = stats; a.n_units = batch; a.vocab = vocab; a.emb = emb; a.n_ctx = n_ctx; a.n_neg = n_neg;
+    a.grad_scale = 1.0f / (float)(batch * n_ctx);                                   // the reference's MEAN loss (loss.py:19)
+    a.neg_vocab = (uint32_t)vocab; a.neg_shift = -1; a.neg_world = 1;
+    a.touch_in = st->touched_in; a.touch_out = st->touched_out; a.list_in = st->list_in; a.list_out = st->list_out; a.touch_counts = st->counts;
+    rc = se::launch<se::MODE_GRAD>(a, (cudaStream_t)stream);
+    if (rc != SE_OK) return rc;
+    rc = se::adam_apply(w_in, st->m_in, st->v_in, st->g_in, st->t_in, st->touched_in, st->list_in, st->counts, st->counts + 2, need_in, emb, lr,
+                        beta1, beta2, eps, (cudaStream_t)stream);
+    if (rc != SE_OK) return rc;
+    return se::adam_apply(w_out, st->m_out, st->v_out, st->g_out, st->t_out, st->touched_out, st->list_out, st->counts + 1, st->counts + 3, need_out,
+                          emb, lr, beta1, beta2, eps, (cudaStream_t)stream);
 }
 
 extern "C" int se_sgns_step(float *w_in, float *w_out, int64_t vocab, int emb, const int64_t *inputs,

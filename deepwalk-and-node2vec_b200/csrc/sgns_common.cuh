@@ -31,11 +31,15 @@ struct SgnsArgs {
     int whole_seq;                       // window kernel: a group's span is rounded up to whole sequences (SE_SGNS_WHOLE_SEQUENCES)
     int64_t n_seq;                       // MODE_WALK: number of sequences
     int win_refresh;                     // window kernel: re-fetch a resident row when its token is the centre (SE_SGNS_WINDOW_REFRESH)
-    // row-sparse Adam (se_sgns_adam_step): first / second moments and per-row step counts of both tables
-    float *m_in, *v_in, *m_out, *v_out;
-    int32_t *t_in, *t_out;
-    float beta1, beta2, eps;
+    // MODE_GRAD, row-sparse optimisers (se_sgns_adam_step): rows that receive a gradient are flagged and appended to a list
+    int32_t *touch_in, *touch_out;       // [vocab] flags, zero between steps (may be null)
+    int32_t *list_in, *list_out;         // touched rows
+    int32_t *touch_counts;               // [0] = entries of list_in, [1] = entries of list_out
 };
+
+// row-sparse Adam apply (adam.cu): one warp per listed row; restores g = 0, flag = 0 and the list length
+int adam_apply(float *w, float *m, float *v, float *g, int32_t *t, int32_t *flags, const int32_t *list, int32_t *count, int32_t *done,
+               int64_t capacity, int emb, float lr, float beta1, float beta2, float eps, cudaStream_t stream);
 
 // window-resident kernel family (sgns_win.cuh), one translation unit per lane-group width so they compile in parallel;
 // each returns SE_ERR_UNSUPPORTED when the shape is not covered
@@ -105,6 +109,11 @@ __device__ __forceinline__ int neg_row(const SgnsArgs &a, uint32_t r0, uint32_t 
         j = ((s * (uint32_t)a.neg_world + (uint32_t)a.neg_rank) << a.neg_shift) | (j & ((1u << a.neg_shift) - 1u));
     }
     return (int)j;
+}
+
+// first toucher of a row appends it to the list (flags are zero between steps)
+__device__ __forceinline__ void mark_row(int32_t *flags, int32_t *list, int32_t *count, int64_t row) {
+    if (flags[row] == 0 && atomicExch(flags + row, 1) == 0) list[atomicAdd(count, 1)] = (int32_t)row;
 }
 
 template <bool FAST> __device__ __forceinline__ float sigmoidf_(float x) {

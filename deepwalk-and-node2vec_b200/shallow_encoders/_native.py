@@ -51,6 +51,7 @@ _SIGNATURES = {
     'se_skipgram_scores_backward': (c_int, [c_p, c_p, c_i64, c_int, c_p, c_p, c_i64, c_int, c_p, c_p, c_p, c_p]),
     'se_ns_loss': (c_int, [c_p, c_p, c_i64, c_int, c_int, c_p, c_p, c_p, c_p]),
     'se_sgns_grad': (c_int, [c_p, c_p, c_i64, c_int, c_p, c_p, c_p, c_i64, c_int, c_int, c_p, c_p, c_p, c_p]),
+    'se_sgns_adam_step': (c_int, [c_p, c_p, c_i64, c_int, c_p, c_p, c_p, c_i64, c_int, c_int, c_p, c_f32, c_f32, c_f32, c_f32, c_p, c_p]),
     'se_sgns_step': (c_int, [c_p, c_p, c_i64, c_int, c_p, c_p, c_p, c_i64, c_int, c_int, c_p, c_p, c_f32, c_u64, c_i64,
                              c_int, c_p, c_p]),
     'se_sgns_update_walks': (c_int, [c_p, c_p, c_i64, c_int, c_p, c_i64, c_int, c_int, c_int, c_int, c_p, c_p, c_f32,
@@ -92,6 +93,13 @@ _SIGNATURES = {
 class ShardSpec(ctypes.Structure):
     """struct se_shard_spec (include/se_b200.h)."""
     _fields_ = [('world', c_i32), ('rank', c_i32), ('stripe_rows', c_i64), ('local_negatives', c_i32), ('reserved', c_i32)]
+
+
+class AdamStateC(ctypes.Structure):
+    """struct se_adam_state (include/se_b200.h)."""
+    _fields_ = [('m_in', c_p), ('v_in', c_p), ('m_out', c_p), ('v_out', c_p), ('g_in', c_p), ('g_out', c_p), ('t_in', c_p), ('t_out', c_p),
+                ('touched_in', c_p), ('touched_out', c_p), ('list_in', c_p), ('list_out', c_p), ('list_in_capacity', c_i64),
+                ('list_out_capacity', c_i64), ('counts', c_p)]
 
 
 def header_symbols():
@@ -336,6 +344,57 @@ def sgns_grad(w_in: torch.Tensor, w_out: torch.Tensor, inputs: torch.Tensor, tar
     out = _stats_dict(stats) if own_stats else {}
     out['grad_in'], out['grad_out'] = g_in, g_out
     return out
+
+
+class AdamState:
+    """Device state of the row-sparse Adam (se_adam_state): moments, gradient accumulators, per-row step counts, touched-row
+    flags and lists.  Everything is zero-initialised; the row lists grow with the largest batch seen."""
+
+    def __init__(self, vocab: int, emb: int, device):
+        z = lambda *shape, dtype=torch.float32: torch.zeros(shape, dtype=dtype, device=device)   # noqa: E731
+        self.vocab, self.emb, self.device = int(vocab), int(emb), device
+        self.m_in, self.v_in, self.m_out, self.v_out = z(vocab, emb), z(vocab, emb), z(vocab, emb), z(vocab, emb)
+        self.g_in, self.g_out = z(vocab, emb), z(vocab, emb)
+        self.t_in, self.t_out = z(vocab, dtype=torch.int32), z(vocab, dtype=torch.int32)
+        self.touched_in, self.touched_out = z(vocab, dtype=torch.int32), z(vocab, dtype=torch.int32)
+        self.counts = z(4, dtype=torch.int32)
+        self.list_in = self.list_out = None
+
+    def ensure(self, batch: int, n_ctx: int, n_neg: int) -> None:
+        need_in, need_out = min(self.vocab, batch), min(self.vocab, batch * n_ctx * (1 + n_neg))
+        if self.list_in is None or self.list_in.numel() < need_in:
+            self.list_in = torch.zeros(need_in, dtype=torch.int32, device=self.device)
+        if self.list_out is None or self.list_out.numel() < need_out:
+            self.list_out = torch.zeros(need_out, dtype=torch.int32, device=self.device)
+
+    def c_struct(self) -> AdamStateC:
+        p = lambda t: t.data_ptr()   # noqa: E731
+        return AdamStateC(p(self.m_in), p(self.v_in), p(self.m_out), p(self.v_out), p(self.g_in), p(self.g_out), p(self.t_in), p(self.t_out),
+                          p(self.touched_in), p(self.touched_out), p(self.list_in), p(self.list_out), self.list_in.numel(),
+                          self.list_out.numel(), p(self.counts))
+
+
+def sgns_adam_step(w_in: torch.Tensor, w_out: torch.Tensor, inputs: torch.Tensor, targets: torch.Tensor, noise: Optional[torch.Tensor],
+                   state: AdamState, lr: float, beta1: float = 0.9, beta2: float = 0.999, eps: float = 1e-8,
+                   stats: Optional[torch.Tensor] = None) -> Optional[Dict[str, float]]:
+    """Row-sparse Adam on an explicit (inputs (B,1), targets (B,N), noise (B,N,K)) batch: gradient of the mean loss + update of the
+    touched rows of both tables, three launches."""
+    global _launches
+    batch, n_ctx = targets.shape
+    n_neg = noise.shape[2] if noise is not None and noise.dim() == 3 else 0
+    state.ensure(batch, n_ctx, n_neg)
+    own_stats = stats is None
+    if own_stats:
+        stats = torch.zeros(STATS_LEN, dtype=torch.float64, device=w_in.device)
+    cs = state.c_struct()
+    with _on(w_in):
+        _check(load().se_sgns_adam_step(
+            _ptr(w_in, torch.float32, 'w_in'), _ptr(w_out, torch.float32, 'w_out'), w_in.shape[0], w_in.shape[1],
+            _ptr(inputs.reshape(-1), torch.int64, 'inputs'), _ptr(targets, torch.int64, 'targets'),
+            _ptr(noise, torch.int64, 'noise') if n_neg else None, batch, n_ctx, n_neg, ctypes.byref(cs), float(lr), float(beta1),
+            float(beta2), float(eps), stats.data_ptr(), _stream()))
+    _launches += 3
+    return _stats_dict(stats) if own_stats else None
 
 
 def sgns_step(w_in: torch.Tensor, w_out: torch.Tensor, inputs: torch.Tensor, targets: torch.Tensor,

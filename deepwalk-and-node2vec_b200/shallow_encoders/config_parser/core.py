@@ -43,12 +43,33 @@ class TrainConfig:
     max_epochs: int
     accelerator: str = 'gpu'
     devices: str = '1'
-    engine: str = 'reference'          # 'reference': autograd + YAML optimizer; 'fused': in-place SGD kernel
-    fused_lr: float = 0.025
+    engine: str = 'reference'          # 'reference': autograd + YAML optimizer (dense); 'fused': device-resident engine (below)
+    # fused engine: the YAML optimizer decides the kernel -- torch.optim.Adam -> row-sparse Adam (se_sgns_adam_step), torch.optim.SGD ->
+    # in-place SGD kernel with the YAML's lr on the mean loss.  An explicit fused_lr forces the in-place SGD kernel with that
+    # mean-loss learning rate (a launch over P pairs applies fused_lr / P per pair) whatever the optimizer block says.
+    fused_lr: Optional[float] = None
     local_negatives: bool = False      # multi-GPU fused engine: draw negatives among the rows the GPU owns
     multi_gpu_negatives: str = 'global'   # multi-GPU fused engine: global | local | owner (reference draw, owner-computes negatives)
 
+    def fused_optimizer_kind(self) -> str:
+        """'sgd' or 'adam': which kernel the fused engine runs for this config."""
+        if self.fused_lr is not None:
+            return 'sgd'
+        target = str(self.optimizer.get('_target_', '')).rsplit('.', 1)[-1].lower()
+        if target == 'adam':
+            return 'adam'
+        if target == 'sgd':
+            return 'sgd'
+        raise ValueError(f'train.engine=fused supports torch.optim.Adam (row-sparse Adam kernel) and torch.optim.SGD (in-place SGD kernel); '
+                         f'got {self.optimizer.get("_target_")!r}.  Set train.fused_lr to force the SGD kernel, or use train.engine=reference.')
+
+    def fused_sgd_lr(self) -> float:
+        return float(self.fused_lr) if self.fused_lr is not None else float(self.optimizer.get('lr', 0.01))
+
     def instantiate_optimizer(self, params):
+        if self.engine == 'fused' and self.fused_optimizer_kind() == 'adam':
+            from shallow_encoders.word2vec.optim import RowSparseAdam
+            return RowSparseAdam.from_torch_config(params, self.optimizer)
         return instantiate(self.optimizer, params=params)
 
     def instantiate_scheduler(self, optimizer):

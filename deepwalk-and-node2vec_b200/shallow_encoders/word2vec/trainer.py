@@ -152,6 +152,24 @@ class Word2VecTrainer(nn.Module):
                                      centre_id_base=launch * tokens.shape[0] * max(n_cen, 1), alias=alias, flags=flags, stats=stats,
                                      local_negatives=local_negatives, check_tokens=check_tokens)
 
+    def fused_adam_step(self, tokens: torch.Tensor, context_radius: int, row_offset: int = 1, seed: int = 0,
+                        stats: Optional[torch.Tensor] = None) -> Optional[Dict[str, float]]:
+        """One mini-batch of the reference's loop with the YAML's Adam, on the device end to end: windows of the int32 token
+        sequences [n_seq, L] (torch_dataset.py:300-309) -> uniform noise (sampling.py:21) -> `se_sgns_adam_step` (mean-loss
+        gradient + row-sparse Adam).  The optimizer must be a RowSparseAdam (its lr follows the YAML's scheduler)."""
+        from shallow_encoders.word2vec.optim import RowSparseAdam
+        assert isinstance(self._optimizer, RowSparseAdam), 'fused_adam_step needs the RowSparseAdam optimizer'
+        w_in, w_out = self._model._input_embedding.weight.data, self._model._output_embedding.weight.data
+        r = context_radius
+        rows = tokens.to(torch.int64) + row_offset
+        win = rows.unfold(1, 2 * r + 1, 1)                                        # (n_seq, L - 2r, 2r + 1): one window per centre
+        inputs = win[:, :, r].reshape(-1, 1).contiguous()
+        targets = torch.cat([win[:, :, :r], win[:, :, r + 1:]], dim=2).reshape(-1, 2 * r).contiguous()
+        launch = next(self._fused_launch)
+        noise = generate_noise_batch(targets.shape[0], 2 * r, self._neg_samples, self._vocab_size, device=w_in.device,
+                                     seed=seed * 0x9E3779B1 + launch)
+        return self._optimizer.step_batch(w_in, w_out, inputs, targets, noise, stats=stats)
+
     # -- checkpoints (state-dict keys `_model._input_embedding.weight`, `_model._output_embedding.weight`) ---------------
     def save_checkpoint(self, path: str) -> None:
         torch.save({'state_dict': {k: v.detach().cpu() for k, v in self.state_dict().items()},

@@ -13,8 +13,11 @@ Checkpoints hold {'state_dict': {'_model._input_embedding.weight', '_model._outp
 Engines (`train.engine`):
     reference   Lightning's loop restated: DataLoader batches of `batch_size` walks -> collate -> training_step ->
                 backward -> YAML optimizer -> per-epoch scheduler.  Same arithmetic as the reference, kernels on the B200.
-    fused       per epoch: one walk-kernel launch + one fused window/negatives/SGNS launch per `batch_size` walks,
-                in-place SGD with lr = train.fused_lr / (pairs per launch) decayed by the YAML's StepLR schedule.
+    fused       per epoch ONE walk-kernel launch, then per `batch_size` walks (the reference's mini-batch), all on the device:
+                `_target_: torch.optim.Adam` (every shipped YAML) -> windows + noise + `se_sgns_adam_step` (mean-loss gradient and
+                row-sparse Adam with the YAML's lr / betas / eps; lr stepped by the YAML's scheduler);
+                `_target_: torch.optim.SGD` or an explicit train.fused_lr -> one fused window/negatives/in-place-SGD launch with
+                lr / (pairs per launch) per pair, decayed by the YAML's StepLR schedule.
 An existing experiment directory is replaced without the reference's interactive prompt (train.py:36-42) unless --keep.
 
 Several GPUs (not in the reference, whose YAMLs all say `devices: '1'`): launch under torchrun, one process per GPU,
@@ -121,9 +124,16 @@ def fit_fused(cfg, dataset, trainer, end_of_epoch, rank: int = 0, world: int = 1
     step_size, gamma = int(sched.get('step_size', 10 ** 9)), float(sched.get('gamma', 1.0))
     from shallow_encoders import _native as nat
     stats = torch.zeros(nat.STATS_LEN, dtype=torch.float64, device='cuda')
+    kind = cfg.train.fused_optimizer_kind()
+    if kind == 'adam':
+        if world > 1:
+            raise ValueError('the row-sparse Adam engine is single-GPU; multi-GPU runs use the in-place SGD kernels (set train.fused_lr)')
+        return fit_fused_adam(cfg, dataset, trainer, end_of_epoch, stats)
+    base_lr = cfg.train.fused_sgd_lr()
+    n_walks_global = len(dataset)
     for epoch in range(cfg.train.max_epochs):
         trainer.current_epoch = epoch
-        lr_batch = cfg.train.fused_lr * gamma ** (epoch // step_size)
+        lr_batch = base_lr * gamma ** (epoch // step_size)
         tokens = dataset.epoch_tokens(rank=rank, world=world)[:, :cfg.datamodule.max_length]
         stats.zero_()
         share = -(-cfg.datamodule.batch_size // world)             # this rank's walks of one global batch
@@ -139,8 +149,12 @@ def fit_fused(cfg, dataset, trainer, end_of_epoch, rank: int = 0, world: int = 1
                                                                  # a ragged last batch falls back to fetching the rows
                 from shallow_encoders.word2vec.sharded import sgns_update_walks_owner_computes
                 w_in, w_out = trainer.model.tables
+                # Philox id of centre 0 of rank 0's walks in this step: a function of (epoch, lo) only, so every rank derives the same base
+                # whatever its own iteration count is
+                steps_per_epoch = -(-n_walks_global // (share * world))
+                cid_base = (epoch * steps_per_epoch + lo // share) * world * share * n_cen
                 sgns_update_walks_owner_computes(w_in, w_out, chunk, r, cfg.train.loss.negative_samples, dataset.row_offset, lr_batch / pairs,
-                                                 seed, trainer.global_step * world * share * n_cen, rank, world, stats=stats)
+                                                 seed, cid_base, rank, world, stats=stats)
             else:
                 trainer.fused_step(chunk, r, lr_batch / pairs, row_offset=dataset.row_offset, seed=seed * world + rank, stats=stats,
                                    local_negatives=mode == 'local')
@@ -152,6 +166,32 @@ def fit_fused(cfg, dataset, trainer, end_of_epoch, rank: int = 0, world: int = 1
         means = {'train-epoch/loss': (s[0] + s[1]) / p, 'train-epoch/positive-loss': s[0] / p,
                  'train-epoch/negative-loss': s[1] / p, 'train-metrics/recall': s[2] / p,
                  'train-metrics/precision': 1 - s[3] / max(s[5], 1.0), 'epoch/lr': lr_batch}
+        for name, value in means.items():
+            trainer.log(name, value)
+        end_of_epoch(trainer, epoch, means)
+
+
+def fit_fused_adam(cfg, dataset, trainer, end_of_epoch, stats):
+    """The reference's loop (tools/train.py:67-83: per batch training_step -> backward -> Adam.step; scheduler.step per epoch) with every
+    stage on the device: walks of the epoch from one kernel launch, then per `batch_size` walks one `fused_adam_step`."""
+    r = cfg.datamodule.context_radius
+    scheduler = trainer.scheduler['scheduler'] if isinstance(trainer.scheduler, dict) else trainer.scheduler
+    bs = cfg.datamodule.batch_size
+    for epoch in range(cfg.train.max_epochs):
+        trainer.current_epoch = epoch
+        tokens = dataset.epoch_tokens()[:, :cfg.datamodule.max_length]
+        stats.zero_()
+        for lo in range(0, tokens.shape[0], bs):
+            trainer.fused_adam_step(tokens[lo:lo + bs], r, row_offset=dataset.row_offset, seed=epoch, stats=stats)
+            trainer.global_step += 1
+        lr = trainer.optimizer.param_groups[0]['lr']
+        if scheduler is not None:
+            scheduler.step()
+        s = stats.tolist()
+        p = max(s[4], 1.0)
+        means = {'train-epoch/loss': (s[0] + s[1]) / p, 'train-epoch/positive-loss': s[0] / p,
+                 'train-epoch/negative-loss': s[1] / p, 'train-metrics/recall': s[2] / p,
+                 'train-metrics/precision': 1 - s[3] / max(s[5], 1.0), 'epoch/lr': lr}
         for name, value in means.items():
             trainer.log(name, value)
         end_of_epoch(trainer, epoch, means)

@@ -148,6 +148,27 @@ int se_sgns_grad(const float *w_in, const float *w_out, int64_t vocab, int emb, 
                  const int64_t *targets, const int64_t *noise, int64_t batch, int n_ctx, int n_neg,
                  double *stats, float *grad_in, float *grad_out, void *stream);
 
+/* Row-sparse Adam step on an explicit batch -- what `loss['loss'].backward(); optimizer.step()` does in the reference when the YAML
+ * names `_target_: torch.optim.Adam` (configs/sge_sg_karate_club.yaml:32-34, config_parser/core.py:43-94), restricted to the rows
+ * the batch touches: gradient of the MEAN loss (word2vec/loss.py:19) accumulated per row, then m, v, theta updated with torch's
+ * formulas and bias correction by the row's own step count.  Equals dense torch.optim.Adam whenever every step touches the same
+ * rows (and on the first step); untouched rows keep their value.  All state is caller-owned device memory:
+ *   m_*, v_*, g_* fp32 [vocab x emb] (zero-initialised; g_* is zero again when the call returns), t_* int32 [vocab] step counts,
+ *   touched_* int32 [vocab] flags (zero between calls), list_in / list_out int32 row lists with at least min(vocab, batch) /
+ *   min(vocab, batch * n_ctx * (1 + n_neg)) entries, counts int32[4] (zero-initialised).  stats as se_sgns_grad. */
+typedef struct se_adam_state {
+    float *m_in, *v_in, *m_out, *v_out;
+    float *g_in, *g_out;
+    int32_t *t_in, *t_out;
+    int32_t *touched_in, *touched_out;
+    int32_t *list_in, *list_out;
+    int64_t list_in_capacity, list_out_capacity;
+    int32_t *counts;
+} se_adam_state;
+int se_sgns_adam_step(float *w_in, float *w_out, int64_t vocab, int emb, const int64_t *inputs, const int64_t *targets,
+                      const int64_t *noise, int64_t batch, int n_ctx, int n_neg, const se_adam_state *state, float lr, float beta1,
+                      float beta2, float eps, double *stats, void *stream);
+
 /* Fused in-place SGD on an explicit batch: every row touched by pair (b, n) moves by -lr * dL_pair/drow where
  * L_pair is the un-averaged per-pair loss (pass lr = lr_ref / (batch * n_ctx) for the reference's mean loss).
  * noise NULL -> K negatives per pair drawn in-kernel (alias or uniform), keyed (seed; pair_id_base + b, n, k). */

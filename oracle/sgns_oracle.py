@@ -143,3 +143,21 @@ def sequential_window_sgd(w_in: np.ndarray, w_out: np.ndarray, tokens: np.ndarra
             w_in[rows[i]] += acc
             c_idx += 1
     return w_in, w_out, loss
+
+
+def lazy_adam_step(w_in, w_out, state, inputs, targets, noise, lr, beta1=0.9, beta2=0.999, eps=1e-8):
+    """torch.optim.Adam's update (lerp / addcmul / sqrt(v) / sqrt(1 - beta2^t) + eps, step lr / (1 - beta1^t)) applied ONLY to the
+    rows that receive a gradient from this batch, with the row's own step count t -- on batches that always touch the same rows it
+    is dense torch.optim.Adam (checked against torch in tests/test_gpu_adam.py).  `state` = dict of m_in, v_in, m_out, v_out
+    (arrays like the tables) and t_in, t_out (int arrays [V]); updated in place.  fp64."""
+    out = training_step(w_in, w_out, inputs, targets, noise)
+    for w, g, m, v, t, rows in ((w_in, out['grad_in'], state['m_in'], state['v_in'], state['t_in'], np.unique(inputs)),
+                                (w_out, out['grad_out'], state['m_out'], state['v_out'], state['t_out'],
+                                 np.unique(np.concatenate([targets.ravel(), noise.ravel()])))):
+        t[rows] += 1
+        tt = t[rows][:, None].astype(np.float64)
+        m[rows] = m[rows] + (g[rows] - m[rows]) * (1 - beta1)
+        v[rows] = v[rows] * beta2 + (1 - beta2) * g[rows] * g[rows]
+        denom = np.sqrt(v[rows]) / np.sqrt(1 - beta2 ** tt) + eps
+        w[rows] = w[rows] - (lr / (1 - beta1 ** tt)) * (m[rows] / denom)
+    return out

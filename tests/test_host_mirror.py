@@ -96,3 +96,19 @@ def test_config_loader_schema_and_overrides():
     from shallow_encoders.split import TrainTestRatioSplit
     from shallow_encoders.config_parser.core import instantiate
     assert isinstance(instantiate(cfg.downstream['node_classification']['split_algorithm']), TrainTestRatioSplit)
+
+
+def test_fused_engine_picks_its_kernel_from_the_yaml_optimizer():
+    """train.engine=fused: torch.optim.Adam -> row-sparse Adam, torch.optim.SGD -> in-place SGD with the YAML lr; an explicit
+    fused_lr forces SGD; anything else is refused with a message instead of silently training with a different optimizer."""
+    from shallow_encoders.config_parser import load_config
+    cfg = load_config('sge_sg_karate_club', ['train.engine=fused'])
+    assert cfg.train.fused_lr is None and cfg.train.fused_optimizer_kind() == 'adam'
+    cfg = load_config('sge_sg_karate_club', ['train.engine=fused', 'train.fused_lr=40.0'])
+    assert cfg.train.fused_optimizer_kind() == 'sgd' and cfg.train.fused_sgd_lr() == 40.0
+    cfg = load_config('sge_sg_karate_club', ['train.engine=fused', 'train.optimizer._target_=torch.optim.SGD', 'train.optimizer.lr=0.5'])
+    assert cfg.train.fused_optimizer_kind() == 'sgd' and cfg.train.fused_sgd_lr() == 0.5
+    cfg = load_config('sge_sg_karate_club', ['train.engine=fused', 'train.optimizer._target_=torch.optim.RMSprop'])
+    import pytest
+    with pytest.raises(ValueError, match='row-sparse Adam'):
+        cfg.train.fused_optimizer_kind()
