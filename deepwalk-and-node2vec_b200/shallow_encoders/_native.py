@@ -84,6 +84,11 @@ _SIGNATURES = {
     'se_check_ids': (c_int, [c_p, c_i64, c_i64, c_i64, c_p, c_p]),
     'se_replica_chunk': (c_int, [c_i64, c_int, c_int, c_p, c_p]),
     'se_replica_sync': (c_int, [c_p, c_i64, c_int, c_int, c_i64, c_p, c_int, c_p]),
+    'se_gemm_nt': (c_int, [c_p, c_p, c_i64, c_i64, c_int, c_p, c_p, c_p, c_p]),
+    'se_row_inv_norms': (c_int, [c_p, c_i64, c_int, c_p, c_p]),
+    'se_cosine_similarity': (c_int, [c_p, c_p, c_i64, c_i64, c_int, c_p, c_p, c_p]),
+    'se_topk_rows': (c_int, [c_p, c_i64, c_i64, c_int, c_p, c_p, c_p]),
+    'se_transpose': (c_int, [c_p, c_i64, c_i64, c_p, c_p]),
     'se_table_fill_uniform': (c_int, [c_p, c_i64, c_f32, c_u64, c_i64, c_int, c_int, c_p]),
     'se_table_gather_rows': (c_int, [c_p, c_int, c_p, c_i64, c_p, c_p]),
     'se_table_scatter_rows': (c_int, [c_p, c_int, c_p, c_i64, c_p, c_p]),
@@ -596,6 +601,59 @@ def replica_sync(base_ptr: int, stride_elems: int, world: int, rank: int, n_elem
         _check(load().se_replica_sync(int(base_ptr), int(stride_elems), int(world), int(rank), int(n_elems),
                                       _ptr(master, torch.float32, 'master'), int(mode), _stream()))
     _launches += 1
+
+
+# ----------------------------------------------------------------------------------------------------------------
+# tensor-core contraction (tcgen05): cosine similarity / closest pairs, shared-negatives scoring
+# ----------------------------------------------------------------------------------------------------------------
+def gemm_nt(a: torch.Tensor, b: torch.Tensor, scale_a: Optional[torch.Tensor] = None, scale_b: Optional[torch.Tensor] = None,
+            out: Optional[torch.Tensor] = None) -> torch.Tensor:
+    """out[i, j] = scale_a[i] * scale_b[j] * <a_i, b_j> for fp32 row-major a [m, k], b [n, k] on the tensor cores (3xTF32)."""
+    global _launches
+    m, kd = a.shape
+    n = b.shape[0]
+    assert b.shape[1] == kd
+    if out is None:
+        out = torch.empty((m, n), dtype=torch.float32, device=a.device)
+    with _on(a):
+        _check(load().se_gemm_nt(_ptr(a, torch.float32, 'a'), _ptr(b, torch.float32, 'b'), m, n, kd, _ptr(scale_a, torch.float32, 'scale_a'),
+                                 _ptr(scale_b, torch.float32, 'scale_b'), _ptr(out, torch.float32, 'out'), _stream()))
+    _launches += 1
+    return out
+
+
+def cosine_similarity(x: torch.Tensor, y: torch.Tensor) -> torch.Tensor:
+    """pairwise_cosine_similarity(x, y) (utils/func.py:7-20) -> [m, n] on the device."""
+    global _launches
+    m, n, emb = x.shape[0], y.shape[0], x.shape[1]
+    out = torch.empty((m, n), dtype=torch.float32, device=x.device)
+    norms = torch.empty(m + n, dtype=torch.float32, device=x.device)
+    with _on(x):
+        _check(load().se_cosine_similarity(_ptr(x, torch.float32, 'x'), _ptr(y, torch.float32, 'y'), m, n, emb, norms.data_ptr(), out.data_ptr(), _stream()))
+    _launches += 3
+    return out
+
+
+def topk_rows(x: torch.Tensor, k: int):
+    """(indices int64 [rows, k], values [rows, k]): the k largest entries per row, descending."""
+    global _launches
+    rows, cols = x.shape
+    idx = torch.empty((rows, k), dtype=torch.int64, device=x.device)
+    val = torch.empty((rows, k), dtype=torch.float32, device=x.device)
+    with _on(x):
+        _check(load().se_topk_rows(_ptr(x, torch.float32, 'x'), rows, cols, int(k), idx.data_ptr(), val.data_ptr(), _stream()))
+    _launches += 1
+    return idx, val
+
+
+def transpose(x: torch.Tensor) -> torch.Tensor:
+    global _launches
+    rows, cols = x.shape
+    out = torch.empty((cols, rows), dtype=torch.float32, device=x.device)
+    with _on(x):
+        _check(load().se_transpose(_ptr(x, torch.float32, 'x'), rows, cols, out.data_ptr(), _stream()))
+    _launches += 1
+    return out
 
 
 # ----------------------------------------------------------------------------------------------------------------

@@ -323,6 +323,25 @@ int se_edge_op(const float *lhs, const float *rhs, int64_t n_elems, int op, floa
 int se_sample_negative_edges(const int64_t *rowptr, const int32_t *col_sorted, int64_t n_nodes, int64_t n, uint64_t seed,
                              int64_t sample_id_base, int32_t *out_src, int32_t *out_dst, int32_t *fail_count, void *stream);
 
+/* ------------------------------------------------------------------------------------------------------------
+ * Tensor-core contraction (csrc/gemm.cu: tcgen05.mma kind::tf32 with TMEM accumulators, 3xTF32 split = fp32-level accuracy).
+ *   se_gemm_nt:            c[i, j] = scale_a[i] * scale_b[j] * <a_i, b_j>, a [m x kdim], b [n x kdim], c [m x n], fp32 row-major;
+ *                          scale vectors may be NULL (= 1)
+ *   se_row_inv_norms:      out[i] = 1 / |x_i|
+ *   se_cosine_similarity:  pairwise_cosine_similarity(x, y) of shallow_encoders/word2vec/utils/func.py:7-20 (x / |x| times (y / |y|)^T),
+ *                          what show_closest_pairs_for_each_word computes before its per-row argsort (tools/model_analysis.py:62-71);
+ *                          inv_norms: scratch for m + n floats
+ *   se_topk_rows:          the k largest entries per row, descending = torch.argsort(row, descending=True)[:k] (model_analysis.py:71);
+ *                          idx_out int64 [rows x k], val_out fp32 [rows x k] or NULL
+ *   se_transpose:          out [cols x rows] = x^T (operands of the shared-negatives update GEMMs)
+ * ---------------------------------------------------------------------------------------------------------- */
+int se_gemm_nt(const float *a, const float *b, int64_t m, int64_t n, int kdim, const float *scale_a, const float *scale_b, float *c,
+               void *stream);
+int se_row_inv_norms(const float *x, int64_t rows, int emb, float *out, void *stream);
+int se_cosine_similarity(const float *x, const float *y, int64_t m, int64_t n, int emb, float *inv_norms, float *out, void *stream);
+int se_topk_rows(const float *x, int64_t rows, int64_t cols, int k, int64_t *idx_out, float *val_out, void *stream);
+int se_transpose(const float *x, int64_t rows, int64_t cols, float *out, void *stream);
+
 /* Table utilities that work on local and sharded tables alike (W2VBase.__init__ xavier_uniform_, word2vec/model.py:22-27;
  * the input_embedding / output_embedding accessors, :29-47).
  *   fill: element i = (2u-1)*bound with u from Philox(seed; i/4) -- independent of the sharding; a rank writes only the

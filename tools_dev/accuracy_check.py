@@ -31,7 +31,7 @@ if len(sys.argv) > 1:
 out = {}
 workers = os.cpu_count() or 1
 for name, (yaml_name, common, fused_over, seeds, n_exp) in CASES.items():
-    res = {'cpu_port': [], 'b200_reference_engine': [], 'b200_fused_engine': [], 'b200_fused_engine_edge_classification': []}
+    res = {'cpu_port': [], 'b200_reference_engine': [], 'b200_fused_adam_engine': [], 'b200_fused_engine': [], 'b200_fused_engine_edge_classification': []}
     for seed in range(seeds):
         base = common + [f'path.output_dir=/tmp/se_acc/{name}_{seed}']
         cfg = load_config(yaml_name, base)
@@ -51,7 +51,8 @@ for name, (yaml_name, common, fused_over, seeds, n_exp) in CASES.items():
         acc = node_classification(w, ds.vocab.get_itos(), ds.labels, instantiate(nc['split_algorithm']), n_exp, nc.get('classifier_params'))
         res['cpu_port'].append(acc[0])
         t1 = time.time()
-        for key, over in (('b200_reference_engine', ['train.engine=reference']), ('b200_fused_engine', ['train.engine=fused'] + fused_over)):
+        for key, over in (('b200_reference_engine', ['train.engine=reference']), ('b200_fused_adam_engine', ['train.engine=fused']),
+                          ('b200_fused_engine', ['train.engine=fused'] + fused_over)):
             torch.manual_seed(seed)
             cfg2 = load_config(yaml_name, base + over)
             tr, ds2 = train(cfg2, quiet=True)
@@ -67,6 +68,7 @@ for name, (yaml_name, common, fused_over, seeds, n_exp) in CASES.items():
     out[name] = {k: {'mean': float(np.mean(v)), 'std': float(np.std(v)), 'runs': v} for k, v in res.items() if v}
     out[name]['delta_reference_engine_pp'] = 100 * (out[name]['b200_reference_engine']['mean'] - out[name]['cpu_port']['mean'])
     out[name]['delta_fused_engine_pp'] = 100 * (out[name]['b200_fused_engine']['mean'] - out[name]['cpu_port']['mean'])
+    out[name]['delta_fused_adam_engine_pp'] = 100 * (out[name]['b200_fused_adam_engine']['mean'] - out[name]['cpu_port']['mean'])
     out[name]['settings'] = {'yaml': yaml_name, 'overrides': common, 'fused_overrides': fused_over, 'seeds': seeds, 'n_experiments': n_exp}
 os.makedirs(os.path.join(ROOT, 'gpurun_out'), exist_ok=True)
 json.dump(out, open(os.path.join(ROOT, 'gpurun_out', 'accuracy.json'), 'w'), indent=1)
