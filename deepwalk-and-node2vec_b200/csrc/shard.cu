@@ -125,8 +125,39 @@ rows_copy_kernel(float *__restrict__ w, int emb, const int64_t *__restrict__ row
     }
 }
 
+// nn.Embedding(max_norm=...) semantics (torch embedding_renorm_, p = 2): every listed row whose L2 norm exceeds max_norm is scaled IN
+// PLACE by max_norm / (norm + 1e-7).  One warp per listed row; the list must not contain a row twice.
+__global__ void __launch_bounds__(256)
+renorm_rows_kernel(float *__restrict__ w, int emb, const int64_t *__restrict__ rows, int64_t n, float max_norm) {
+    const int lane = threadIdx.x & 31;
+    const int64_t warp = ((int64_t)blockIdx.x * blockDim.x + threadIdx.x) >> 5, n_warps = ((int64_t)gridDim.x * blockDim.x) >> 5;
+    for (int64_t i = warp; i < n; i += n_warps) {
+        float *row = w + __ldg(rows + i) * emb;
+        float s = 0.f;
+        for (int e = lane; e < emb; e += 32) { const float v = __ldcg(row + e); s = fmaf(v, v, s); }
+#pragma unroll
+        for (int off = 16; off > 0; off >>= 1) s += __shfl_xor_sync(FULL, s, off);
+        const float norm = sqrtf(s);
+        if (norm > max_norm) {
+            const float scale = max_norm / (norm + 1e-7f);
+            for (int e = lane; e < emb; e += 32) __stcg(row + e, __ldcg(row + e) * scale);
+        }
+    }
+}
+
 }  // namespace
 }  // namespace se
+
+extern "C" int se_table_renorm_rows(float *w, int emb, const int64_t *rows, int64_t n, float max_norm, void *stream) {
+    SE_REQUIRE(w && emb >= 1 && n >= 0 && (n == 0 || rows) && max_norm > 0.f, "se_table_renorm_rows: bad arguments");
+    if (n == 0) return SE_OK;
+    const int sms = se::sm_count();
+    if (sms <= 0) return SE_ERR_CUDA;
+    int64_t blocks = (n + 7) / 8;
+    if (blocks > (int64_t)sms * 8) blocks = (int64_t)sms * 8;
+    se::renorm_rows_kernel<<<(int)blocks, 256, 0, (cudaStream_t)stream>>>(w, emb, rows, n, max_norm);
+    return se::check_cuda(cudaGetLastError(), "renorm_rows_kernel launch");
+}
 
 extern "C" int se_shard_granularity(int64_t *bytes) {
     SE_REQUIRE(bytes, "se_shard_granularity: null pointer");

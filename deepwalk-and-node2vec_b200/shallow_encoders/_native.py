@@ -49,6 +49,8 @@ _SIGNATURES = {
     'se_sample_negatives': (c_int, [c_p, c_p, c_i64, c_u64, c_i64, c_i64, c_p, c_p]),
     'se_skipgram_scores': (c_int, [c_p, c_p, c_i64, c_int, c_p, c_p, c_i64, c_int, c_int, c_p, c_p]),
     'se_skipgram_scores_backward': (c_int, [c_p, c_p, c_i64, c_int, c_p, c_p, c_i64, c_int, c_p, c_p, c_p, c_p]),
+    'se_cbow_scores': (c_int, [c_p, c_p, c_i64, c_int, c_p, c_p, c_i64, c_int, c_int, c_int, c_p, c_p]),
+    'se_cbow_grad': (c_int, [c_p, c_p, c_i64, c_int, c_p, c_p, c_p, c_i64, c_int, c_int, c_int, c_p, c_p, c_p, c_p]),
     'se_ns_loss': (c_int, [c_p, c_p, c_i64, c_int, c_int, c_p, c_p, c_p, c_p]),
     'se_sgns_grad': (c_int, [c_p, c_p, c_i64, c_int, c_p, c_p, c_p, c_i64, c_int, c_int, c_p, c_p, c_p, c_p]),
     'se_sgns_adam_step': (c_int, [c_p, c_p, c_i64, c_int, c_p, c_p, c_p, c_i64, c_int, c_int, c_p, c_f32, c_f32, c_f32, c_f32, c_p, c_p]),
@@ -84,6 +86,7 @@ _SIGNATURES = {
     'se_check_ids': (c_int, [c_p, c_i64, c_i64, c_i64, c_p, c_p]),
     'se_replica_chunk': (c_int, [c_i64, c_int, c_int, c_p, c_p]),
     'se_replica_sync': (c_int, [c_p, c_i64, c_int, c_int, c_i64, c_p, c_int, c_p]),
+    'se_table_renorm_rows': (c_int, [c_p, c_int, c_p, c_i64, c_f32, c_p]),
     'se_gemm_nt': (c_int, [c_p, c_p, c_i64, c_i64, c_int, c_p, c_p, c_p, c_p]),
     'se_row_inv_norms': (c_int, [c_p, c_i64, c_int, c_p, c_p]),
     'se_cosine_similarity': (c_int, [c_p, c_p, c_i64, c_i64, c_int, c_p, c_p, c_p]),
@@ -310,6 +313,41 @@ def skipgram_scores_backward(w_in: torch.Tensor, w_out: torch.Tensor, inputs: to
             _ptr(grad_scores, torch.float32, 'grad_scores'), _ptr(grad_in, torch.float32, 'grad_in'),
             _ptr(grad_out, torch.float32, 'grad_out'), _stream()))
     _launches += 1
+
+
+def cbow_scores(w_in: torch.Tensor, w_out: torch.Tensor, inputs: torch.Tensor, outputs: torch.Tensor, proba: bool) -> torch.Tensor:
+    """CBOW.forward: inputs (B, N) context ids, outputs (B, M) -> scores (B, M)."""
+    global _launches
+    batch, m = outputs.shape
+    out = torch.empty((batch, m), dtype=torch.float32, device=w_in.device)
+    with _on(w_in):
+        _check(load().se_cbow_scores(_ptr(w_in, torch.float32, 'w_in'), _ptr(w_out, torch.float32, 'w_out'), w_in.shape[0], w_in.shape[1],
+                                     _ptr(inputs, torch.int64, 'inputs'), _ptr(outputs, torch.int64, 'outputs'), batch, inputs.shape[1], m,
+                                     int(bool(proba)), out.data_ptr(), _stream()))
+    _launches += 1
+    return out
+
+
+def cbow_grad(w_in: torch.Tensor, w_out: torch.Tensor, inputs: torch.Tensor, targets: torch.Tensor, noise: torch.Tensor,
+              want_grads: bool = True, stats: Optional[torch.Tensor] = None) -> Dict:
+    """CBOW training step: loss dict (+ dense grads of the mean loss) for inputs (B, N), targets (B, M), noise (B, M, K)."""
+    global _launches
+    batch, m = targets.shape
+    n_neg = noise.shape[2] if noise is not None and noise.dim() == 3 else 0
+    own_stats = stats is None
+    if own_stats:
+        stats = torch.zeros(STATS_LEN, dtype=torch.float64, device=w_in.device)
+    g_in = torch.zeros_like(w_in) if want_grads else None
+    g_out = torch.zeros_like(w_out) if want_grads else None
+    with _on(w_in):
+        _check(load().se_cbow_grad(_ptr(w_in, torch.float32, 'w_in'), _ptr(w_out, torch.float32, 'w_out'), w_in.shape[0], w_in.shape[1],
+                                   _ptr(inputs, torch.int64, 'inputs'), _ptr(targets, torch.int64, 'targets'),
+                                   _ptr(noise, torch.int64, 'noise') if n_neg else None, batch, inputs.shape[1], m, n_neg, stats.data_ptr(),
+                                   _ptr(g_in), _ptr(g_out), _stream()))
+    _launches += 1
+    out = _stats_dict(stats) if own_stats else {}
+    out['grad_in'], out['grad_out'] = g_in, g_out
+    return out
 
 
 def ns_loss(pos_logits: torch.Tensor, neg_logits: torch.Tensor, want_grads: bool = True):
@@ -584,6 +622,16 @@ def table_scatter_rows(table, rows: torch.Tensor, src: torch.Tensor) -> None:
     assert src.shape == (rows.numel(), emb)
     with torch.cuda.device(dev):
         _check(load().se_table_scatter_rows(ptr, emb, _ptr(rows, torch.int64, 'rows'), rows.numel(), _ptr(src, torch.float32, 'src'), _stream()))
+    _launches += 1
+
+
+def table_renorm_rows(table, rows: torch.Tensor, max_norm: float) -> None:
+    """nn.Embedding(max_norm) look-up side effect: renormalise the (de-duplicated) rows whose norm exceeds max_norm, in place."""
+    global _launches
+    ptr, vocab, emb, _, dev = _table(table)
+    rows = torch.unique(rows.reshape(-1).to(dev, torch.int64))
+    with torch.cuda.device(dev):
+        _check(load().se_table_renorm_rows(ptr, emb, _ptr(rows, torch.int64, 'rows'), rows.numel(), float(max_norm), _stream()))
     _launches += 1
 
 

@@ -95,9 +95,10 @@ class DatamoduleConfig:
     additional_parameters: dict = field(default_factory=dict)
 
     def instantiate_dataset(self):
-        from shallow_encoders.word2vec.dataloader.torch_dataset import GraphDataset
-        if not self.is_graph:
-            raise NotImplementedError('text datasets (tokenizer / vocabulary pipeline) are outside the B200 hot path')
+        from shallow_encoders.word2vec.dataloader.torch_dataset import GraphDataset, W2VDataset
+        if not self.is_graph:           # text corpora (reference core.py:115-134)
+            return W2VDataset(dataset_name=self.dataset_name, context_radius=self.context_radius, min_word_frequency=self.min_word_frequency,
+                              lemmatize=self.lemmatize, additional_parameters=self.additional_parameters)
         return GraphDataset(dataset_name=self.dataset_name, context_radius=self.context_radius,
                             additional_parameters=self.additional_parameters)
 

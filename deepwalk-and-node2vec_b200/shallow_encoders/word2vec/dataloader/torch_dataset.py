@@ -1,6 +1,12 @@
 """
-Dataset adapters and the skip-gram collate with the reference's interface
-(shallow_encoders/word2vec/dataloader/torch_dataset.py:216-322: GraphDataset, W2VCollateFunctional).
+Dataset adapters and the window collate with the reference's interface
+(shallow_encoders/word2vec/dataloader/torch_dataset.py:23-322: tokenize, W2VDataset, GraphDataset, W2VCollateFunctional).
+
+W2VDataset (text corpora)
+  * tokenize / optional lemmatisation / min-frequency vocabulary in torchtext's order ('<unk>' first, then by (-frequency, token)) /
+    word frequencies / id sequences, as the reference (:23-213); the corpus is tokenised ONCE (the reference re-tokenises every epoch)
+  * `epoch_token_groups()` is the batched device API of the fused engine: the epoch's sentences grouped by (clipped) length as int32
+    matrices in HBM
 
 GraphDataset
   * vocabulary = ['<unk>'] + lexicographically sorted (lower-cased) node names, assigned directly from the graph --
@@ -12,6 +18,7 @@ W2VCollateFunctional
   * `sg`: centres i in [r, L - r), inputs = text[i:i+1], targets = text[i-r:i] ++ text[i+1:i+1+r]   (:300-309)
   * same-length batches are windowed with one strided view instead of a python loop per centre
 """
+import re
 from collections import Counter
 from typing import Dict, Iterator, List, Optional, Tuple
 
@@ -22,9 +29,41 @@ from torch.utils.data import IterableDataset
 
 from shallow_encoders.graph import datasets as _graph_datasets  # noqa: F401  (registers the graph datasets)
 from shallow_encoders.graph.datasets import RandomWalkDataset
+from shallow_encoders.word2vec.dataloader import w2v_datasets as _text_datasets  # noqa: F401  (registers the text datasets)
 from shallow_encoders.word2vec.dataloader.registry import DATASET_REGISTRY
 
 UNK = '<unk>'
+_TOKEN = re.compile(r"[A-Za-z]+[\w^\']*|[\w^\']*[A-Za-z]+[\w^\']*|<unk>")     # the reference's token pattern (:38), the parity contract
+
+
+def tokenize(text: str) -> List[str]:
+    """Lower-case, keep tokens that contain a letter (plus `<unk>`), drop punctuation and pure numbers (reference :23-39)."""
+    return _TOKEN.findall(text.lower())
+
+
+def lemmatize_sentence(text: str) -> str:
+    """WordNet lemmatisation of every word as adjective, adverb, noun, verb in turn (reference :42-59); needs nltk."""
+    try:
+        from nltk.stem import WordNetLemmatizer
+    except ImportError as e:            # nltk is not installable offline: fail loudly instead of silently skipping the step
+        raise NotImplementedError('lemmatize=True needs nltk (WordNetLemmatizer), which is not installed') from e
+    lemmatizer = WordNetLemmatizer()
+    words = text.lower().split(' ')
+    for tag in ('a', 'r', 'n', 'v'):
+        words = [lemmatizer.lemmatize(w, tag) for w in words]
+    return ' '.join(words)
+
+
+def build_vocab(token_lists, min_freq: int, specials=(UNK,)) -> 'Vocab':
+    """torchtext 0.15 `build_vocab_from_iterator(..., specials, min_freq)` ordering: specials first, then tokens with
+    frequency >= min_freq by (-frequency, token)."""
+    counter = Counter()
+    for tokens in token_lists:
+        counter.update(tokens)
+    for sp in specials:
+        counter.pop(sp, None)
+    ordered = sorted(counter.items(), key=lambda kv: (-kv[1], kv[0]))
+    return Vocab(list(specials) + [t for t, f in ordered if f >= min_freq])
 
 
 class Vocab:
@@ -58,6 +97,90 @@ class Vocab:
 
     def get_itos(self) -> List[str]:
         return list(self._itos)
+
+
+class W2VDataset(IterableDataset):
+    """Text corpus as id sequences (reference :61-213)."""
+
+    def __init__(self, dataset_name: str, context_radius: int = 5, min_word_frequency: int = 20, lemmatize: bool = False,
+                 sort_by_frequency: bool = True, additional_parameters: Optional[dict] = None):
+        assert dataset_name in DATASET_REGISTRY, \
+            f'Dataset "{dataset_name}" is not supported. Supported: {list(DATASET_REGISTRY.keys())}'
+        self._context_radius = context_radius
+        self._lemmatize = lemmatize
+        self._dataset = DATASET_REGISTRY[dataset_name](**(additional_parameters or {}))
+        # the whole corpus, tokenised once (the reference also loads it into memory here, :91)
+        self._tokens: List[List[str]] = [self.sentence_pipeline(s, apply_filter=False) for s in self._dataset]
+        vocab_source = self._tokens if sort_by_frequency else [[t] for t in {t for tl in self._tokens for t in tl}]
+        self._vocab = build_vocab(vocab_source, min_word_frequency)
+        self._vocab.set_default_index(self._vocab[UNK])
+        freq = Counter(t for tl in self._tokens for t in tl if t in self._vocab)
+        self._word_frequency: Dict[str, int] = dict(freq)
+        self._pending: Optional[Iterator[torch.Tensor]] = None
+        self._device_groups = None
+
+    def sentence_pipeline(self, sentence: str, apply_filter: bool = True) -> Optional[List[str]]:
+        sentence = lemmatize_sentence(sentence) if self._lemmatize else sentence
+        tokens = tokenize(sentence)
+        if apply_filter and len(tokens) < 2 * self._context_radius + 1:
+            return None
+        return tokens
+
+    def get_iterator(self, apply_filter: bool = True) -> Iterator[List[str]]:
+        keep = 2 * self._context_radius + 1 if apply_filter else 0
+        return (tl for tl in self._tokens if len(tl) >= keep)
+
+    def get_n_most_frequent_words(self, n: int) -> Tuple[List[str], List[int]]:
+        top = sorted(self._word_frequency.items(), key=lambda kv: kv[1], reverse=True)[:n]      # stable, like the reference's sort (:168-169)
+        words = [w for w, _ in top]
+        return words, [self._vocab[w] for w in words]
+
+    @property
+    def vocab(self) -> Vocab:
+        return self._vocab
+
+    @property
+    def has_labels(self) -> bool:
+        return False
+
+    @property
+    def labels(self) -> Dict[str, str]:
+        raise NotImplementedError('This function is not implemented!')
+
+    @property
+    def word_counts(self) -> np.ndarray:
+        """Occurrences per vocabulary row (row 0 = '<unk>' counts the out-of-vocabulary tokens): the unigram table for alias negatives."""
+        counts = np.zeros(len(self._vocab), dtype=np.float64)
+        for tl in self._tokens:
+            for i in self._vocab(tl):
+                counts[i] += 1
+        return counts
+
+    def __iter__(self) -> 'W2VDataset':
+        self._pending = (torch.tensor(self._vocab(tl), dtype=torch.long) for tl in self.get_iterator())
+        return self
+
+    def __next__(self) -> torch.Tensor:
+        if self._pending is None:
+            self.__iter__()
+        return next(self._pending)
+
+    # -- batched device API ----------------------------------------------------------------------------------------
+    @property
+    def row_offset(self) -> int:
+        return 0                       # ids ARE table rows ('<unk>' = 0 is a vocabulary entry)
+
+    def epoch_token_groups(self, max_length: int, device='cuda') -> Dict[int, torch.Tensor]:
+        """The epoch's sentences (filtered, clipped to max_length) grouped by length: {L: int32 [n_L, L] on the device}.  The fused
+        kernels take equal-length sequences; a launch per length class replaces the reference's per-sentence python collate."""
+        if self._device_groups is None or self._device_groups[0] != (max_length, str(device)):
+            groups: Dict[int, List[List[int]]] = {}
+            for tl in self.get_iterator():
+                ids = self._vocab(tl)[:max_length]
+                groups.setdefault(len(ids), []).append(ids)
+            self._device_groups = ((max_length, str(device)),
+                                   {n: torch.tensor(rows, dtype=torch.int32, device=device) for n, rows in sorted(groups.items())})
+        return self._device_groups[1]
 
 
 class GraphDataset(IterableDataset):

@@ -1,5 +1,5 @@
 """
-Word2vec models with the reference's interface (shallow_encoders/word2vec/model.py:10-91: W2VBase, SkipGram).
+Word2vec models with the reference's interface (shallow_encoders/word2vec/model.py:10-110: W2VBase, SkipGram, CBOW).
 
 The two tables are ordinary `nn.Embedding` parameters (state-dict keys `_input_embedding.weight`,
 `_output_embedding.weight`, Xavier-uniform init) living in HBM; scoring and its backward run in the sm_100a kernels
@@ -41,9 +41,9 @@ class W2VBase(nn.Module):
         ONE pair of `ShardedTable`s striped over the GPUs of the node instead of per-process `nn.Embedding`s; only the
         fused engine and `forward` without autograd work on them."""
         super().__init__()
-        if max_norm is not None:
-            raise NotImplementedError('max_norm renormalisation is not implemented on the B200 path (only the abcde toy '
-                                      'configs of the reference set it)')
+        self.max_norm = None if max_norm is None else float(max_norm)
+        if self.max_norm is not None and shard is not None and shard.get('world', 1) > 1:
+            raise NotImplementedError('max_norm is not supported on striped multi-GPU tables')
         device = torch.device('cuda' if device is None else device)
         self._sharded = None
         if shard is not None and shard.get('world', 1) > 1:
@@ -96,14 +96,26 @@ class W2VBase(nn.Module):
         self._sharded[0].load_owned(state_dict[prefix + '_input_embedding.weight'])
         self._sharded[1].load_owned(state_dict[prefix + '_output_embedding.weight'])
 
+    def renorm_(self, inputs: Optional[torch.Tensor] = None, outputs: Optional[torch.Tensor] = None) -> None:
+        """`nn.Embedding(max_norm=...)` (reference :22-23; configs/w2v_sg_abcde.yaml:7) renormalises the rows it looks up, in
+        place, before using them: the same side effect for the ids about to be scored.  No-op when max_norm is None."""
+        if self.max_norm is None:
+            return
+        if inputs is not None:
+            nat.table_renorm_rows(self._input_embedding.weight.data, inputs, self.max_norm)
+        if outputs is not None:
+            nat.table_renorm_rows(self._output_embedding.weight.data, outputs, self.max_norm)
+
     def embed_inputs(self, inputs: torch.Tensor) -> torch.Tensor:
         if self._sharded is not None:
             return self._sharded[0].gather(inputs.reshape(-1)).reshape(*inputs.shape, -1)
+        self.renorm_(inputs=inputs)
         return self._input_embedding(inputs)
 
     def embed_outs(self, outputs: torch.Tensor) -> torch.Tensor:
         if self._sharded is not None:
             return self._sharded[1].gather(outputs.reshape(-1)).reshape(*outputs.shape, -1)
+        self.renorm_(outputs=outputs)
         return self._output_embedding(outputs)
 
 
@@ -118,7 +130,44 @@ class SkipGram(W2VBase):
         w_in, w_out = self._input_embedding.weight, self._output_embedding.weight
         inputs = inputs.to(w_in.device).reshape(-1)
         outputs = outputs.to(w_in.device)
+        self.renorm_(inputs, outputs)
         if not (torch.is_grad_enabled() and (w_in.requires_grad or w_out.requires_grad)):
             return nat.skipgram_scores(w_in.detach(), w_out.detach(), inputs.contiguous(), outputs.contiguous(), proba=proba)
         scores = _SkipGramScores.apply(w_in, w_out, inputs, outputs)
+        return torch.sigmoid(scores) if proba else scores
+
+
+class _CbowScores(torch.autograd.Function):
+    """scores[b, j] = <mean_n W_in[inputs[b, n]], W_out[outputs[b, j]]>; backward = what autograd gives for model.py:103-106,
+    evaluated by the same kernel family (dense gradients through `se_cbow_grad`-style accumulation in torch index_add form)."""
+
+    @staticmethod
+    def forward(ctx, w_in, w_out, inputs, outputs):
+        inputs, outputs = inputs.contiguous(), outputs.contiguous()
+        ctx.save_for_backward(w_in, w_out, inputs, outputs)
+        return nat.cbow_scores(w_in.detach(), w_out.detach(), inputs, outputs, proba=False)
+
+    @staticmethod
+    def backward(ctx, grad_scores):
+        w_in, w_out, inputs, outputs = ctx.saved_tensors
+        b, n = inputs.shape
+        h = w_in.detach()[inputs].mean(dim=1)                                              # (B, E)
+        g_out = torch.zeros_like(w_out).index_add_(0, outputs.reshape(-1), (grad_scores.unsqueeze(-1) * h.unsqueeze(1)).reshape(-1, h.shape[1]))
+        gh = torch.einsum('bm,bme->be', grad_scores, w_out.detach()[outputs]) / n
+        g_in = torch.zeros_like(w_in).index_add_(0, inputs.reshape(-1), gh.unsqueeze(1).expand(b, n, -1).reshape(-1, h.shape[1]))
+        return g_in, g_out, None, None
+
+
+class CBOW(W2VBase):
+    """inputs (B, N) context ids, outputs (B, 1) centre ids (or (B, K) noise) -> scores (B, M) (reference :94-110)."""
+
+    def forward(self, inputs: torch.Tensor, outputs: torch.Tensor, proba: bool = True) -> torch.Tensor:
+        if self._sharded is not None:
+            raise NotImplementedError('CBOW runs on per-GPU tables (the striped multi-GPU tables serve the SkipGram fused engine)')
+        w_in, w_out = self._input_embedding.weight, self._output_embedding.weight
+        inputs, outputs = inputs.to(w_in.device), outputs.to(w_in.device)
+        self.renorm_(inputs, outputs)
+        if not (torch.is_grad_enabled() and (w_in.requires_grad or w_out.requires_grad)):
+            return nat.cbow_scores(w_in.detach(), w_out.detach(), inputs.contiguous(), outputs.contiguous(), proba=proba)
+        scores = _CbowScores.apply(w_in, w_out, inputs, outputs)
         return torch.sigmoid(scores) if proba else scores

@@ -50,6 +50,26 @@ class _SgnsStep(torch.autograd.Function):
         return g_in * g_loss, g_out * g_loss, None, None, None
 
 
+class _CbowStep(torch.autograd.Function):
+    """The same for a CBOW model: inputs (B, N) context ids, targets (B, 1), noise (B, 1, K); one launch of `se_cbow_grad`."""
+
+    @staticmethod
+    def forward(ctx, w_in, w_out, inputs, targets, noise):
+        stats = torch.zeros(nat.STATS_LEN, dtype=torch.float64, device=w_in.device)
+        res = nat.cbow_grad(w_in.detach(), w_out.detach(), inputs.contiguous(), targets.contiguous(), noise.contiguous(), want_grads=True, stats=stats)
+        ctx.save_for_backward(res['grad_in'], res['grad_out'])
+        pairs, negs = stats[4].clamp(min=1.0), stats[5].clamp(min=1.0)
+        pl, nl = (stats[0] / pairs).float(), (stats[1] / pairs).float()
+        recall, precision = (stats[2] / pairs).float(), (1.0 - stats[3] / negs).float()
+        ctx.mark_non_differentiable(recall, precision)
+        return pl + nl, pl, nl, recall, precision
+
+    @staticmethod
+    def backward(ctx, g_loss, g_pl, g_nl, _g_recall, _g_precision):
+        g_in, g_out = ctx.saved_tensors
+        return g_in * g_loss, g_out * g_loss, None, None, None
+
+
 class Word2VecTrainer(nn.Module):
     """Trains a W2V model."""
 
@@ -100,7 +120,11 @@ class Word2VecTrainer(nn.Module):
         w_in, w_out = self._model._input_embedding.weight, self._model._output_embedding.weight
         inputs, outputs = inputs.to(w_in.device), outputs.to(w_in.device)
         noise = generate_noise_batch(outputs.shape[0], outputs.shape[1], self._neg_samples, self._vocab_size, device=w_in.device)
-        loss, pos, neg, recall, precision = _SgnsStep.apply(w_in, w_out, inputs, outputs, noise)
+        from shallow_encoders.word2vec.model import CBOW
+        # the reference's two forward passes look the rows up through nn.Embedding(max_norm): same in-place renormalisation first
+        self._model.renorm_(inputs, torch.cat([outputs.reshape(-1), noise.reshape(-1)]))
+        step = _CbowStep if isinstance(self._model, CBOW) else _SgnsStep          # cbow collate: inputs (B, N) contexts, outputs (B, 1) centre
+        loss, pos, neg, recall, precision = step.apply(w_in, w_out, inputs, outputs, noise)
         out = {'loss': loss, 'positive-loss': pos, 'negative-loss': neg}
         for name, value in out.items():
             value = value.detach()
@@ -145,6 +169,9 @@ class Word2VecTrainer(nn.Module):
                    local_negatives: bool = False, check_tokens: bool = False) -> Optional[Dict[str, float]]:
         """In-place SGNS update from int32 token sequences [n_seq, L] in HBM; `lr` multiplies the un-averaged per-pair
         gradient (for the reference's mean loss over a launch of P pairs pass lr_batch / P)."""
+        if getattr(self._model, 'max_norm', None) is not None:
+            raise NotImplementedError('max_norm needs the rows of a step before it runs; the in-place SGD kernel draws its negatives '
+                                      'in-kernel.  Use the Adam engine (train.engine=fused with torch.optim.Adam) or train.engine=reference.')
         w_in, w_out = self._model.tables
         launch = next(self._fused_launch)
         n_cen = tokens.shape[1] - 2 * context_radius
@@ -168,6 +195,7 @@ class Word2VecTrainer(nn.Module):
         launch = next(self._fused_launch)
         noise = generate_noise_batch(targets.shape[0], 2 * r, self._neg_samples, self._vocab_size, device=w_in.device,
                                      seed=seed * 0x9E3779B1 + launch)
+        self._model.renorm_(inputs, torch.cat([targets.reshape(-1), noise.reshape(-1)]))
         return self._optimizer.step_batch(w_in, w_out, inputs, targets, noise, stats=stats)
 
     # -- checkpoints (state-dict keys `_model._input_embedding.weight`, `_model._output_embedding.weight`) ---------------

@@ -130,6 +130,10 @@ def fit_fused(cfg, dataset, trainer, end_of_epoch, rank: int = 0, world: int = 1
             raise ValueError('the row-sparse Adam engine is single-GPU; multi-GPU runs use the in-place SGD kernels (set train.fused_lr)')
         return fit_fused_adam(cfg, dataset, trainer, end_of_epoch, stats)
     base_lr = cfg.train.fused_sgd_lr()
+    if not cfg.datamodule.is_graph:
+        if world > 1:
+            raise ValueError('text corpora train on one GPU')
+        return fit_fused_text_sgd(cfg, dataset, trainer, end_of_epoch, stats, base_lr, step_size, gamma)
     n_walks_global = len(dataset)
     for epoch in range(cfg.train.max_epochs):
         trainer.current_epoch = epoch
@@ -171,27 +175,63 @@ def fit_fused(cfg, dataset, trainer, end_of_epoch, rank: int = 0, world: int = 1
         end_of_epoch(trainer, epoch, means)
 
 
+def _epoch_batches(cfg, dataset):
+    """Equal-length int32 token matrices of at most `batch_size` sequences: one per mini-batch of a graph epoch, one per
+    (length class, mini-batch) of a text epoch (sentences are grouped by clipped length; the kernels take equal-length rows)."""
+    bs = cfg.datamodule.batch_size
+    if cfg.datamodule.is_graph:
+        tokens = dataset.epoch_tokens()[:, :cfg.datamodule.max_length]
+        groups = [tokens]
+    else:
+        groups = list(dataset.epoch_token_groups(cfg.datamodule.max_length).values())
+    for tokens in groups:
+        for lo in range(0, tokens.shape[0], bs):
+            yield tokens[lo:lo + bs]
+
+
+def _epoch_means(stats, lr):
+    s = stats.tolist()
+    p = max(s[4], 1.0)
+    return {'train-epoch/loss': (s[0] + s[1]) / p, 'train-epoch/positive-loss': s[0] / p, 'train-epoch/negative-loss': s[1] / p,
+            'train-metrics/recall': s[2] / p, 'train-metrics/precision': 1 - s[3] / max(s[5], 1.0), 'epoch/lr': lr}
+
+
+def fit_fused_text_sgd(cfg, dataset, trainer, end_of_epoch, stats, base_lr, step_size, gamma):
+    """Text corpus through the fused window / negatives / in-place SGD kernel, one launch per mini-batch of equal-length sentences."""
+    r = cfg.datamodule.context_radius
+    from shallow_encoders import _native as nat
+    for epoch in range(cfg.train.max_epochs):
+        trainer.current_epoch = epoch
+        lr_batch = base_lr * gamma ** (epoch // step_size)
+        stats.zero_()
+        for chunk in _epoch_batches(cfg, dataset):
+            pairs = chunk.shape[0] * (chunk.shape[1] - 2 * r) * 2 * r
+            trainer.fused_step(chunk.contiguous(), r, lr_batch / pairs, row_offset=dataset.row_offset, seed=epoch * 1_000_003 + trainer.global_step,
+                               stats=stats, flags=nat.SCATTER_RED | nat.WINDOW_REFRESH)
+            trainer.global_step += 1
+        means = _epoch_means(stats, lr_batch)
+        for name, value in means.items():
+            trainer.log(name, value)
+        end_of_epoch(trainer, epoch, means)
+
+
 def fit_fused_adam(cfg, dataset, trainer, end_of_epoch, stats):
     """The reference's loop (tools/train.py:67-83: per batch training_step -> backward -> Adam.step; scheduler.step per epoch) with every
     stage on the device: walks of the epoch from one kernel launch, then per `batch_size` walks one `fused_adam_step`."""
     r = cfg.datamodule.context_radius
+    if cfg.datamodule.mode.lower() != 'sg':
+        raise ValueError('the fused engine trains SkipGram (mode: sg); CBOW runs with train.engine=reference')
     scheduler = trainer.scheduler['scheduler'] if isinstance(trainer.scheduler, dict) else trainer.scheduler
-    bs = cfg.datamodule.batch_size
     for epoch in range(cfg.train.max_epochs):
         trainer.current_epoch = epoch
-        tokens = dataset.epoch_tokens()[:, :cfg.datamodule.max_length]
         stats.zero_()
-        for lo in range(0, tokens.shape[0], bs):
-            trainer.fused_adam_step(tokens[lo:lo + bs], r, row_offset=dataset.row_offset, seed=epoch, stats=stats)
+        for chunk in _epoch_batches(cfg, dataset):
+            trainer.fused_adam_step(chunk, r, row_offset=dataset.row_offset, seed=epoch, stats=stats)
             trainer.global_step += 1
         lr = trainer.optimizer.param_groups[0]['lr']
         if scheduler is not None:
             scheduler.step()
-        s = stats.tolist()
-        p = max(s[4], 1.0)
-        means = {'train-epoch/loss': (s[0] + s[1]) / p, 'train-epoch/positive-loss': s[0] / p,
-                 'train-epoch/negative-loss': s[1] / p, 'train-metrics/recall': s[2] / p,
-                 'train-metrics/precision': 1 - s[3] / max(s[5], 1.0), 'epoch/lr': lr}
+        means = _epoch_means(stats, lr)
         for name, value in means.items():
             trainer.log(name, value)
         end_of_epoch(trainer, epoch, means)

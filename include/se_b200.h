@@ -135,6 +135,17 @@ int se_skipgram_scores_backward(const float *w_in, const float *w_out, int64_t v
                                 const int64_t *outputs, int64_t batch, int m, const float *grad_scores, float *grad_in,
                                 float *grad_out, void *stream);
 
+/* CBOW.forward (word2vec/model.py:98-110): out[b*m + j] = <mean_n W_in[inputs[b*n_in + n]], W_out[outputs[b*m + j]]>, sigmoid when
+ * proba != 0.  inputs (B, n_in) are the 2r context ids, outputs (B, m) the centre (m = 1) or noise ids (collate mode `cbow`,
+ * word2vec/dataloader/torch_dataset.py:310-314).  emb <= 1024. */
+int se_cbow_scores(const float *w_in, const float *w_out, int64_t vocab, int emb, const int64_t *inputs, const int64_t *outputs,
+                   int64_t batch, int n_in, int m, int proba, float *out, void *stream);
+/* Word2VecTrainer.training_step + backward for a CBOW model (trainer.py:131-139, loss.py:14-22): targets (B, m), noise (B, m, K);
+ * stats as se_sgns_grad (pairs = B * m); dense gradients of the MEAN loss ACCUMULATED into grad_in / grad_out (both or neither). */
+int se_cbow_grad(const float *w_in, const float *w_out, int64_t vocab, int emb, const int64_t *inputs, const int64_t *targets,
+                 const int64_t *noise, int64_t batch, int n_in, int m, int n_neg, double *stats, float *grad_in, float *grad_out,
+                 void *stream);
+
 /* NegativeSamplingLoss.forward on logits (word2vec/loss.py:14-22): pos_logits (B,N), neg_logits (B,N,K) -> stats
  * (same layout as above) and, when non-NULL, grad_pos (B,N) = d mean(positive-loss)/d pos_logits and
  * grad_neg (B,N,K) = d mean(negative-loss)/d neg_logits. */
@@ -351,6 +362,9 @@ int se_table_fill_uniform(float *w, int64_t n_elems, float bound, uint64_t seed,
                           int rank, void *stream);
 int se_table_gather_rows(const float *w, int emb, const int64_t *rows, int64_t n, float *out, void *stream);
 int se_table_scatter_rows(float *w, int emb, const int64_t *rows, int64_t n, const float *src, void *stream);
+/* nn.Embedding(max_norm) (word2vec/model.py:22-23, set by configs/w2v_sg_abcde.yaml:7): rows[i] (DISTINCT ids) whose L2 norm exceeds
+ * max_norm are rescaled in place by max_norm / (norm + 1e-7), what torch's embedding_renorm_ does at look-up time. */
+int se_table_renorm_rows(float *w, int emb, const int64_t *rows, int64_t n, float max_norm, void *stream);
 
 #ifdef __cplusplus
 }
