@@ -82,7 +82,7 @@ def test_walk_factory_and_schedule():
 
 def test_config_loader_schema_and_overrides():
     cfg = load_config('sge_sg_karate_club', ['train.max_epochs=3', 'datamodule.additional_parameters.method_params.q=2.0'])
-    assert cfg.train.max_epochs == 3 and cfg.train.loss.negative_samples == 1 and cfg.train.engine == 'reference'
+    assert cfg.train.max_epochs == 3 and cfg.train.loss.negative_samples == 1 and cfg.train.engine == 'fused'
     assert cfg.datamodule.additional_parameters['method_params'] == {'p': 1, 'q': 2.0}
     assert cfg.model['_target_'] == 'shallow_encoders.word2vec.model.SkipGram'
     assert cfg.train.optimizer['_target_'] == 'torch.optim.Adam' and cfg.datamodule.batch_size == 64
@@ -90,9 +90,16 @@ def test_config_loader_schema_and_overrides():
         c = load_config(name)
         assert c.datamodule.is_graph and c.datamodule.mode == 'sg'
     p = torch.nn.Parameter(torch.zeros(2))
-    opt = cfg.train.instantiate_optimizer([p])
+    from shallow_encoders.word2vec.optim import RowSparseAdam
+    opt = cfg.train.instantiate_optimizer([p])                       # shipped default: fused engine -> the YAML's Adam becomes the row-sparse kernel
     sched = cfg.train.instantiate_scheduler(opt)
-    assert isinstance(opt, torch.optim.Adam) and isinstance(sched, torch.optim.lr_scheduler.StepLR)
+    assert isinstance(opt, RowSparseAdam) and opt.param_groups[0]['lr'] == 0.1 and isinstance(sched, torch.optim.lr_scheduler.StepLR)
+    ref = load_config('sge_sg_karate_club', ['train.engine=reference'])
+    assert isinstance(ref.train.instantiate_optimizer([p]), torch.optim.Adam)
+    # the reference's own YAML (no `engine` key) loads too and takes the dense reference engine
+    if os.path.exists('/root/reference/configs/sge_sg_karate_club.yaml'):
+        orig = load_config('/root/reference/configs/sge_sg_karate_club.yaml')
+        assert orig.train.engine == 'reference' and orig.datamodule.batch_size == 64
     from shallow_encoders.split import TrainTestRatioSplit
     from shallow_encoders.config_parser.core import instantiate
     assert isinstance(instantiate(cfg.downstream['node_classification']['split_algorithm']), TrainTestRatioSplit)
