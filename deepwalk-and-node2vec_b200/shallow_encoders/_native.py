@@ -92,6 +92,8 @@ _SIGNATURES = {
     'se_cosine_similarity': (c_int, [c_p, c_p, c_i64, c_i64, c_int, c_p, c_p, c_p]),
     'se_topk_rows': (c_int, [c_p, c_i64, c_i64, c_int, c_p, c_p, c_p]),
     'se_transpose': (c_int, [c_p, c_i64, c_i64, c_p, c_p]),
+    'se_shared_negatives_scratch_floats': (c_i64, [c_i64, c_i64, c_int]),
+    'se_sgns_step_shared_negatives': (c_int, [c_p, c_p, c_i64, c_int, c_p, c_i64, c_p, c_i64, c_int, c_int, c_f32, c_p, c_i64, c_p, c_p]),
     'se_table_fill_uniform': (c_int, [c_p, c_i64, c_f32, c_u64, c_i64, c_int, c_int, c_p]),
     'se_table_gather_rows': (c_int, [c_p, c_int, c_p, c_i64, c_p, c_p]),
     'se_table_scatter_rows': (c_int, [c_p, c_int, c_p, c_i64, c_p, c_p]),
@@ -692,6 +694,27 @@ def topk_rows(x: torch.Tensor, k: int):
         _check(load().se_topk_rows(_ptr(x, torch.float32, 'x'), rows, cols, int(k), idx.data_ptr(), val.data_ptr(), _stream()))
     _launches += 1
     return idx, val
+
+
+def sgns_step_shared_negatives(w_in: torch.Tensor, w_out: torch.Tensor, inputs: torch.Tensor, shared: torch.Tensor, n_ctx: int, n_neg: int,
+                               lr: float, stats: Optional[torch.Tensor] = None, scratch: Optional[torch.Tensor] = None) -> Optional[Dict[str, float]]:
+    """Negative half of an SGNS step with ONE shared set of negative rows for the whole batch (three tcgen05 GEMMs); see the header."""
+    global _launches
+    batch, s = inputs.numel(), shared.numel()
+    need = load().se_shared_negatives_scratch_floats(batch, s, w_in.shape[1])
+    if scratch is None or scratch.numel() < need:
+        scratch = torch.empty(max(int(need), 4), dtype=torch.float32, device=w_in.device)
+    own_stats = stats is None
+    if own_stats:
+        stats = torch.zeros(STATS_LEN, dtype=torch.float64, device=w_in.device)
+    with _on(w_in):
+        _check(load().se_sgns_step_shared_negatives(
+            _ptr(w_in, torch.float32, 'w_in'), _ptr(w_out, torch.float32, 'w_out'), w_in.shape[0], w_in.shape[1],
+            _ptr(inputs.reshape(-1), torch.int64, 'inputs'), batch, _ptr(shared.reshape(-1), torch.int64, 'shared'), s, int(n_ctx), int(n_neg),
+            float(lr), scratch.data_ptr(), scratch.numel(), stats.data_ptr(), _stream()))
+    stats[5] += float(batch * n_ctx * n_neg)        # negatives the step stands for
+    _launches += 11
+    return _stats_dict(stats) if own_stats else None
 
 
 def transpose(x: torch.Tensor) -> torch.Tensor:

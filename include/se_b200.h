@@ -353,6 +353,18 @@ int se_cosine_similarity(const float *x, const float *y, int64_t m, int64_t n, i
 int se_topk_rows(const float *x, int64_t rows, int64_t cols, int k, int64_t *idx_out, float *val_out, void *stream);
 int se_transpose(const float *x, int64_t rows, int64_t cols, float *out, void *stream);
 
+/* Optional SHARED-NEGATIVES batch mode (csrc/shared_neg.cu): the negative half of an SGNS step for `batch` centres against ONE set
+ * of n_shared negative rows, as three tensor-core GEMMs (scores B x S, centre updates B x E, negative-row updates S x E) instead of
+ * per-pair dot products; each shared row is weighted n_ctx * n_neg / n_shared, the number of per-pair negatives of the reference
+ * (word2vec/utils/sampling.py:21, trainer.py:133-138) it stands for.  inputs[batch] centre rows, shared[n_shared] negative rows
+ * (duplicates accumulate); lr multiplies the un-averaged per-pair gradient like se_sgns_step; the positive pairs go through
+ * se_sgns_step with n_neg = 0.  stats: [1] += weighted negative loss, [3] += weighted count of sigmoid(s-) >= 0.5.
+ * scratch: se_shared_negatives_scratch_floats(batch, n_shared, emb) floats, 16-byte aligned. */
+int64_t se_shared_negatives_scratch_floats(int64_t batch, int64_t n_shared, int emb);
+int se_sgns_step_shared_negatives(float *w_in, float *w_out, int64_t vocab, int emb, const int64_t *inputs, int64_t batch,
+                                  const int64_t *shared, int64_t n_shared, int n_ctx, int n_neg, float lr, float *scratch,
+                                  int64_t scratch_floats, double *stats, void *stream);
+
 /* Table utilities that work on local and sharded tables alike (W2VBase.__init__ xavier_uniform_, word2vec/model.py:22-27;
  * the input_embedding / output_embedding accessors, :29-47).
  *   fill: element i = (2u-1)*bound with u from Philox(seed; i/4) -- independent of the sharding; a rank writes only the
