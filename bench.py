@@ -97,6 +97,8 @@ def parse_args():
                          'reduce-scatter/all-gather kernel over peer memory per step (product, reference-exact draw); sharded = one striped table '
                          'pair gathered / red.added per pair over NVLink (capacity mode; --negatives local|global|owner); a2a = the NCCL all-to-all '
                          'baseline; replicas = NCCL all-reduce averaging')
+    ap.add_argument('--merge', default='sum', help='--multi synced: how the GPUs\' updates of a step combine in the sync kernel: mean (local SGD with '
+                    'model averaging), sum (synchronous SGD with summed updates; default, accuracy-checked on 2 and 8 GPUs) or a weight in (0, 1]')
     ap.add_argument('--a2a-micro-walks', type=int, default=8192, help='a2a baseline: walks per exchange micro-batch')
     ap.add_argument('--negatives', default='auto', choices=['auto', 'local', 'global', 'owner'],
                     help='sharded tables: local (auto) = draw negatives among the rows the GPU owns; global = reference draw over the whole table, rows '
@@ -141,7 +143,8 @@ def workload_config(a, n_gpus):
         'emb': a.emb, 'context_radius': a.radius, 'negatives': a.neg,
         'negative_sampling': ('uniform over the rows owned by the GPU (walks are dealt to GPUs by id)'
                               if (n_gpus > 1 and a.multi in ('sharded', 'a2a') and a.negatives in ('auto', 'local')) else 'uniform (reference)'),
-        'table_sync': ('every step: master += sum over GPUs of (working copy - master), written back to all copies' if n_gpus > 1 and a.multi == 'synced' else None),
+        'table_sync': (f'every step: master += beta * sum over GPUs of (working copy - master), written back to all copies; merge = {a.merge}'
+                       if n_gpus > 1 and a.multi == 'synced' else None),
         'optimizer': 'in-place SGD (Hogwild, red.global.add.v4.f32)' if a.scatter == 'red' else 'in-place SGD (Hogwild, plain stores)',
         'parallelism': parallelism(a, n_gpus),
         'l2': 'inputs exceed L2 (tables 2 x %.2f GB, CSR ~%.1f GB); no flush' % ((a.nodes + 1) * a.emb * 4 / 1e9, (2 * a.edges * 4 + a.nodes * 8) / 1e9),
@@ -443,7 +446,7 @@ def run_b200(a, rank, local_rank, world):
             s0.record()
         if T['synced']:
             from shallow_encoders.word2vec.sharded import sync_replicated
-            sync_replicated([T['w_in'], T['w_out']])
+            sync_replicated([T['w_in'], T['w_out']], merge=a.merge)
         else:
             dist.all_reduce(T['w_in'], op=dist.ReduceOp.AVG)
             dist.all_reduce(T['w_out'], op=dist.ReduceOp.AVG)

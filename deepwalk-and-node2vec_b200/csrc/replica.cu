@@ -8,7 +8,8 @@
 // doing it ONCE per step as bulk coalesced traffic runs at the link rate.  So every GPU trains on a full working copy in
 // its own HBM with the unchanged single-GPU kernels (Hogwild, device-scope reductions), and rank r OWNS the master of rows
 // chunk r.  After a step, the owner of each element computes
-//         master' = master + sum_g (copy_g - master)            (the summed updates of all GPUs since the last sync)
+//         master' = master + beta * sum_g (copy_g - master)     (beta = 1: the SUMMED updates of all GPUs since the last sync;
+//                                                                beta = 1/G: their MEAN = local SGD with model averaging)
 // reading the G copies over NVLink (7/8 of them peers), and stores master' back into all G copies -- reduce-scatter of the
 // updates and all-gather of the rows fused in one pass, 2 (G-1)/G of the table per direction per GPU, no staging buffers,
 // no NCCL on the data path (a barrier on either side is the only collective).  sum-of-differences keeps the arithmetic
@@ -36,7 +37,7 @@ __device__ __forceinline__ void st_sys(float4 *p, const float4 &v) {
 template <int W>
 __global__ void __launch_bounds__(256)
 replica_sync_kernel(float *__restrict__ base, int64_t stride_elems, int world, int rank, int64_t lo4, int64_t hi4,
-                    float4 *__restrict__ master, int mode) {
+                    float4 *__restrict__ master, int mode, float beta) {
     const int G = W > 0 ? W : world;
     for (int64_t i = lo4 + (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < hi4; i += (int64_t)gridDim.x * blockDim.x) {
         if (mode == 1) {
@@ -54,7 +55,7 @@ replica_sync_kernel(float *__restrict__ base, int64_t stride_elems, int world, i
 #pragma unroll
             for (int g = 0; g < (W > 0 ? W : REPLICA_MAX_WORLD); ++g)
                 if (g < G) { acc.x += s[g].x - m.x; acc.y += s[g].y - m.y; acc.z += s[g].z - m.z; acc.w += s[g].w - m.w; }
-            nv = make_float4(m.x + acc.x, m.y + acc.y, m.z + acc.z, m.w + acc.w);
+            nv = make_float4(fmaf(beta, acc.x, m.x), fmaf(beta, acc.y, m.y), fmaf(beta, acc.z, m.z), fmaf(beta, acc.w, m.w));
             master[i - lo4] = nv;
         }
 #pragma unroll
@@ -82,7 +83,7 @@ extern "C" int se_replica_chunk(int64_t n_elems, int world, int rank, int64_t *l
 }
 
 extern "C" int se_replica_sync(float *base, int64_t stride_elems, int world, int rank, int64_t n_elems, float *master, int mode,
-                               void *stream) {
+                               float beta, void *stream) {
     SE_REQUIRE(base && master, "se_replica_sync: null pointer");
     SE_REQUIRE(world >= 1 && world <= se::REPLICA_MAX_WORLD && rank >= 0 && rank < world, "se_replica_sync: bad world %d / rank %d (max %d GPUs)",
                world, rank, se::REPLICA_MAX_WORLD);
@@ -91,6 +92,7 @@ extern "C" int se_replica_sync(float *base, int64_t stride_elems, int world, int
                (long long)n_elems);
     SE_REQUIRE(((uintptr_t)base % 16) == 0 && ((uintptr_t)master % 16) == 0, "se_replica_sync: buffers must be 16-byte aligned");
     SE_REQUIRE(mode >= 0 && mode <= 2, "se_replica_sync: unknown mode %d", mode);
+    SE_REQUIRE(mode != 0 || (beta > 0.f && beta <= 1.f), "se_replica_sync: merge weight beta must be in (0, 1] (got %g)", (double)beta);
     int64_t lo4, hi4;
     se::chunk_bounds(n_elems, world, rank, lo4, hi4);
     if (hi4 <= lo4) return SE_OK;
@@ -101,10 +103,10 @@ extern "C" int se_replica_sync(float *base, int64_t stride_elems, int world, int
     cudaStream_t st = (cudaStream_t)stream;
     float4 *m4 = reinterpret_cast<float4 *>(master);
     switch (world) {
-        case 2: se::replica_sync_kernel<2><<<(int)blocks, 256, 0, st>>>(base, stride_elems, world, rank, lo4, hi4, m4, mode); break;
-        case 4: se::replica_sync_kernel<4><<<(int)blocks, 256, 0, st>>>(base, stride_elems, world, rank, lo4, hi4, m4, mode); break;
-        case 8: se::replica_sync_kernel<8><<<(int)blocks, 256, 0, st>>>(base, stride_elems, world, rank, lo4, hi4, m4, mode); break;
-        default: se::replica_sync_kernel<0><<<(int)blocks, 256, 0, st>>>(base, stride_elems, world, rank, lo4, hi4, m4, mode); break;
+        case 2: se::replica_sync_kernel<2><<<(int)blocks, 256, 0, st>>>(base, stride_elems, world, rank, lo4, hi4, m4, mode, beta); break;
+        case 4: se::replica_sync_kernel<4><<<(int)blocks, 256, 0, st>>>(base, stride_elems, world, rank, lo4, hi4, m4, mode, beta); break;
+        case 8: se::replica_sync_kernel<8><<<(int)blocks, 256, 0, st>>>(base, stride_elems, world, rank, lo4, hi4, m4, mode, beta); break;
+        default: se::replica_sync_kernel<0><<<(int)blocks, 256, 0, st>>>(base, stride_elems, world, rank, lo4, hi4, m4, mode, beta); break;
     }
     return se::check_cuda(cudaGetLastError(), "replica_sync_kernel launch");
 }

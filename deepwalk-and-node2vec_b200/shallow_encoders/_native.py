@@ -85,7 +85,7 @@ _SIGNATURES = {
     'se_sample_negative_edges': (c_int, [c_p, c_p, c_i64, c_i64, c_u64, c_i64, c_p, c_p, c_p, c_p]),
     'se_check_ids': (c_int, [c_p, c_i64, c_i64, c_i64, c_p, c_p]),
     'se_replica_chunk': (c_int, [c_i64, c_int, c_int, c_p, c_p]),
-    'se_replica_sync': (c_int, [c_p, c_i64, c_int, c_int, c_i64, c_p, c_int, c_p]),
+    'se_replica_sync': (c_int, [c_p, c_i64, c_int, c_int, c_i64, c_p, c_int, c_f32, c_p]),
     'se_table_renorm_rows': (c_int, [c_p, c_int, c_p, c_i64, c_f32, c_p]),
     'se_gemm_nt': (c_int, [c_p, c_p, c_i64, c_i64, c_int, c_p, c_p, c_p, c_p]),
     'se_row_inv_norms': (c_int, [c_p, c_i64, c_int, c_p, c_p]),
@@ -644,12 +644,13 @@ def replica_chunk(n_elems: int, world: int, rank: int):
     return lo.value, hi.value
 
 
-def replica_sync(base_ptr: int, stride_elems: int, world: int, rank: int, n_elems: int, master: torch.Tensor, mode: int = 0) -> None:
+def replica_sync(base_ptr: int, stride_elems: int, world: int, rank: int, n_elems: int, master: torch.Tensor, mode: int = 0,
+                 beta: float = 1.0) -> None:
     """One rank's share of the fused reduce-scatter + all-gather over the working copies (csrc/replica.cu)."""
     global _launches
     with _on(master):
         _check(load().se_replica_sync(int(base_ptr), int(stride_elems), int(world), int(rank), int(n_elems),
-                                      _ptr(master, torch.float32, 'master'), int(mode), _stream()))
+                                      _ptr(master, torch.float32, 'master'), int(mode), float(beta), _stream()))
     _launches += 1
 
 

@@ -49,7 +49,10 @@ class TrainConfig:
     # mean-loss learning rate (a launch over P pairs applies fused_lr / P per pair) whatever the optimizer block says.
     fused_lr: Optional[float] = None
     local_negatives: bool = False      # multi-GPU fused engine: draw negatives among the rows the GPU owns
-    multi_gpu_negatives: str = 'global'   # multi-GPU fused engine: global | local | owner (reference draw, owner-computes negatives)
+    # multi-GPU fused engine: synced (default: working copy per GPU + row-sharded masters, the reference's global draw, one fused
+    # reduce-scatter/all-gather kernel per step) | global | local | owner (ONE striped table pair accessed per pair over NVLink)
+    multi_gpu_negatives: str = 'synced'
+    multi_gpu_merge: Any = 'sum'       # synced mode: sum (summed updates; measured best) | mean (model averaging) | weight in (0, 1]
 
     def fused_optimizer_kind(self) -> str:
         """'sgd' or 'adam': which kernel the fused engine runs for this config."""

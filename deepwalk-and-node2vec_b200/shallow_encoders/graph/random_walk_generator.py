@@ -42,6 +42,13 @@ class RandomWalk(ABC):
     def csr(self) -> CSRGraph:
         if self._csr is None:
             self._csr = CSRGraph.from_networkx(self._graph, device=self._device)
+        if not getattr(self, '_degrees_checked', False):
+            # the reference cannot walk out of a node without neighbours (`random.choices` on an empty population raises IndexError,
+            # random_walk_generator.py:68,113); the kernels would park the walk there and feed self-pairs to SGNS.  Refuse such graphs once.
+            self._degrees_checked = True
+            c = self._csr
+            if self._length > 1 and c.n_nodes > 0 and int((c.rowptr[1:] - c.rowptr[:-1]).min().item()) == 0:
+                raise IndexError('the graph has nodes without neighbours: a random walk cannot leave them (the reference raises here too)')
         return self._csr
 
     @property

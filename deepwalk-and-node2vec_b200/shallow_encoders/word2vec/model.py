@@ -47,17 +47,30 @@ class W2VBase(nn.Module):
         device = torch.device('cuda' if device is None else device)
         self._sharded = None
         if shard is not None and shard.get('world', 1) > 1:
-            from shallow_encoders.word2vec.sharded import ShardedTable
+            from shallow_encoders.word2vec.sharded import ReplicatedTable, ShardedTable
             bound = (6.0 / (vocab_size + embedding_size)) ** 0.5           # xavier_uniform_ (reference :26-27)
-            self._sharded = tuple(ShardedTable(vocab_size, embedding_size, device, shard['rank'], shard['world'], shard['exchange'])
+            # 'synced': a working copy per GPU + row-sharded masters, synchronised after every step (reference-exact global negatives at
+            # NVLink bulk rate); otherwise ONE striped pair that the kernels read / update over NVLink per pair
+            make = ReplicatedTable if shard.get('mode') == 'synced' else ShardedTable
+            self._sharded = tuple(make(vocab_size, embedding_size, device, shard['rank'], shard['world'], shard['exchange'])
                                   for _ in range(2))
             for k, t in enumerate(self._sharded):
                 t.fill_uniform(bound, int(shard.get('seed', 0)) * 2 + k)
+            self._publish(device)
             return
         self._input_embedding = nn.Embedding(vocab_size, embedding_size, device=device)
         self._output_embedding = nn.Embedding(vocab_size, embedding_size, device=device)
         torch.nn.init.xavier_uniform_(self._input_embedding.weight)
         torch.nn.init.xavier_uniform_(self._output_embedding.weight)
+
+    @staticmethod
+    def _publish(device) -> None:
+        """Every rank has written the stripes it owns: nobody may gather from, or red.add into, a peer's stripes before that peer's
+        fill / load kernel has run (fresh cuMemCreate memory is not zeroed, and the owner's plain stores would overwrite early updates)."""
+        import torch.distributed as dist
+        torch.cuda.synchronize(device)
+        if dist.is_available() and dist.is_initialized():
+            dist.barrier()
 
     @property
     def input_embedding(self) -> torch.Tensor:
@@ -93,8 +106,12 @@ class W2VBase(nn.Module):
     def _load_from_state_dict(self, state_dict, prefix, *args, **kwargs):
         if self._sharded is None:
             return super()._load_from_state_dict(state_dict, prefix, *args, **kwargs)
-        self._sharded[0].load_owned(state_dict[prefix + '_input_embedding.weight'])
-        self._sharded[1].load_owned(state_dict[prefix + '_output_embedding.weight'])
+        for table, key in zip(self._sharded, ('_input_embedding.weight', '_output_embedding.weight')):
+            if hasattr(table, 'load_owned'):
+                table.load_owned(state_dict[prefix + key])
+            else:
+                table.load(state_dict[prefix + key])
+        self._publish(self._sharded[0].device)
 
     def renorm_(self, inputs: Optional[torch.Tensor] = None, outputs: Optional[torch.Tensor] = None) -> None:
         """`nn.Embedding(max_norm=...)` (reference :22-23; configs/w2v_sg_abcde.yaml:7) renormalises the rows it looks up, in

@@ -22,9 +22,10 @@ An existing experiment directory is replaced without the reference's interactive
 
 Several GPUs (not in the reference, whose YAMLs all say `devices: '1'`): launch under torchrun, one process per GPU,
     python -m torch.distributed.run --nproc-per-node G --master-addr 127.0.0.1 tools/train.py --config-name=... train.engine=fused
-Both tables then exist ONCE, striped over the G HBMs (shallow_encoders/word2vec/sharded.py); every rank generates walks
-rank, rank+G, ... of each epoch and runs the fused kernel on the shared tables (Hogwild across GPUs, barrier per epoch);
-rank 0 writes the checkpoints (same state-dict keys, dense tensors).
+Every rank generates walks rank, rank+G, ... of each epoch.  train.multi_gpu_negatives=synced (default): each GPU trains a working copy
+with the reference's global negative draw and after every mini-batch ONE kernel per table sums the updates into row-sharded masters and
+writes the rows back over NVLink (csrc/replica.cu).  global | local | owner: both tables exist ONCE, striped over the G HBMs, and the
+fused kernel reads / updates peer rows per pair (Hogwild across GPUs, barrier per epoch).  Rank 0 writes the checkpoints.
 """
 import argparse
 import json
@@ -82,6 +83,8 @@ def train(cfg, keep: bool = False, quiet: bool = False):
         torch.distributed.barrier()
 
     dataset = cfg.datamodule.instantiate_dataset()
+    if shard is not None:
+        shard['mode'] = 'synced' if (not cfg.train.local_negatives and cfg.train.multi_gpu_negatives == 'synced') else 'striped'
     trainer = cfg.instantiate_trainer(dataset=dataset, shard=shard)
     scalars = open(os.path.join(dirs['tb_logs'], 'scalars.jsonl'), 'a') if rank == 0 else None
 
@@ -141,7 +144,7 @@ def fit_fused(cfg, dataset, trainer, end_of_epoch, rank: int = 0, world: int = 1
         tokens = dataset.epoch_tokens(rank=rank, world=world)[:, :cfg.datamodule.max_length]
         stats.zero_()
         share = -(-cfg.datamodule.batch_size // world)             # this rank's walks of one global batch
-        mode = 'local' if getattr(cfg.train, 'local_negatives', False) else getattr(cfg.train, 'multi_gpu_negatives', 'global')
+        mode = 'local' if getattr(cfg.train, 'local_negatives', False) else getattr(cfg.train, 'multi_gpu_negatives', 'synced')
         mode = mode if world > 1 else 'global'
         n_cen = tokens.shape[1] - 2 * r
         n_min = len(dataset) // world                              # walks every rank is guaranteed to have this epoch
@@ -162,7 +165,13 @@ def fit_fused(cfg, dataset, trainer, end_of_epoch, rank: int = 0, world: int = 1
             else:
                 trainer.fused_step(chunk, r, lr_batch / pairs, row_offset=dataset.row_offset, seed=seed * world + rank, stats=stats,
                                    local_negatives=mode == 'local')
+                if mode == 'synced' and lo + share <= n_min:     # every rank reaches this together (the sync contains barriers)
+                    from shallow_encoders.word2vec.sharded import sync_replicated
+                    sync_replicated(trainer.model.tables, merge=cfg.train.multi_gpu_merge)
             trainer.global_step += 1
+        if mode == 'synced':                                     # a ragged last batch is folded in here
+            from shallow_encoders.word2vec.sharded import sync_replicated
+            sync_replicated(trainer.model.tables, merge=cfg.train.multi_gpu_merge)
         if world > 1:
             torch.distributed.all_reduce(stats)
         s = stats.tolist()

@@ -289,13 +289,15 @@ int se_host_walk_sgns_step_sharded(const int64_t *rowptr, const int32_t *col, co
  * copy, physically in GPU g's HBM, mapped into every process through the se_shard_* calls above); the single-GPU kernels
  * train on segment `rank`.  Rank r owns the master of the element chunk se_replica_chunk returns (contiguous rows).
  * se_replica_sync, enqueued by EVERY rank between two inter-GPU barriers, does for the chunk the caller owns
- *     mode 0:  master' = master + sum_g (copy_g - master);  every copy_g <- master'     (fused reduce-scatter + all-gather)
+ *     mode 0:  master' = master + beta * sum_g (copy_g - master);  every copy_g <- master'   (fused reduce-scatter + all-gather)
  *     mode 1:  master <- copy_rank                                                     (after initialisation)
  *     mode 2:  every copy_g <- master                                                  (after loading a checkpoint)
- * which equals synchronous data-parallel SGD with SUMMED updates, on one model.  `master` holds hi_elem - lo_elem floats.
+ * beta = 1 is synchronous data-parallel SGD with SUMMED updates (right while a step touches a row about once), beta = 1 / world
+ * is local SGD with model averaging (right when every GPU updates every row many times per step); 0 < beta <= 1.
+ * `master` holds hi_elem - lo_elem floats.
  * ---------------------------------------------------------------------------------------------------------- */
 int se_replica_chunk(int64_t n_elems, int world, int rank, int64_t *lo_elem, int64_t *hi_elem);
-int se_replica_sync(float *base, int64_t stride_elems, int world, int rank, int64_t n_elems, float *master, int mode,
+int se_replica_sync(float *base, int64_t stride_elems, int world, int rank, int64_t n_elems, float *master, int mode, float beta,
                     void *stream);
 
 /* Input hygiene for token / node ids that come from outside the library (the reference's nn.Embedding raises IndexError on an

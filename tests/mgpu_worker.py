@@ -206,7 +206,7 @@ def main():
         mine_in, mine_out = r_in.to_tensor().double() - before_in, r_out.to_tensor().double() - before_out
         assert float(mine_in.abs().max()) > 1e-4
         dist.all_reduce(mine_in); dist.all_reduce(mine_out)                      # NCCL cross-check of the summed updates
-        sync_replicated([r_in, r_out])
+        sync_replicated([r_in, r_out], merge='sum')
         torch.cuda.synchronize()
         assert float((r_in.to_tensor().double() - (before_in + mine_in)).abs().max()) < 2e-6
         assert float((r_out.to_tensor().double() - (before_out + mine_out)).abs().max()) < 2e-6

@@ -363,7 +363,8 @@ def test_two_gpus_train_one_pair_of_tables_over_nvlink():
 
 
 @pytest.mark.skipif(torch.cuda.device_count() < 2, reason='needs two GPUs on one NVLink/NVSwitch node')
-def test_train_cli_on_two_gpus_matches_single_gpu_accuracy(tmp_path):
+@pytest.mark.parametrize('mode', ['owner', 'synced'])
+def test_train_cli_on_two_gpus_matches_single_gpu_accuracy(tmp_path, mode):
     """`torchrun tools/train.py ... train.engine=fused train.multi_gpu_negatives=owner` on 2 GPUs trains ONE striped model
     (positives on the home GPU, negatives on the GPU that owns their rows); rank 0's checkpoint has the
     reference's state-dict keys and its downstream node-classification accuracy (tools/graph_model_downstream_classification.py
@@ -373,7 +374,7 @@ def test_train_cli_on_two_gpus_matches_single_gpu_accuracy(tmp_path):
     from tools.downstream import node_classification
     pkg = os.path.join(ROOT, 'deepwalk-and-node2vec_b200')
     over = ['train.engine=fused', 'train.fused_lr=60.0', 'train.max_epochs=8', 'train.scheduler.step_size=4', 'model.embedding_size=128',
-            'datamodule.additional_parameters.method_params.q=0.5', 'train.multi_gpu_negatives=owner', f'path.output_dir={tmp_path}']
+            'datamodule.additional_parameters.method_params.q=0.5', f'train.multi_gpu_negatives={mode}', f'path.output_dir={tmp_path}']
     env = dict(os.environ, PYTHONPATH=os.pathsep.join([pkg, ROOT]))
     cmd = [sys.executable, '-m', 'torch.distributed.run', '--nnodes=1', '--nproc-per-node=2', '--master-addr', '127.0.0.1',
            '--master-port', str(29900 + os.getpid() % 90), os.path.join(pkg, 'tools', 'train.py'), '--config-name=sge_sg_cora', *over]

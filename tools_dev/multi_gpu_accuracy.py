@@ -4,6 +4,7 @@ engine in three ways and compares downstream node-classification accuracy of W_i
     G GPUs, one striped table pair, reference (global) negatives
     G GPUs, one striped table pair, LOCAL negatives (each GPU draws among the rows it owns; bench.py's default)
     G GPUs, one striped table pair, reference negatives, OWNER-COMPUTES (every GPU processes the negatives whose rows it owns)
+    G GPUs, SYNCED working copies + row-sharded masters, reference negatives (bench.py's N > 1 headline: csrc/replica.cu)
 Run under torchrun with G >= 2 ranks (rank 0 also does the 1-GPU run); writes gpurun_out/multi_gpu_accuracy.json.
 
     python -m torch.distributed.run --nproc-per-node 2 --master-addr 127.0.0.1 tools_dev/multi_gpu_accuracy.py
@@ -22,7 +23,7 @@ import torch.distributed as dist
 
 from shallow_encoders import _native as nat
 from shallow_encoders.graph.synthetic import sbm_graph_device
-from shallow_encoders.word2vec.sharded import ShardedTable, make_exchange, sgns_update_walks_owner_computes
+from shallow_encoders.word2vec.sharded import ReplicatedTable, ShardedTable, make_exchange, sgns_update_walks_owner_computes, sync_replicated
 
 ap = argparse.ArgumentParser()
 ap.add_argument('--nodes', type=int, default=200_000)
@@ -37,6 +38,8 @@ ap.add_argument('--neg', type=int, default=5)
 ap.add_argument('--epochs', type=int, default=2)
 ap.add_argument('--lr', type=float, default=0.025)
 ap.add_argument('--batch-walks', type=int, default=65536)
+ap.add_argument('--arms', default='one,global,local,owner,synced')
+ap.add_argument('--merge', default='sum', help='synced arm: merge rules to try (mean | sum | weight), comma separated')
 ap.add_argument('--owner-micro-walks', type=int, default=0, help='owner-computes arm: interleave positives / negatives in slices of this many walks')
 a = ap.parse_args()
 
@@ -59,7 +62,7 @@ def barrier():
         torch.cuda.synchronize()
 
 
-def train(w_in, w_out, r, g, local_neg, owner=False):
+def train(w_in, w_out, r, g, local_neg, owner=False, synced=False, merge='sum'):
     """Epochs of walks -> fused update; rank r of g takes walks r, r+g, ... of every batch."""
     gen = torch.Generator()
     gen.manual_seed(1)
@@ -79,6 +82,8 @@ def train(w_in, w_out, r, g, local_neg, owner=False):
             else:
                 nat.sgns_update_walks(w_in, w_out, walks, a.radius, a.neg, 1, lr, seed=11, centre_id_base=base * n_cen, stats=stats,
                                       local_negatives=local_neg)
+            if synced:
+                sync_replicated([w_in, w_out], merge=merge)
         s = stats.tolist()
         losses.append((s[0] + s[1]) / max(s[4], 1))
     return losses
@@ -97,7 +102,8 @@ def evaluate(w_in_dense):
 
 out = {'config': vars(a), 'world': world}
 # ---- 1 GPU, reference negatives (rank 0 only) ---------------------------------------------------------------------------
-if rank == 0:
+arms = set(a.arms.split(','))
+if rank == 0 and 'one' in arms:
     w_in = torch.empty((vocab, a.emb), device=dev); w_out = torch.empty((vocab, a.emb), device=dev)
     nat.table_fill_uniform(w_in, bound, 101); nat.table_fill_uniform(w_out, bound, 102)
     t0 = time.time()
@@ -111,13 +117,18 @@ barrier()
 # ---- G GPUs, striped tables ---------------------------------------------------------------------------------------------
 if world > 1:
     ex = make_exchange(rank, world)
-    for name, local_neg, owner in (('striped_global_negatives', False, False), ('striped_local_negatives', True, False),
-                                   ('striped_owner_computes_negatives', False, True)):
-        s_in, s_out = ShardedTable(vocab, a.emb, dev, rank, world, ex), ShardedTable(vocab, a.emb, dev, rank, world, ex)
+    plan = [('global', 'striped_global_negatives', False, False, False, None), ('local', 'striped_local_negatives', True, False, False, None),
+            ('owner', 'striped_owner_computes_negatives', False, True, False, None)]
+    plan += [('synced', f'synced_copies_global_negatives_merge_{mg}', False, False, True, mg) for mg in a.merge.split(',')]
+    for key, name, local_neg, owner, synced, merge in plan:
+        if key not in arms:
+            continue
+        make = ReplicatedTable if synced else ShardedTable
+        s_in, s_out = make(vocab, a.emb, dev, rank, world, ex), make(vocab, a.emb, dev, rank, world, ex)
         s_in.fill_uniform(bound, 101); s_out.fill_uniform(bound, 102)
         barrier()
         t0 = time.time()
-        losses = train(s_in, s_out, rank, world, local_neg, owner)
+        losses = train(s_in, s_out, rank, world, local_neg, owner, synced, merge)
         barrier()
         secs = time.time() - t0
         if rank == 0:
