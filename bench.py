@@ -92,17 +92,19 @@ def parse_args():
     ap.add_argument('--seed', type=int, default=0)
     ap.add_argument('--kernel', default='window', choices=['window', 'context'],
                     help='window: context rows resident in shared memory while in the window; context: gathered per pair')
-    ap.add_argument('--multi', default='synced', choices=['synced', 'sharded', 'replicas', 'a2a'],
+    ap.add_argument('--multi', default='sharded', choices=['sharded', 'synced', 'hybrid', 'replicas', 'a2a'],
                     help='N > 1: synced = the reference\'s global negative draw on per-GPU working copies + row-sharded masters, one fused '
                          'reduce-scatter/all-gather kernel over peer memory per step (product, reference-exact draw); sharded = one striped table '
                          'pair gathered / red.added per pair over NVLink (capacity mode; --negatives local|global|owner); a2a = the NCCL all-to-all '
-                         'baseline; replicas = NCCL all-reduce averaging')
-    ap.add_argument('--merge', default='sum', help='--multi synced: how the GPUs\' updates of a step combine in the sync kernel: mean (local SGD with '
-                    'model averaging), sum (synchronous SGD with summed updates; default, accuracy-checked on 2 and 8 GPUs) or a weight in (0, 1]')
+                         'baseline; replicas = NCCL all-reduce averaging; hybrid = W_out ONE striped table updated by the GPU that owns each negative row '
+                         '(owner-computes, reference draw, no staleness), W_in a working copy per GPU merged by the sync kernel every step')
+    ap.add_argument('--merge', default=None, help='--multi synced: how the GPUs\' updates of a step combine in the sync kernel: mean (local SGD with '
+                    'model averaging), sum (synchronous SGD with summed updates), stable (weight min(1, 2/G): cannot overshoot) or a weight in (0, 1]; '
+                    'default: stable for --multi synced, sum for --multi hybrid (only W_in is merged there)')
     ap.add_argument('--a2a-micro-walks', type=int, default=8192, help='a2a baseline: walks per exchange micro-batch')
     ap.add_argument('--negatives', default='auto', choices=['auto', 'local', 'global', 'owner'],
-                    help='sharded tables: local (auto) = draw negatives among the rows the GPU owns; global = reference draw over the whole table, rows '
-                         'fetched over NVLink; owner = reference draw, every GPU processes the negatives it owns for all GPUs\' centres')
+                    help='sharded tables: owner (auto) = the reference\'s draw over the whole table, every GPU processes the negatives whose rows it owns for all '
+                         'GPUs\' centres; local = draw negatives among the rows the GPU owns; global = reference draw, rows fetched over NVLink per pair')
     ap.add_argument('--tables', default='torch', choices=['torch', 'vmm'], help='N = 1: torch tensor or a 1-shard VMM table')
     ap.add_argument('--extra-steps', type=int, default=5, help='sharded: steps of the other negative mode timed after the main run')
     ap.add_argument('--no-cpu-baseline', action='store_true')
@@ -118,12 +120,16 @@ def parallelism(a, n_gpus):
         return 'single GPU' + (' (tables in a 1-shard VMM mapping)' if a.tables == 'vmm' else '')
     if a.multi == 'replicas':
         return f'dp{n_gpus}: walks sharded by id, table replicas averaged by NCCL all-reduce every step'
+    if a.multi == 'hybrid':
+        return (f'dp{n_gpus}: walks sharded by id (replicated CSR) and all-gathered (4 B per token); W_out is ONE table row-striped over {n_gpus} HBMs and every '
+                f'negative pair (reference draw over the whole table) is computed by the GPU that owns the negative row, against its own HBM; W_in is a working '
+                f'copy per GPU + row-sharded masters merged every step by ONE kernel over NVLink peer memory (csrc/replica.cu); positives on the walk\'s home GPU')
     if a.multi == 'synced':
         return (f'dp{n_gpus}: walks sharded by id (replicated CSR, no communication); both tables row-sharded into {n_gpus} master chunks (rows by node id) '
                 f'+ one working copy per GPU; every GPU runs the single-GPU fused kernel with the reference\'s uniform draw over the WHOLE table, then '
                 f'ONE kernel per table sums the updates of all copies into the masters and writes the rows back over NVLink peer memory '
                 f'(fused reduce-scatter + all-gather, csrc/replica.cu); no NCCL on the data path')
-    neg = 'local' if a.negatives == 'auto' else a.negatives
+    neg = ('local' if a.multi == 'a2a' else 'owner') if a.negatives == 'auto' else a.negatives
     if a.multi == 'a2a':
         return (f'dp{n_gpus} NCCL BASELINE: tables row-sharded by row % {n_gpus}; per micro-batch of {a.a2a_micro_walks} walks: unique ids -> '
                 f'all_to_all ids / rows -> se_sgns_grad on compact tables -> all_to_all gradients -> owners apply; negatives '
@@ -142,7 +148,8 @@ def workload_config(a, n_gpus):
         'walk_len': a.walk_len, 'walks_per_node': a.walks_per_node, 'walks_per_step_per_gpu': a.walks_per_step,
         'emb': a.emb, 'context_radius': a.radius, 'negatives': a.neg,
         'negative_sampling': ('uniform over the rows owned by the GPU (walks are dealt to GPUs by id)'
-                              if (n_gpus > 1 and a.multi in ('sharded', 'a2a') and a.negatives in ('auto', 'local')) else 'uniform (reference)'),
+                              if (n_gpus > 1 and ((a.multi == 'a2a' and a.negatives in ('auto', 'local')) or (a.multi == 'sharded' and a.negatives == 'local')))
+                              else 'uniform (reference)'),
         'table_sync': (f'every step: master += beta * sum over GPUs of (working copy - master), written back to all copies; merge = {a.merge}'
                        if n_gpus > 1 and a.multi == 'synced' else None),
         'optimizer': 'in-place SGD (Hogwild, red.global.add.v4.f32)' if a.scatter == 'red' else 'in-place SGD (Hogwild, plain stores)',
@@ -357,10 +364,13 @@ def run_b200(a, rank, local_rank, world):
     sharded = (world > 1 and a.multi == 'sharded') or (world == 1 and a.tables == 'vmm')
     a2a = world > 1 and a.multi == 'a2a'
     synced = world > 1 and a.multi == 'synced'
+    hybrid = world > 1 and a.multi == 'hybrid'
+    if a.merge is None:
+        a.merge = 'sum' if a.multi == 'hybrid' else 'stable'
     ex = None
     neg_mode = 'global'
     if (sharded or a2a) and world > 1:
-        neg_mode = 'local' if a.negatives == 'auto' else a.negatives
+        neg_mode = ('local' if a2a else 'owner') if a.negatives == 'auto' else a.negatives
         assert not (a2a and neg_mode == 'owner'), 'the NCCL baseline has no owner-computes mode'
     local_neg = neg_mode == 'local'
     if a2a:
@@ -368,16 +378,15 @@ def run_b200(a, rank, local_rank, world):
         tables = RowShardedTables(vocab, a.emb, rank, world, dev)
         tables.fill_uniform(bound, a.seed + 101, a.seed + 102)
         w_in = w_out = None
-    elif sharded or synced:
+    elif sharded or synced or hybrid:
         # Peer-mapped tables need CUDA VMM handle export between processes (POSIX fds over unix sockets).  If the platform
         # refuses that on ANY rank, every rank drops to the replica mode (still the same CUDA kernels) and the line says so.
         from shallow_encoders.word2vec.sharded import ReplicatedTable, ShardedTable, make_exchange
         w_in = w_out = None
         try:
             ex = make_exchange(rank, world)
-            make = ReplicatedTable if synced else ShardedTable
-            w_in = make(vocab, a.emb, dev, rank, world, ex)
-            w_out = make(vocab, a.emb, dev, rank, world, ex)
+            w_in = (ReplicatedTable if (synced or hybrid) else ShardedTable)(vocab, a.emb, dev, rank, world, ex)
+            w_out = (ReplicatedTable if synced else ShardedTable)(vocab, a.emb, dev, rank, world, ex)
             ok, why = 1, ''
         except Exception as e:   # noqa: BLE001
             ok, why = 0, repr(e)
@@ -391,7 +400,7 @@ def run_b200(a, rank, local_rank, world):
             for t in (w_in, w_out):
                 if t is not None:
                     t.close()
-            sharded, synced, local_neg, neg_mode = False, False, False, 'global'
+            sharded, synced, hybrid, local_neg, neg_mode = False, False, False, False, 'global'
             fallback_note = f'peer-mapped tables unavailable ({why or "on another rank"}): ran --multi replicas'
             a.multi = 'replicas'
             w_in = torch.empty((vocab, a.emb), dtype=torch.float32, device=dev)
@@ -399,22 +408,26 @@ def run_b200(a, rank, local_rank, world):
     else:
         w_in = torch.empty((vocab, a.emb), dtype=torch.float32, device=dev)
         w_out = torch.empty((vocab, a.emb), dtype=torch.float32, device=dev)
-    if synced:
+    if synced or hybrid:
         w_in.fill_uniform(bound, a.seed + 101)                # every rank fills its working copy and adopts its master chunk
-        w_out.fill_uniform(bound, a.seed + 102)
+        if synced:
+            w_out.fill_uniform(bound, a.seed + 102)
+        else:
+            nat.table_fill_uniform(w_out, bound, a.seed + 102)
+            neg_mode = 'owner'
     elif not a2a:
         nat.table_fill_uniform(w_in, bound, a.seed + 101)     # same content on every rank / for every sharding
         nat.table_fill_uniform(w_out, bound, a.seed + 102)
     if world > 1:
         torch.cuda.synchronize()
         dist.barrier()                                        # nobody touches a peer's rows before they are initialised
-    T = {'w_in': w_in, 'w_out': w_out, 'synced': synced, 'sharded': sharded}
+    T = {'w_in': w_in, 'w_out': w_out, 'synced': synced, 'sharded': sharded, 'hybrid': hybrid}
     flags = nat.SCATTER_RED if a.scatter == 'red' else nat.SCATTER_STORE
     if a.kernel == 'context':
         flags |= nat.NO_WINDOW
 
     # ---- schedule: shuffled node list, walks_per_node consecutive walks per node (graph/datasets.py:45,76) -----
-    total_steps = a.warmup + 2 * a.steps + 2 + 2 * (a.extra_steps + 1)
+    total_steps = a.warmup + 2 * a.steps + 2 + 3 * (a.extra_steps + 1)
     n_walks = a.walks_per_step
     g_cpu = torch.Generator()
     g_cpu.manual_seed(a.seed)
@@ -444,9 +457,9 @@ def run_b200(a, rank, local_rank, world):
         if record:
             s0, s1 = ev(), ev()
             s0.record()
-        if T['synced']:
+        if T['synced'] or T['hybrid']:
             from shallow_encoders.word2vec.sharded import sync_replicated
-            sync_replicated([T['w_in'], T['w_out']], merge=a.merge)
+            sync_replicated([T['w_in'], T['w_out']] if T['synced'] else [T['w_in']], merge=a.merge)
         else:
             dist.all_reduce(T['w_in'], op=dist.ReduceOp.AVG)
             dist.all_reduce(T['w_out'], op=dist.ReduceOp.AVG)
@@ -491,6 +504,7 @@ def run_b200(a, rank, local_rank, world):
             stats.zero_()
             nat.walk(csr, scratch['starts'], a.walk_len, a.p, a.q, True, nat.RULE_REFERENCE, a.seed, walk_id_base=base, out=walks)
             sgns_stage(base, step, neg_mode)
+            sync_tables()
             stats_host.copy_(stats)
             torch.cuda.synchronize()
             return
@@ -556,39 +570,59 @@ def run_b200(a, rank, local_rank, world):
 
     # ---- the other multi-GPU modes, a few steps each, reported beside the headline ---------------------------------
     other = None
-    if (sharded or a2a or synced) and world > 1 and a.extra_steps > 0:
-        names = {'local': 'striped tables, negatives among the rows the GPU owns (changed sampler; per-pair NVLink traffic 0.2 rows)',
+    if (sharded or a2a or synced or hybrid) and world > 1 and a.extra_steps > 0:
+        names = {'local': 'striped tables, negatives among the rows the GPU owns (GraphVite-style partitioned sampler: not the reference\'s per-pair draw; '
+                          'accuracy = 1 GPU at 8 GPUs, profiles/r02_multi_gpu.md)',
                  'global': 'striped tables, reference draw, negative rows fetched / red.added over NVLink per pair',
-                 'owner': 'striped tables, reference draw, owner-computes (centre rows travel instead of negative rows)'}
-        if synced:
-            # swap the working copies for ONE striped table pair (the capacity mode) and time its negative modes beside the headline
-            from shallow_encoders.word2vec.sharded import ShardedTable
+                 'owner': 'striped tables, reference draw, owner-computes (every negative pair on the GPU that owns the negative row; accuracy = 1 GPU)',
+                 'synced': 'working copy per GPU + row-sharded masters, reference draw, one fused reduce-scatter/all-gather kernel per step, merge = stable '
+                           '(throughput mode: statistically inefficient at this step size on 8 GPUs, profiles/r02_multi_gpu.md)'}
+
+        def swap_tables(kind):
+            """Replace the resident table pair by a freshly initialised one of the other kind (striped <-> working copies)."""
+            from shallow_encoders.word2vec.sharded import ReplicatedTable, ShardedTable
             T['w_in'].close(); T['w_out'].close()
             torch.cuda.empty_cache()
-            T['w_in'] = ShardedTable(vocab, a.emb, dev, rank, world, ex)
-            T['w_out'] = ShardedTable(vocab, a.emb, dev, rank, world, ex)
-            nat.table_fill_uniform(T['w_in'], bound, a.seed + 101)
-            nat.table_fill_uniform(T['w_out'], bound, a.seed + 102)
-            T['synced'], T['sharded'] = False, True
+            make = ReplicatedTable if kind == 'synced' else ShardedTable
+            T['w_in'], T['w_out'] = make(vocab, a.emb, dev, rank, world, ex), make(vocab, a.emb, dev, rank, world, ex)
+            if kind == 'synced':
+                T['w_in'].fill_uniform(bound, a.seed + 101); T['w_out'].fill_uniform(bound, a.seed + 102)
+            else:
+                nat.table_fill_uniform(T['w_in'], bound, a.seed + 101); nat.table_fill_uniform(T['w_out'], bound, a.seed + 102)
+            T['synced'], T['hybrid'], T['sharded'] = kind == 'synced', False, kind != 'synced'
             barrier()
-        modes = ('local', 'global') if a2a else (('local', 'owner') if synced else ('local', 'global', 'owner'))
+
+        main_mode = 'synced' if synced else ('hybrid' if hybrid else neg_mode)
+        if a2a:
+            plan = [m for m in ('local', 'global') if m != main_mode]
+        else:
+            plan = [m for m in ('owner', 'local', 'synced') if m != main_mode]
         other, first = [], a.warmup + 2 * a.steps + 1
-        for mode in [m for m in modes if synced or m != neg_mode]:
-            device_step(first, mode=mode)
+        merge_main = a.merge
+        for mode in plan:
+            if not a2a:
+                want = 'synced' if mode == 'synced' else 'striped'
+                have = 'synced' if T['synced'] else ('striped' if T['sharded'] else 'other')
+                if want != have:
+                    swap_tables(want)
+            a.merge = 'stable' if mode == 'synced' else merge_main
+            step_mode = 'global' if mode == 'synced' else mode
+            device_step(first, mode=step_mode)
             barrier()
             x0, x1 = ev(), ev()
             x0.record()
             for s in range(first + 1, first + 1 + a.extra_steps):
-                device_step(s, mode=mode)
+                device_step(s, mode=step_mode)
             x1.record()
             barrier()
             other_ms = max_over_ranks(x0.elapsed_time(x1))
             other.append({'mode': names[mode], 'value': world * pairs_per_step * a.extra_steps / (other_ms / 1e3), 'unit': UNIT,
                           'steps': a.extra_steps, 'ms_per_step': other_ms / a.extra_steps})
             first += a.extra_steps + 1
+        a.merge = merge_main
 
     def close_tables():
-        if T['sharded'] or T['synced']:
+        if T['sharded'] or T['synced'] or T.get('hybrid'):
             T['w_in'].close(); T['w_out'].close()
         if ex is not None:
             ex.close()
@@ -642,10 +676,12 @@ def run_b200(a, rank, local_rank, world):
     if sharded:
         line['tables'] = {'kind': 'vmm-striped', 'stripe_bytes': w_in.stripe_bytes, 'stripes_per_table': w_in.n_stripes,
                           'bytes_per_gpu': 2 * w_in.n_stripes * w_in.stripe_bytes // world}
-    if synced:
+    if synced or hybrid:
         table_bytes = vocab * a.emb * 4
-        moved = 2 * 2 * table_bytes * (world - 1) / world          # per GPU per direction per step, both tables
-        line['tables'] = {'kind': 'working copy per GPU + row-sharded masters (vmm peer-mapped)', 'bytes_per_gpu': 2 * w_in.seg_bytes + 2 * table_bytes // world}
+        moved = (2 if synced else 1) * 2 * table_bytes * (world - 1) / world          # per GPU per direction per step (both tables / W_in only)
+        line['tables'] = {'kind': ('working copy per GPU + row-sharded masters (vmm peer-mapped)' if synced else
+                                   'W_in: working copy per GPU + row-sharded masters; W_out: one table striped over the GPUs (vmm peer-mapped)'),
+                          'bytes_per_gpu': (2 if synced else 1) * w_in.seg_bytes + 2 * table_bytes // world, 'merge': a.merge}
         line['table_sync'] = {'ms_per_step': sync_ms, 'nvlink_bytes_per_gpu_per_direction': moved,
                               'achieved_gbs_per_direction': (moved / (sync_ms / 1e3) / 1e9) if sync_ms else None,
                               'reference_gbs_per_direction': 770.0, 'reference_source': 'B200_PROFILING.md measured peer copy'}

@@ -191,6 +191,9 @@ def _table(t, name='table'):
 def _same_sharding(si, so):
     if (si is None) != (so is None):
         raise ValueError('w_in and w_out must both be torch tensors or both be ShardedTables')
+    if si is not None and si.world == 1 and so.world > 1:
+        # hybrid: W_in is this GPU's working copy of a ReplicatedTable (a local table to the kernels), W_out one striped table
+        return so
     if si is not None and (si.world, si.rank, si.stripe_rows) != (so.world, so.rank, so.stripe_rows):
         raise ValueError('w_in and w_out must be sharded the same way')
     return si

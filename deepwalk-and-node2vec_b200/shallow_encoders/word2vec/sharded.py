@@ -397,21 +397,25 @@ def device_barrier(device, group=None) -> None:
 
 
 def merge_weight(merge, world: int) -> float:
-    """'sum' -> 1, 'mean' -> 1 / world, or a number in (0, 1]."""
+    """'sum' -> 1, 'mean' -> 1 / world, 'stable' -> min(1, 2 / world), or a number in (0, 1].
+    'stable' is the largest weight for which merging G parallel chains cannot overshoot on a quadratic: a chain that closes a
+    fraction rho of the distance to its optimum moves the merged model by G beta rho, which stays below 2 for every rho <= 1 iff
+    beta <= 2 / G.  'sum' (beta = 1) is exact data-parallel SGD but diverges once G rho > 2 (measured: 8 GPUs, profiles/r02_multi_gpu_accuracy.json)."""
     if merge == 'sum':
         return 1.0
+    if merge == 'stable':
+        return min(1.0, 2.0 / world)
     if merge == 'mean':
         return 1.0 / world
     return float(merge)
 
 
-def sync_replicated(tables, group=None, merge='sum') -> None:
+def sync_replicated(tables, group=None, merge='stable') -> None:
     """End-of-step synchronisation of ReplicatedTables on every rank: barrier (all steps done) -> each rank's fused
     reduce-scatter + all-gather kernels over peer memory -> barrier (all copies written).  world == 1: nothing to do.
-    merge: how the GPUs' updates since the last sync combine -- 'sum' (default; synchronous SGD with summed updates: every GPU's
-    progress counts in full; measured within 0.4 pp of the single-GPU accuracy after 2 epochs on 2 and 8 GPUs,
-    profiles/r02_multi_gpu_accuracy.json), 'mean' (local SGD with model averaging: loses 1 - 1/G of the progress per step; measured
-    far worse), or a weight in (0, 1]."""
+    merge: how the GPUs' updates since the last sync combine (see merge_weight) -- 'stable' (default: weight min(1, 2/G)), 'sum'
+    (synchronous SGD with summed updates: every GPU's progress counts in full; fine on 2 GPUs, diverges on 8 when a step updates
+    every row many times), 'mean' (local SGD with model averaging: loses 1 - 1/G of the progress per step), or a weight in (0, 1]."""
     tables = [t for t in tables if t.world > 1]
     if not tables:
         return

@@ -30,14 +30,15 @@ def test_workload_config_names_the_parallelism():
     a = _args(['--gpus', '8'])
     cfg = bench.workload_config(a, 8)
     assert cfg['nodes'] == 10_000_000 and cfg['edges'] == 250_000_000 and cfg['walk_len'] == 80 and cfg['emb'] == 128
-    # the N > 1 headline keeps the reference's negative distribution (uniform over the WHOLE table), like N = 1
-    assert 'row-sharded' in cfg['parallelism'] and 'reduce-scatter + all-gather' in cfg['parallelism']
+    # the N > 1 headline keeps the reference's negative distribution (uniform over the WHOLE table), like N = 1: owner-computes on striped tables
+    assert 'row-striped' in cfg['parallelism'] and 'owns the negative row' in cfg['parallelism']
     assert cfg['negative_sampling'] == 'uniform (reference)' == bench.workload_config(_args([]), 1)['negative_sampling']
-    a = _args(['--gpus', '8', '--multi', 'sharded'])
+    a = _args(['--gpus', '8', '--negatives', 'local'])
     cfg = bench.workload_config(a, 8)
-    assert 'row-striped' in cfg['parallelism'] and 'rows each GPU owns' in cfg['parallelism']
-    assert 'owned by the GPU' in cfg['negative_sampling']
-    a = _args(['--gpus', '2', '--multi', 'sharded', '--negatives', 'global'])
+    assert 'rows each GPU owns' in cfg['parallelism'] and 'owned by the GPU' in cfg['negative_sampling']
+    a = _args(['--gpus', '8', '--multi', 'synced'])
+    assert 'reduce-scatter + all-gather' in bench.workload_config(a, 8)['parallelism']
+    a = _args(['--gpus', '2', '--negatives', 'global'])
     assert 'uniform (reference)' == bench.workload_config(a, 2)['negative_sampling']
     a = _args(['--gpus', '2', '--multi', 'a2a'])
     assert 'NCCL BASELINE' in bench.workload_config(a, 2)['parallelism']

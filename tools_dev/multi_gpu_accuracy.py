@@ -38,8 +38,8 @@ ap.add_argument('--neg', type=int, default=5)
 ap.add_argument('--epochs', type=int, default=2)
 ap.add_argument('--lr', type=float, default=0.025)
 ap.add_argument('--batch-walks', type=int, default=65536)
-ap.add_argument('--arms', default='one,global,local,owner,synced')
-ap.add_argument('--merge', default='sum', help='synced arm: merge rules to try (mean | sum | weight), comma separated')
+ap.add_argument('--arms', default='one,global,local,owner,synced,hybrid')
+ap.add_argument('--merge', default='stable', help='synced arm: merge rules to try (mean | sum | weight), comma separated')
 ap.add_argument('--owner-micro-walks', type=int, default=0, help='owner-computes arm: interleave positives / negatives in slices of this many walks')
 a = ap.parse_args()
 
@@ -62,7 +62,7 @@ def barrier():
         torch.cuda.synchronize()
 
 
-def train(w_in, w_out, r, g, local_neg, owner=False, synced=False, merge='sum'):
+def train(w_in, w_out, r, g, local_neg, owner=False, synced=False, merge='sum', micro=None):
     """Epochs of walks -> fused update; rank r of g takes walks r, r+g, ... of every batch."""
     gen = torch.Generator()
     gen.manual_seed(1)
@@ -78,12 +78,19 @@ def train(w_in, w_out, r, g, local_neg, owner=False, synced=False, merge='sum'):
             lr = a.lr * (1.0 - 0.5 * epoch / max(a.epochs, 1))
             if owner and walks.shape[0] * g == min(a.batch_walks, order.numel() - lo):      # same decision on every rank
                 sgns_update_walks_owner_computes(w_in, w_out, walks, a.radius, a.neg, 1, lr, 11, (epoch * order.numel() + lo) * n_cen, r, g,
-                                                 stats=stats, micro_walks=a.owner_micro_walks or None)
+                                                 stats=stats, micro_walks=(a.owner_micro_walks or None) if micro is None else micro)
             else:
                 nat.sgns_update_walks(w_in, w_out, walks, a.radius, a.neg, 1, lr, seed=11, centre_id_base=base * n_cen, stats=stats,
                                       local_negatives=local_neg)
-            if synced:
-                sync_replicated([w_in, w_out], merge=merge)
+            mg = merge
+            if isinstance(merge, str) and merge.startswith('warmup:'):      # large-batch practice: ramp the merge weight from 2/G to 1 over K syncs
+                k = float(merge.split(':')[1])
+                n_sync = epoch * (-(-order.numel() // a.batch_walks)) + lo // a.batch_walks
+                mg = min(1.0, 2.0 / g + (1.0 - 2.0 / g) * n_sync / k)
+            if synced is True:
+                sync_replicated([w_in, w_out], merge=mg)
+            elif synced == 'hybrid':
+                sync_replicated([w_in], merge=mg)
         s = stats.tolist()
         losses.append((s[0] + s[1]) / max(s[4], 1))
     return losses
@@ -120,15 +127,17 @@ if world > 1:
     plan = [('global', 'striped_global_negatives', False, False, False, None), ('local', 'striped_local_negatives', True, False, False, None),
             ('owner', 'striped_owner_computes_negatives', False, True, False, None)]
     plan += [('synced', f'synced_copies_global_negatives_merge_{mg}', False, False, True, mg) for mg in a.merge.split(',')]
+    plan += [('hybrid', 'hybrid_w_in_synced_sum_w_out_striped_owner_computes', False, True, 'hybrid', 'sum')]
+    plan += [('ownermicro', 'striped_owner_computes_micro4096', False, True, False, None)]
     for key, name, local_neg, owner, synced, merge in plan:
         if key not in arms:
             continue
-        make = ReplicatedTable if synced else ShardedTable
-        s_in, s_out = make(vocab, a.emb, dev, rank, world, ex), make(vocab, a.emb, dev, rank, world, ex)
+        s_in = (ReplicatedTable if synced else ShardedTable)(vocab, a.emb, dev, rank, world, ex)
+        s_out = (ReplicatedTable if synced is True else ShardedTable)(vocab, a.emb, dev, rank, world, ex)
         s_in.fill_uniform(bound, 101); s_out.fill_uniform(bound, 102)
         barrier()
         t0 = time.time()
-        losses = train(s_in, s_out, rank, world, local_neg, owner, synced, merge)
+        losses = train(s_in, s_out, rank, world, local_neg, owner, synced, merge, micro=(4096 // world) if key == 'ownermicro' else None)
         barrier()
         secs = time.time() - t0
         if rank == 0:
