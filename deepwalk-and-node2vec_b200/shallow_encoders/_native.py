@@ -87,6 +87,9 @@ _SIGNATURES = {
     'se_replica_chunk': (c_int, [c_i64, c_int, c_int, c_p, c_p]),
     'se_replica_sync': (c_int, [c_p, c_i64, c_int, c_int, c_i64, c_p, c_int, c_f32, c_p]),
     'se_table_renorm_rows': (c_int, [c_p, c_int, c_p, c_i64, c_f32, c_p]),
+    'se_softmax_xent': (c_int, [c_p, c_p, c_p, c_i64, c_int, c_f32, c_p, c_p, c_p]),
+    'se_csr_build_scratch_bytes': (c_i64, [c_i64, c_i64, c_int]),
+    'se_csr_build': (c_int, [c_p, c_p, c_p, c_i64, c_i64, c_int, c_p, c_i64, c_p, c_p, c_p, c_p, c_p, c_p]),
     'se_gemm_nt': (c_int, [c_p, c_p, c_i64, c_i64, c_int, c_p, c_p, c_p, c_p]),
     'se_row_inv_norms': (c_int, [c_p, c_i64, c_int, c_p, c_p]),
     'se_cosine_similarity': (c_int, [c_p, c_p, c_i64, c_i64, c_int, c_p, c_p, c_p]),
@@ -640,6 +643,30 @@ def table_renorm_rows(table, rows: torch.Tensor, max_norm: float) -> None:
     _launches += 1
 
 
+def csr_build(src: torch.Tensor, dst: torch.Tensor, n_nodes: int, weights: Optional[torch.Tensor] = None, symmetrize: bool = True):
+    """Device edge list -> (rowptr int64 [n+1], col int32 [nnz], w fp64 [nnz] | None, wcdf fp32 [nnz] | None, max_degree, skipped)
+    with networkx's simple-graph semantics (csrc/ingest.cu); one synchronisation to learn nnz."""
+    global _launches
+    dev = src.device
+    n_edges = src.numel()
+    slots = n_edges * (2 if symmetrize else 1)
+    lib = load()
+    scratch = torch.empty(max(int(lib.se_csr_build_scratch_bytes(n_nodes, n_edges, int(symmetrize))), 16), dtype=torch.uint8, device=dev)
+    rowptr = torch.empty(n_nodes + 1, dtype=torch.int64, device=dev)
+    col = torch.empty(max(slots, 1), dtype=torch.int32, device=dev)
+    w_out = torch.empty(max(slots, 1), dtype=torch.float64, device=dev) if weights is not None else None
+    wcdf = torch.empty(max(slots, 1), dtype=torch.float32, device=dev) if weights is not None else None
+    info = torch.zeros(3, dtype=torch.int64, device=dev)
+    with _on(src):
+        _check(lib.se_csr_build(_ptr(src, torch.int32, 'src'), _ptr(dst, torch.int32, 'dst'), _ptr(weights, torch.float64, 'weights'), n_edges,
+                                int(n_nodes), int(symmetrize), scratch.data_ptr(), scratch.numel(), rowptr.data_ptr(), col.data_ptr(),
+                                _ptr(w_out), _ptr(wcdf), info.data_ptr(), _stream()))
+    _launches += 16
+    nnz, max_degree, skipped = (int(x) for x in info.tolist())
+    skipped &= 0xffffffff
+    return rowptr, col[:nnz].clone(), (w_out[:nnz].clone() if w_out is not None else None), (wcdf[:nnz].clone() if wcdf is not None else None), max_degree, skipped
+
+
 def replica_chunk(n_elems: int, world: int, rank: int):
     """[lo, hi) element range of the flat table whose master lives on `rank` (host arithmetic, no GPU)."""
     lo, hi = c_i64(), c_i64()
@@ -719,6 +746,17 @@ def sgns_step_shared_negatives(w_in: torch.Tensor, w_out: torch.Tensor, inputs: 
     stats[5] += float(batch * n_ctx * n_neg)        # negatives the step stands for
     _launches += 11
     return _stats_dict(stats) if own_stats else None
+
+
+def softmax_xent(logits: torch.Tensor, labels: torch.Tensor, bias: Optional[torch.Tensor], grad_scale: float, loss_sum: Optional[torch.Tensor] = None,
+                 n_correct: Optional[torch.Tensor] = None) -> None:
+    """In place: logits [n, C] (C = 1: binary) -> grad_scale * d loss / d logits; loss / correct counts accumulated."""
+    global _launches
+    n, c = logits.shape
+    with _on(logits):
+        _check(load().se_softmax_xent(_ptr(logits, torch.float32, 'logits'), _ptr(labels, torch.int32, 'labels'), _ptr(bias, torch.float32, 'bias'), n, c,
+                                      float(grad_scale), _ptr(loss_sum, torch.float64, 'loss_sum'), _ptr(n_correct, torch.int32, 'n_correct'), _stream()))
+    _launches += 1
 
 
 def transpose(x: torch.Tensor) -> torch.Tensor:

@@ -103,22 +103,35 @@ class CSRGraph:
                                     symmetric=not graph.is_directed(), names=names, device=device)
 
     @staticmethod
-    def from_edges_device(src: torch.Tensor, dst: torch.Tensor, n_nodes: int, symmetrize: bool = True) -> 'CSRGraph':
-        """Unweighted CSR from a device edge list (torch sort/unique as plumbing; used for the synthetic benchmarks).
-        Removes self loops and duplicate edges; adjacency rows come out ascending, so one array serves both orders."""
-        dev = src.device
-        src, dst = src.to(torch.int64), dst.to(torch.int64)
-        keep = src != dst
-        src, dst = src[keep], dst[keep]
-        if symmetrize:
-            src, dst = torch.cat([src, dst]), torch.cat([dst, src])
-        key = torch.unique(src * n_nodes + dst)            # sorted
-        del src, dst
-        rows = torch.div(key, n_nodes, rounding_mode='floor')
-        col = (key - rows * n_nodes).to(torch.int32)
-        del key
-        deg = torch.bincount(rows, minlength=n_nodes)
-        del rows
-        rowptr = torch.zeros(n_nodes + 1, dtype=torch.int64, device=dev)
-        torch.cumsum(deg, 0, out=rowptr[1:])
-        return CSRGraph(rowptr, col, col, None, None, True, symmetrize, None, int(deg.max().item()))
+    def from_edges_device(src: torch.Tensor, dst: torch.Tensor, n_nodes: int, symmetrize: bool = True,
+                          weights: Optional[torch.Tensor] = None, names: Optional[List[str]] = None) -> 'CSRGraph':
+        """CSR from an edge list in HBM, built by the library's own kernels (`se_csr_build`, csrc/ingest.cu: degree count, scans,
+        bucket fill, per-row bitonic sort, duplicate removal, weight prefix sums) with networkx's simple-graph semantics: self loops
+        dropped, duplicate edges collapse to the LAST occurrence's weight, rows ascending (one array serves as CDF order and as
+        membership order).  `weights`: float per edge (integral values keep the reference's int-weight arithmetic in exact mode)."""
+        from shallow_encoders import _native as nat
+        if not src.is_cuda:
+            raise RuntimeError('from_edges_device needs CUDA tensors: the B200 path has no CPU fallback (use from_arrays / from_networkx on the host)')
+        w64 = weights.to(torch.float64).contiguous() if weights is not None else None
+        rowptr, col, w, wcdf, max_degree, skipped = nat.csr_build(src.to(torch.int32).contiguous(), dst.to(torch.int32).contiguous(), n_nodes,
+                                                                  w64, symmetrize)
+        if skipped:
+            raise IndexError(f'{skipped} edges have an endpoint outside [0, {n_nodes})')
+        w_is_int = bool(w is None or bool((w == w.round()).all().item()))
+        return CSRGraph(rowptr, col, col, w, wcdf, w_is_int, symmetrize, names, max_degree)
+
+    @staticmethod
+    def from_edge_file(path: str, device='cuda', delimiter: Optional[str] = None, prefix: str = 'n', weighted: bool = False) -> 'CSRGraph':
+        """An edge-list text file (`cora.cites` of the reference, graph/datasets.py:199-200: one `cited citing` pair per line) -> CSR on
+        the device.  Node names are `prefix + token` as the reference's CoraDataset names them (`n<paperid>`), node id = lexicographic
+        rank of the name (so embedding row = id + 1); parsing and the name -> id map are host work, everything after is `se_csr_build`."""
+        import pandas as pd
+        ncols = 3 if weighted else 2
+        df = pd.read_csv(path, sep=delimiter if delimiter is not None else r'\s+', header=None, usecols=list(range(ncols)), dtype=str, engine='python')
+        a, b = (prefix + df[0]).str.lower(), (prefix + df[1]).str.lower()
+        names = sorted(set(a) | set(b))
+        index = {n: i for i, n in enumerate(names)}
+        src = torch.tensor([index[x] for x in a], dtype=torch.int32, device=device)
+        dst = torch.tensor([index[x] for x in b], dtype=torch.int32, device=device)
+        w = torch.tensor(df[2].astype(float).values, dtype=torch.float64, device=device) if weighted else None
+        return CSRGraph.from_edges_device(src, dst, len(names), True, w, names)

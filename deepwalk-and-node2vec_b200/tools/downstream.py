@@ -11,6 +11,32 @@ import numpy as np
 from sklearn.linear_model import LogisticRegression
 
 
+def node_classification_device(embedding, itos: List[str], labels: Dict[str, str], split_algorithm, n_experiments: int,
+                               classifier_params: Optional[dict] = None, return_all: bool = False):
+    """The same yardstick with the embedding matrix staying in HBM: `embedding` is a CUDA tensor [V x E] (row 0 = '<unk>' skipped, :116),
+    the splits are the reference's (its split class is applied to the row INDICES, which shuffles exactly like applying it to the rows),
+    the classifier is tools/device_classifier.DeviceLogisticRegression (same objective as sklearn's default LogisticRegression, two
+    tensor-core GEMMs per gradient).  Returns (mean accuracy, best accuracy) [and the per-experiment list]."""
+    import torch
+    from tools.device_classifier import DeviceLogisticRegression
+    x = embedding[1:].to(torch.float32).contiguous()
+    vertices = itos[1:]
+    classes = {c: i for i, c in enumerate(sorted(set(labels.values())))}
+    y_host = np.array([classes[labels[v]] for v in vertices], dtype=np.float32)
+    y = torch.from_numpy(y_host.astype(np.int64)).to(x.device)
+    index = np.arange(len(vertices), dtype=np.int64).reshape(-1, 1)
+    accs = []
+    for i in range(n_experiments):
+        split_algorithm.random_state = i
+        split = split_algorithm(index, y_host)
+        tr = torch.from_numpy(split['X_train'].reshape(-1)).to(x.device)
+        te = torch.from_numpy(split['X_test'].reshape(-1)).to(x.device)
+        clf = DeviceLogisticRegression(**(classifier_params or {})).fit(x[tr], y[tr])
+        accs.append(clf.score(x[te], y[te]))
+    out = (float(np.mean(accs)), float(np.max(accs)))
+    return out + (accs,) if return_all else out
+
+
 def node_classification(embedding: np.ndarray, itos: List[str], labels: Dict[str, str], split_algorithm,
                         n_experiments: int, classifier_params: Optional[dict] = None,
                         features: Optional[Dict[str, np.ndarray]] = None) -> Tuple[float, float]:

@@ -367,6 +367,29 @@ int se_sgns_step_shared_negatives(float *w_in, float *w_out, int64_t vocab, int 
                                   const int64_t *shared, int64_t n_shared, int n_ctx, int n_neg, float lr, float *scratch,
                                   int64_t scratch_floats, double *stats, void *stream);
 
+/* Elementwise half of a logistic-regression gradient for the device-side downstream classifier (the reference fits sklearn's
+ * LogisticRegression on the host, tools/graph_model_downstream_classification.py:85-91): logits fp32 [n x n_cols] (+ bias[n_cols] or
+ * NULL), labels int32 [n].  n_cols == 1: binary logistic (label 1 = positive); else softmax.  ADDS the summed loss to *loss_sum and
+ * the number of correctly classified rows to *n_correct (either may be NULL) and OVERWRITES logits with grad_scale * d loss / d logits.
+ * The two GEMMs around it (X W^T and G^T X) are se_gemm_nt. */
+int se_softmax_xent(float *logits, const int32_t *labels, const float *bias, int64_t n, int n_cols, float grad_scale, double *loss_sum,
+                    int32_t *n_correct, void *stream);
+
+/* ------------------------------------------------------------------------------------------------------------
+ * Graph ingest on the device (csrc/ingest.cu): edge list -> CSR with networkx's semantics for a simple graph -- what the reference
+ * does edge by edge on the host (graph/datasets.py:126-221: nx.Graph.add_edge per line, e.g. cora.cites at :199-200) before
+ * random_walk_generator.py:41-48 re-reads the adjacency on every step.
+ *   src / dst int32 [n_edges] node ids, w fp64 [n_edges] or NULL; symmetrize != 0 stores every edge in both rows (undirected graph);
+ *   self loops and edges with an endpoint outside [0, n_nodes) are dropped (the latter counted in info[2]); duplicate edges collapse
+ *   to one entry with the weight of the LAST occurrence (a repeated add_edge overwrites the attributes).
+ *   Outputs: rowptr_out int64 [n_nodes + 1]; col_out int32 (rows ascending: serves as CDF order and as membership order), w_out fp64 and
+ *   wcdf_out fp32 (per-row inclusive prefix sums; NULL with unweighted input) sized for the worst case n_edges * (symmetrize ? 2 : 1);
+ *   info int64[3] on the device: [0] nnz, [1] max degree, [2] skipped edges.  scratch: se_csr_build_scratch_bytes, 16-byte aligned.
+ * ---------------------------------------------------------------------------------------------------------- */
+int64_t se_csr_build_scratch_bytes(int64_t n_nodes, int64_t n_edges, int symmetrize);
+int se_csr_build(const int32_t *src, const int32_t *dst, const double *w, int64_t n_edges, int64_t n_nodes, int symmetrize, void *scratch,
+                 int64_t scratch_bytes, int64_t *rowptr_out, int32_t *col_out, double *w_out, float *wcdf_out, int64_t *info, void *stream);
+
 /* Table utilities that work on local and sharded tables alike (W2VBase.__init__ xavier_uniform_, word2vec/model.py:22-27;
  * the input_embedding / output_embedding accessors, :29-47).
  *   fill: element i = (2u-1)*bound with u from Philox(seed; i/4) -- independent of the sharding; a rank writes only the

@@ -35,11 +35,9 @@ def test_unsorted_rows_get_a_sorted_copy():
     assert np.array_equal(csr.col_sorted.numpy(), csr2.col.numpy())
 
 
-def test_from_edges_device_dedup_symmetrize():
+def test_from_edges_device_refuses_host_tensors():
+    """Device ingest is a CUDA path (csrc/ingest.cu); host edge lists go through from_arrays / from_networkx."""
+    import pytest
     import torch
-    src = torch.tensor([0, 1, 1, 2, 3, 3, 0])
-    dst = torch.tensor([1, 0, 2, 2, 0, 0, 1])
-    csr = CSRGraph.from_edges_device(src, dst, 4)
-    assert csr.rowptr.tolist() == [0, 2, 4, 5, 6]
-    assert csr.col.tolist() == [1, 3, 0, 2, 1, 0]
-    assert csr.max_degree == 2
+    with pytest.raises(RuntimeError, match='no CPU fallback'):
+        CSRGraph.from_edges_device(torch.tensor([0, 1]), torch.tensor([1, 0]), 2)
