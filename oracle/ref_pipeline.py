@@ -191,9 +191,69 @@ def sgns_only(a):
             'pairs_per_s': pairs / t, 'cores': workers}
 
 
+def walks_only(a):
+    """Node2Vec.walk / DeepWalk.walk steps/s over disjoint start nodes, 1 process or `workers` processes."""
+    from oracle import ref_import
+    if ref_import.reference_root() is None:
+        return {'unavailable': 'reference not available'}
+    ref_import.import_reference()
+    from shallow_encoders.graph.random_walk_generator import random_walk_factory
+    graph, _ = named_graph(a.graph, a.nodes, a.edges, a.seed)
+    nodes = sorted(graph.nodes)
+    params = {'p': a.p, 'q': a.q} if a.method == 'node2vec' else {}
+    _W['gen'] = random_walk_factory(a.method, graph, a.walk_len, params)
+    workers = a.workers or (os.cpu_count() or 1)
+    n_walks = a.walks_per_step * a.steps
+    starts = [nodes[i % len(nodes)] for i in range(n_walks)]
+    t0 = time.perf_counter()
+    if workers == 1 or a.no_pool:
+        _worker_walks((starts, a.seed))
+        used = 1
+    else:
+        import multiprocessing as mp
+        with mp.get_context('fork').Pool(workers) as pool:
+            t0 = time.perf_counter()
+            pool.map(_worker_walks, [(starts[i::workers], a.seed + i) for i in range(workers)])
+        used = workers
+    dt = time.perf_counter() - t0
+    return {'kind': 'reference', 'what': f'{a.method}.walk', 'graph': a.graph, 'nodes': graph.number_of_nodes(), 'walk_len': a.walk_len,
+            'processes': used, 'walk_steps_per_s': n_walks * (a.walk_len - 1) / dt, 'seconds': dt}
+
+
+def dataloader_epoch(a):
+    """The reference's own data path end to end on karate: GraphDataset -> DataLoader(num_workers) -> W2VCollateFunctional ->
+    training_step -> backward -> Adam (num_workers = 8 is the shipped setting and generates 8x the walks)."""
+    from oracle import ref_import
+    if ref_import.reference_root() is None:
+        return {'unavailable': 'reference not available'}
+    ref_import.import_reference()
+    import torch
+    from torch.utils.data import DataLoader
+    from shallow_encoders.word2vec.dataloader.torch_dataset import GraphDataset, W2VCollateFunctional
+    from shallow_encoders.word2vec.model import SkipGram
+    from shallow_encoders.word2vec.trainer import Word2VecTrainer
+    torch.manual_seed(a.seed)
+    ds = GraphDataset('graph_karate_club', context_radius=2,
+                      additional_parameters={'walks_per_node': 64, 'walk_length': 10, 'method': 'node2vec', 'method_params': {'p': 1, 'q': 0.5}})
+    model = SkipGram(vocab_size=len(ds.vocab), embedding_size=2)
+    opt = torch.optim.Adam(model.parameters(), lr=0.1)
+    trainer = Word2VecTrainer(model=model, optimizer=opt, scheduler=None, neg_samples=1, vocab_size=len(ds.vocab))
+    dl = DataLoader(ds, batch_size=64, num_workers=a.workers, collate_fn=W2VCollateFunctional('sg', 2, 256))
+    pairs = rows = 0
+    t0 = time.perf_counter()
+    for _ in range(a.steps):                      # epochs
+        for batch in dl:
+            loss = trainer.training_step(list(batch))
+            opt.zero_grad(); loss['loss'].backward(); opt.step()
+            pairs += batch[1].shape[0] * batch[1].shape[1]; rows += batch[1].shape[0]
+    dt = time.perf_counter() - t0
+    return {'kind': 'reference', 'what': 'GraphDataset + DataLoader + training_step + Adam (karate YAML values)', 'num_workers': a.workers,
+            'epochs': a.steps, 'rows_per_epoch': rows / a.steps, 'pairs_per_s': pairs / dt, 'walk_steps_per_s': rows / 6 * 9 / dt, 'seconds': dt}
+
+
 def parse(argv=None):
     ap = argparse.ArgumentParser()
-    ap.add_argument('--mode', default='pipeline', choices=['pipeline', 'sgns'])
+    ap.add_argument('--mode', default='pipeline', choices=['pipeline', 'sgns', 'walks', 'dataloader'])
     ap.add_argument('--graph', default='powerlaw', choices=['powerlaw', 'karate', 'cora_shape'])
     ap.add_argument('--nodes', type=int, default=100_000)
     ap.add_argument('--edges', type=int, default=2_500_000)
@@ -223,7 +283,7 @@ def main():
     a = parse()
     real_stdout = os.dup(1)
     os.dup2(2, 1)                      # anything libraries print goes to stderr; stdout carries one JSON line
-    out = run(a) if a.mode == 'pipeline' else sgns_only(a)
+    out = {'pipeline': run, 'sgns': sgns_only, 'walks': walks_only, 'dataloader': dataloader_epoch}[a.mode](a)
     os.write(real_stdout, (json.dumps(out) + '\n').encode())
 
 

@@ -14,6 +14,9 @@ KEEP = [
     'lts__t_sectors_srcunit_tex_op_read.sum', 'lts__t_sectors_srcunit_tex_op_red.sum', 'lts__t_sectors_srcunit_tex_op_write.sum',
     'smsp__inst_executed.sum', 'smsp__issue_active.avg.pct_of_peak_sustained_active',
     'sm__throughput.avg.pct_of_peak_sustained_elapsed', 'smsp__thread_inst_executed_per_inst_executed.ratio',
+    'lts__d_atomic_input_cycles_active.avg.pct_of_peak_sustained_elapsed', 'lts__d_atomic_input_cycles_active.max.pct_of_peak_sustained_elapsed',
+    'lts__throughput.avg.pct_of_peak_sustained_elapsed', 'l1tex__throughput.avg.pct_of_peak_sustained_elapsed',
+    'sm__pipe_tensor_cycles_active.avg.pct_of_peak_sustained_active',
     'l1tex__data_bank_conflicts_pipe_lsu_mem_shared.sum', 'smsp__inst_executed_op_shared_ld.sum', 'smsp__inst_executed_op_shared_st.sum',
 ]
 STALL = 'smsp__average_warps_issue_stalled_'
