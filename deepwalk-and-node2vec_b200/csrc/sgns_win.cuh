@@ -113,7 +113,6 @@ sgns_win_kernel(const SgnsArgs a) {
                 if (g * 4 + j < N && lg >= 1 && lg < T) out[j] = neg_row(a, pick_word(wb, j), pick_word(wc, j));
         }
     };
-    int nxt[4] = {0, 0, 0, 0};
 
     int64_t span = (a.n_units + n_groups - 1) / n_groups;
     if (a.whole_seq) span = ((span + a.n_cen - 1) / a.n_cen) * a.n_cen;            // no sequence is split between two groups
@@ -132,7 +131,6 @@ sgns_win_kernel(const SgnsArgs a) {
         for (int j = 0; j <= 2 * r; ++j) enter(j, __ldg(seq + p0 - r + j) + a.row_offset, 0, j);
         cp_async_wait_all();
         int head = 0;                                                              // logical slot of position p - r
-        draw_group(u, 0, nxt);
 
         for (int p = p0; p < p0 + m; ++p, ++u) {
             // the row entering the window for the next centre goes to the free logical slot while this centre is processed
@@ -161,11 +159,11 @@ sgns_win_kernel(const SgnsArgs a) {
             }
 
             for (int g = 0; g < NG; ++g) {
-                // ids of the negatives this lane owns (lane t = negative t - 1) in contexts 4g .. 4g + 3 were resolved one group ago;
-                // resolve the next group's now (Philox + alias-table loads), off the critical path of this group's row gathers
-                int ids[4] = {nxt[0], nxt[1], nxt[2], nxt[3]};
-                if (g + 1 < NG) draw_group(u, g + 1, nxt);
-                else if (p + 1 < p0 + m) draw_group(u + 1, 0, nxt);
+                // ids of the negatives this lane owns (lane t = negative t - 1) in contexts 4g .. 4g + 3.  (Measured and dropped,
+                // profiles/r02_sgns_tuning.md: resolving them one group ahead -- no gain with alias tables, -2 % on S3 through register
+                // pressure; keeping the negative rows of TWO contexts in flight per warp at 12 warps / 165 registers -- 191 ms vs 182 ms.)
+                int ids[4];
+                draw_group(u, g, ids);
 #pragma unroll
                 for (int j = 0; j < 4; ++j) {
                     const int n = g * 4 + j;
