@@ -357,7 +357,12 @@ def run_b200(a, rank, local_rank, world):
     nat.load()
 
     # ---- resident state: replicated CSR, tables ----------------------------------------------------------------
+    t_build = time.perf_counter()
     csr = powerlaw_graph_device(a.nodes, a.edges, a.seed, dev)
+    torch.cuda.synchronize()
+    t_build = time.perf_counter() - t_build
+    print(f'[bench] rank {rank}: graph built on the device in {t_build:.2f} s (se_csr_build: {csr.n_nodes} nodes, {csr.nnz} CSR entries, max degree {csr.max_degree})',
+          file=sys.stderr, flush=True)
     vocab = a.nodes + 1                                   # row 0 = '<unk>' (torch_dataset.py:99-110)
     bound = (6.0 / (vocab + a.emb)) ** 0.5                # xavier_uniform_ (model.py:26-27)
     fallback_note = None
@@ -664,7 +669,7 @@ def run_b200(a, rank, local_rank, world):
         'gpu_launches': launches,
         'clocks': clocks,
         'train_stats': {'loss': (stat_vals[0] + stat_vals[1]) / max(stat_vals[4], 1), 'pairs': stat_vals[4]},
-        'graph': {'n_nodes': csr.n_nodes, 'nnz': csr.nnz, 'max_degree': csr.max_degree},
+        'graph': {'n_nodes': csr.n_nodes, 'nnz': csr.nnz, 'max_degree': csr.max_degree, 'device_build_s': t_build},
         'library': nat.version(),
     }
     if fallback_note:
