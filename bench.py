@@ -271,14 +271,20 @@ def measured_peak():
 
 
 def recorded_traffic():
-    """DRAM bytes per launch of the dominant kernel from the committed `ncu --set full` capture, or None."""
+    """DRAM bytes per launch of the dominant kernel from the committed `ncu --set full` capture -- only while the kernel sources are the
+    ones that were profiled (profiles/sgns_traffic.json carries their hash, tools_dev/make_traffic_json.py); otherwise None."""
     path = os.path.join(ROOT, 'profiles', 'sgns_traffic.json')
-    if os.path.exists(path):
-        try:
-            return json.load(open(path))
-        except Exception:   # noqa: BLE001
-            return None
-    return None
+    try:
+        js = json.load(open(path))
+        import hashlib
+        h = hashlib.sha256()
+        for rel in ('sgns_win.cuh', 'sgns_common.cuh', 'common.cuh', 'sgns_win_g32.cu'):
+            h.update(open(os.path.join(ROOT, 'deepwalk-and-node2vec_b200', 'csrc', rel), 'rb').read())
+        if js.get('kernel_source_sha') != h.hexdigest()[:16]:
+            return {'dram_bytes_per_launch': None, 'source': 'stale: profiles/sgns_traffic.json was captured for other kernel sources; re-run tools_dev/make_traffic_json.py'}
+        return js
+    except Exception:   # noqa: BLE001
+        return None
 
 
 # --------------------------------------------------------------------------------------------------------------
