@@ -1047,8 +1047,8 @@ extern "C" int se_sgns_update_walks_sharded(float *w_in, float *w_out, int64_t v
     // W2VCollateFunctional asserts text_length >= 2r+1 (torch_dataset.py:298)
     SE_REQUIRE(seq_len >= 2 * radius + 1, "Text is too short! [text_length=%d] < [min_text_length=%d]", seq_len, 2 * radius + 1);
     SE_REQUIRE((alias_prob == nullptr) == (alias_idx == nullptr), "se_sgns_update_walks: pass both alias arrays or neither");
-    SE_REQUIRE((flags & ~(SE_SGNS_SCATTER_STORE | SE_SGNS_GENERIC_KERNEL | SE_SGNS_NO_WINDOW | SE_SGNS_WHOLE_SEQUENCES | SE_SGNS_WINDOW_REFRESH)) == 0,
-               "se_sgns_update_walks: unknown flags %d", flags);
+    SE_REQUIRE((flags & ~(SE_SGNS_SCATTER_STORE | SE_SGNS_GENERIC_KERNEL | SE_SGNS_NO_WINDOW | SE_SGNS_WHOLE_SEQUENCES | SE_SGNS_WINDOW_REFRESH |
+                          SE_SGNS_BATCHED_POSITIVES)) == 0, "se_sgns_update_walks: unknown flags %d", flags);
     se::SgnsArgs a{};
     a.w_in = w_in; a.w_out = w_out; a.tokens = tokens; a.alias_prob = alias_prob; a.alias_idx = alias_idx;
     a.stats = stats; a.vocab = vocab; a.emb = emb; a.n_ctx = 2 * radius; a.n_neg = n_neg;
@@ -1059,6 +1059,7 @@ extern "C" int se_sgns_update_walks_sharded(float *w_in, float *w_out, int64_t v
     a.no_window = (flags & SE_SGNS_NO_WINDOW) != 0;
     a.whole_seq = (flags & SE_SGNS_WHOLE_SEQUENCES) != 0;
     a.win_refresh = (flags & SE_SGNS_WINDOW_REFRESH) != 0;
+    a.batch_pos = (flags & SE_SGNS_BATCHED_POSITIVES) != 0;
     a.n_seq = n_seq;
     rc = apply_shard_spec("se_sgns_update_walks_sharded", a, spec);
     if (rc != SE_OK) return rc;

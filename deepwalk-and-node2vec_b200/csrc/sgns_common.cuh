@@ -31,6 +31,7 @@ struct SgnsArgs {
     int whole_seq;                       // window kernel: a group's span is rounded up to whole sequences (SE_SGNS_WHOLE_SEQUENCES)
     int64_t n_seq;                       // MODE_WALK: number of sequences
     int win_refresh;                     // window kernel: re-fetch a resident row when its token is the centre (SE_SGNS_WINDOW_REFRESH)
+    int batch_pos;                       // window kernel, n_neg = 0: the 2r pairs of a centre share one butterfly (SE_SGNS_BATCHED_POSITIVES)
     // MODE_GRAD, row-sparse optimisers (se_sgns_adam_step): rows that receive a gradient are flagged and appended to a list
     int32_t *touch_in, *touch_out;       // [vocab] flags, zero between steps (may be null)
     int32_t *list_in, *list_out;         // touched rows

@@ -131,6 +131,9 @@ sgns_win_kernel(const SgnsArgs a) {
         for (int j = 0; j <= 2 * r; ++j) enter(j, __ldg(seq + p0 - r + j) + a.row_offset, 0, j);
         cp_async_wait_all();
         int head = 0;                                                              // logical slot of position p - r
+        // T == 1 (positives only): a centre is over in a few hundred cycles, so its row is fetched while the previous centre is computed
+        float cen_pre[4] = {0.f, 0.f, 0.f, 0.f};
+        if (T == 1 && ok) load_vec<4>(a.w_in + ((int64_t)__ldg(seq + p0) + a.row_offset) * E + eoff, cen_pre);
 
         for (int p = p0; p < p0 + m; ++p, ++u) {
             // the row entering the window for the next centre goes to the free logical slot while this centre is processed
@@ -139,7 +142,15 @@ sgns_win_kernel(const SgnsArgs a) {
             if (slide) enter(l_in, __ldg(seq + p + r + 1) + a.row_offset, head, 2 * r + 1);
             const int64_t crow = (int64_t)__ldg(seq + p) + a.row_offset;
             float cen[4] = {0.f, 0.f, 0.f, 0.f}, acc[4] = {0.f, 0.f, 0.f, 0.f};
-            if (ok) load_vec<4>(a.w_in + crow * E + eoff, cen);
+            if constexpr (T == 1) {
+#pragma unroll
+                for (int e = 0; e < 4; ++e) cen[e] = cen_pre[e];
+                // (issued after the reductions of all earlier centres, which a later load of the same thread observes; only THIS centre's
+                //  update is missing from it and is added below when the next centre is the same row)
+                if (slide && ok) load_vec<4>(a.w_in + ((int64_t)__ldg(seq + p + 1) + a.row_offset) * E + eoff, cen_pre);
+            } else {
+                if (ok) load_vec<4>(a.w_in + crow * E + eoff, cen);
+            }
             // mid-life refresh: the token that is the centre right now is not a context of this centre, so its resident W_out row can
             // be scattered and re-fetched asynchronously without touching anything in use -- halves how stale a resident copy gets
             // relative to the other groups (matters for frequent tokens, which sit in thousands of windows at once)
@@ -158,77 +169,126 @@ sgns_win_kernel(const SgnsArgs a) {
                 }
             }
 
-            for (int g = 0; g < NG; ++g) {
-                // ids of the negatives this lane owns (lane t = negative t - 1) in contexts 4g .. 4g + 3.  (Measured and dropped,
-                // profiles/r02_sgns_tuning.md: resolving them one group ahead -- no gain with alias tables, -2 % on S3 through register
-                // pressure; keeping the negative rows of TWO contexts in flight per warp at 12 warps / 165 registers -- 191 ms vs 182 ms.)
-                int ids[4];
-                draw_group(u, g, ids);
+            if (T == 1 && G == 32 && a.batch_pos) {
+                // SE_SGNS_BATCHED_POSITIVES, positives only (the owner-computes mode runs the negatives elsewhere): all 2r context rows are resident, so the 2r dots
+                // of a centre are reduced by ONE transposed butterfly (15 + 1 shuffles instead of 2r x 5 dependent ones) and the sigmoids
+                // run side by side, two lanes per context.  The 2r pairs of a centre are scored against the same snapshot of the window;
+                // their updates are then applied one after the other (a row that sits in the window twice receives both).
+                float dot[16];
 #pragma unroll
-                for (int j = 0; j < 4; ++j) {
-                    const int n = g * 4 + j;
-                    if (n < N) {
-                        int l = head + ((n < r) ? n : n + 1);                      // window offset of context n (centre skipped)
+                for (int n = 0; n < 16; ++n) {
+                    float d = 0.f;
+                    if (n < N && ok) {
+                        int l = head + ((n < r) ? n : n + 1);
                         if (l >= RING) l -= RING;
-                        const int ph = phys_s[l];
-                        int tid[T];
-                        float row[T][4];
-                        float dot[P];
+                        const float4 c4 = cur[phys_s[l] * G];
+                        d = fmaf(c4.x, cen[0], fmaf(c4.y, cen[1], fmaf(c4.z, cen[2], c4.w * cen[3])));
+                    }
+                    dot[n] = d;
+                }
+                const float x = transposed_reduce<16, 32>(dot, lg, gmask);               // context n in lanes 2n, 2n + 1
+                float step_mine = 0.f;
+                if ((lg >> 1) < N) {
+                    const float ex = __expf(-x);
+                    const float sig = __fdividef(1.0f, 1.0f + ex);
+                    step_mine = (sig > CLAMP_MIN) ? a.lr * ex * sig : 0.f;               // -lr * dL/ds, loss = -log clamp(sigmoid(x), 1e-6)
+                    if ((lg & 1) == 0) { loss_pos -= __logf(fmaxf(sig, CLAMP_MIN)); cnt_recall += x >= 0.f; cnt_pairs += 1; }
+                }
+                for (int n = 0; n < N; ++n) {
+                    const float step = __shfl_sync(gmask, step_mine, 2 * n, G);
+                    int l = head + ((n < r) ? n : n + 1);
+                    if (l >= RING) l -= RING;
+                    const int ph = phys_s[l];
+                    if (ok) {
+                        const float4 c4 = cur[ph * G];
+                        const float upd[4] = {step * cen[0], step * cen[1], step * cen[2], step * cen[3]};
+                        acc[0] = fmaf(step, c4.x, acc[0]); acc[1] = fmaf(step, c4.y, acc[1]);
+                        acc[2] = fmaf(step, c4.z, acc[2]); acc[3] = fmaf(step, c4.w, acc[3]);
+                        cur[ph * G] = make_float4(c4.x + upd[0], c4.y + upd[1], c4.z + upd[2], c4.w + upd[3]);
+                        float4 d4 = del[ph * G];
+                        d4.x += upd[0]; d4.y += upd[1]; d4.z += upd[2]; d4.w += upd[3];
+                        del[ph * G] = d4;
+                    }
+                }
+            } else {
+                for (int g = 0; g < NG; ++g) {
+                    // ids of the negatives this lane owns (lane t = negative t - 1) in contexts 4g .. 4g + 3.  (Measured and dropped,
+                    // profiles/r02_sgns_tuning.md: resolving them one group ahead -- no gain with alias tables, -2 % on S3 through register
+                    // pressure; keeping the negative rows of TWO contexts in flight per warp at 12 warps / 165 registers -- 191 ms vs 182 ms.)
+                    int ids[4];
+                    draw_group(u, g, ids);
 #pragma unroll
-                        for (int t = 1; t < T; ++t) tid[t] = __shfl_sync(gmask, ids[j], t, G);
-                        row[0][0] = row[0][1] = row[0][2] = row[0][3] = 0.f;
-                        if (ok) { const float4 c4 = cur[ph * G]; row[0][0] = c4.x; row[0][1] = c4.y; row[0][2] = c4.z; row[0][3] = c4.w; }
+                    for (int j = 0; j < 4; ++j) {
+                        const int n = g * 4 + j;
+                        if (n < N) {
+                            int l = head + ((n < r) ? n : n + 1);                      // window offset of context n (centre skipped)
+                            if (l >= RING) l -= RING;
+                            const int ph = phys_s[l];
+                            int tid[T];
+                            float row[T][4];
+                            float dot[P];
 #pragma unroll
-                        for (int t = 1; t < T; ++t) load_row(tid[t], row[t]);
+                            for (int t = 1; t < T; ++t) tid[t] = __shfl_sync(gmask, ids[j], t, G);
+                            row[0][0] = row[0][1] = row[0][2] = row[0][3] = 0.f;
+                            if (ok) { const float4 c4 = cur[ph * G]; row[0][0] = c4.x; row[0][1] = c4.y; row[0][2] = c4.z; row[0][3] = c4.w; }
 #pragma unroll
-                        for (int t = 0; t < P; ++t) {
-                            float d = 0.f;
-                            if (t < T) {
+                            for (int t = 1; t < T; ++t) load_row(tid[t], row[t]);
 #pragma unroll
-                                for (int e = 0; e < 4; ++e) d = fmaf(row[t][e], cen[e], d);
+                            for (int t = 0; t < P; ++t) {
+                                float d = 0.f;
+                                if (t < T) {
+#pragma unroll
+                                    for (int e = 0; e < 4; ++e) d = fmaf(row[t][e], cen[e], d);
+                                }
+                                dot[t] = d;
                             }
-                            dot[t] = d;
-                        }
-                        const float sc = transposed_reduce<P, G>(dot, lg, gmask);
-                        float step_mine = 0.f;
-                        if (owner_t < T) {
-                            const bool positive = owner_t == 0;
-                            const float x = positive ? sc : -sc;                      // loss = -log clamp(sigmoid(x), 1e-6)
-                            const float ex = __expf(-x);
-                            const float sig = __fdividef(1.0f, 1.0f + ex);
-                            const bool live = sig > CLAMP_MIN;
-                            const float gmag = live ? ex * sig : 0.f;                 // |dL/ds| = sigmoid(-x)
-                            step_mine = positive ? a.lr * gmag : -a.lr * gmag;        // -lr * dL/ds
-                            if (owner_rep) {
-                                const float lo = -__logf(fmaxf(sig, CLAMP_MIN));
-                                if (positive) { loss_pos += lo; cnt_recall += x >= 0.f; cnt_pairs += 1; }
-                                else { loss_neg += lo; cnt_fp += x <= 0.f; }
+                            const float sc = transposed_reduce<P, G>(dot, lg, gmask);
+                            float step_mine = 0.f;
+                            if (owner_t < T) {
+                                const bool positive = owner_t == 0;
+                                const float x = positive ? sc : -sc;                      // loss = -log clamp(sigmoid(x), 1e-6)
+                                const float ex = __expf(-x);
+                                const float sig = __fdividef(1.0f, 1.0f + ex);
+                                const bool live = sig > CLAMP_MIN;
+                                const float gmag = live ? ex * sig : 0.f;                 // |dL/ds| = sigmoid(-x)
+                                step_mine = positive ? a.lr * gmag : -a.lr * gmag;        // -lr * dL/ds
+                                if (owner_rep) {
+                                    const float lo = -__logf(fmaxf(sig, CLAMP_MIN));
+                                    if (positive) { loss_pos += lo; cnt_recall += x >= 0.f; cnt_pairs += 1; }
+                                    else { loss_neg += lo; cnt_fp += x <= 0.f; }
+                                }
                             }
-                        }
-                        {   // positive row: update the resident copy and its pending update
-                            const float step = __shfl_sync(gmask, step_mine, 0, G);
-                            const float upd[4] = {step * cen[0], step * cen[1], step * cen[2], step * cen[3]};
+                            {   // positive row: update the resident copy and its pending update
+                                const float step = __shfl_sync(gmask, step_mine, 0, G);
+                                const float upd[4] = {step * cen[0], step * cen[1], step * cen[2], step * cen[3]};
 #pragma unroll
-                            for (int e = 0; e < 4; ++e) acc[e] = fmaf(step, row[0][e], acc[e]);
-                            if (ok) {
-                                cur[ph * G] = make_float4(row[0][0] + upd[0], row[0][1] + upd[1], row[0][2] + upd[2], row[0][3] + upd[3]);
-                                float4 d4 = del[ph * G];
-                                d4.x += upd[0]; d4.y += upd[1]; d4.z += upd[2]; d4.w += upd[3];
-                                del[ph * G] = d4;
+                                for (int e = 0; e < 4; ++e) acc[e] = fmaf(step, row[0][e], acc[e]);
+                                if (ok) {
+                                    cur[ph * G] = make_float4(row[0][0] + upd[0], row[0][1] + upd[1], row[0][2] + upd[2], row[0][3] + upd[3]);
+                                    float4 d4 = del[ph * G];
+                                    d4.x += upd[0]; d4.y += upd[1]; d4.z += upd[2]; d4.w += upd[3];
+                                    del[ph * G] = d4;
+                                }
                             }
-                        }
 #pragma unroll
-                        for (int t = 1; t < T; ++t) {
-                            const float step = __shfl_sync(gmask, step_mine, t << SHIFT, G);
-                            float d[4];
+                            for (int t = 1; t < T; ++t) {
+                                const float step = __shfl_sync(gmask, step_mine, t << SHIFT, G);
+                                float d[4];
 #pragma unroll
-                            for (int e = 0; e < 4; ++e) { acc[e] = fmaf(step, row[t][e], acc[e]); d[e] = step * cen[e]; }
-                            push_row(tid[t], d);
+                                for (int e = 0; e < 4; ++e) { acc[e] = fmaf(step, row[t][e], acc[e]); d[e] = step * cen[e]; }
+                                push_row(tid[t], d);
+                            }
                         }
                     }
                 }
             }
             if (ok) red_vec<4>(a.w_in + crow * E + eoff, acc, a.sys_scope);
+            if constexpr (T == 1) {
+                if (slide && (int64_t)__ldg(seq + p + 1) + a.row_offset == crow) {
+#pragma unroll
+                    for (int e = 0; e < 4; ++e) cen_pre[e] += acc[e];
+                }
+            }
             // slide: the oldest position leaves the window.  Its pending update is scattered now (even if other positions alias
             // the slot: updates never wait longer than one window length); the slot is freed when no alias is left.
             if (slide) {

@@ -26,6 +26,7 @@ GENERIC_KERNEL = 2
 NO_WINDOW = 4
 WHOLE_SEQUENCES = 8
 WINDOW_REFRESH = 16
+BATCHED_POSITIVES = 32
 STATS_LEN = 6
 WALK_AUTO, WALK_WARP, WALK_THREAD = 0, 1, 2
 EDGE_OPS = {'average': 0, 'hadamard': 1, 'weighted_l1': 2, 'weighted_l2': 3}
@@ -75,6 +76,9 @@ _SIGNATURES = {
                                              c_f32, c_u64, c_i64, c_int, c_p, c_p, c_p]),
     'se_sgns_update_negatives_owned': (c_int, [c_p, c_p, c_i64, c_int, c_p, c_i64, c_int, c_int, c_int, c_int, c_p, c_p, c_f32, c_u64,
                                                c_i64, c_p, c_p, c_p]),
+    'se_pairs_owned_scratch_bytes': (c_i64, [c_i64, c_i64, c_int, c_int]),
+    'se_sgns_update_pairs_owned': (c_int, [c_p, c_p, c_i64, c_int, c_p, c_i64, c_int, c_int, c_int, c_int, c_int, c_p, c_p, c_f32,
+                                           c_u64, c_i64, c_p, c_p, c_i64, c_p, c_p]),
     'se_host_walk_sgns_step_sharded': (c_int, [c_p, c_p, c_p, c_i64, c_int, c_p, c_i64, c_int, c_f64, c_f64, c_int, c_int,
                                                c_u64, c_i64, c_p, c_p, c_i64, c_int, c_int, c_int, c_int, c_p, c_p, c_f32,
                                                c_int, c_p, c_p, c_p, c_p, c_p, c_p, c_p]),
@@ -518,12 +522,21 @@ def sgns_update_walks(w_in, w_out, tokens: torch.Tensor, radius: int, n_neg: int
     return _stats_dict(stats) if own_stats else None
 
 
+_pairs_scratch: Dict[int, torch.Tensor] = {}
+
+
 def sgns_update_negatives_owned(w_in, w_out, tokens: torch.Tensor, radius: int, n_neg: int, row_offset: int, lr: float, seed: int,
                                 centre_id_base: int = 0, alias: Optional[Dict[str, torch.Tensor]] = None,
-                                stats: Optional[torch.Tensor] = None) -> None:
+                                stats: Optional[torch.Tensor] = None, grouped: bool = True,
+                                scratch: Optional[torch.Tensor] = None) -> None:
     """Owner-computes negatives on striped tables: processes, for every centre of `tokens` (any GPU's walks), the
-    negatives whose rows this rank owns (global negative distribution, same Philox keys as `sgns_update_walks`)."""
+    negatives whose rows this rank owns (global negative distribution, same Philox keys as `sgns_update_walks`).
+    grouped (default): centres bucketed by table row first (`sgns_update_pairs_owned` without the positives); False: walk order
+    (`se_sgns_update_negatives_owned`)."""
     global _launches
+    if grouped:
+        return sgns_update_pairs_owned(w_in, w_out, tokens, radius, n_neg, row_offset, lr, seed, centre_id_base=centre_id_base, alias=alias,
+                                       stats=stats, positives=False, scratch=scratch)
     n_seq, seq_len = tokens.shape
     p_in, vocab, emb, s_in, dev = _table(w_in, 'w_in')
     p_out, _, _, s_out, _ = _table(w_out, 'w_out')
@@ -538,6 +551,45 @@ def sgns_update_negatives_owned(w_in, w_out, tokens: torch.Tensor, radius: int, 
             float(lr), int(seed) & (2 ** 64 - 1), int(centre_id_base), ctypes.byref(spec),
             stats.data_ptr() if stats is not None else None, _stream()))
     _launches += 1
+
+
+def sgns_update_pairs_owned(w_in, w_out, tokens: torch.Tensor, radius: int, n_neg: int, row_offset: int, lr: float, seed: int,
+                            centre_id_base: int = 0, alias: Optional[Dict[str, torch.Tensor]] = None,
+                            stats: Optional[torch.Tensor] = None, positives: bool = True,
+                            scratch: Optional[torch.Tensor] = None) -> None:
+    """Owner-computes on striped tables, centres bucketed by table row (`se_sgns_update_pairs_owned`): for every centre of `tokens`
+    (the gathered walks of all GPUs) the negatives -- and with `positives` the context tokens -- whose W_out rows this rank owns.
+    Called on every rank with the same tokens and keys, every pair of the batch is computed exactly once.  `scratch`: a uint8 device
+    tensor of `pairs_owned_scratch_bytes` (default: one cached per device)."""
+    global _launches
+    n_seq, seq_len = tokens.shape
+    p_in, vocab, emb, s_in, dev = _table(w_in, 'w_in')
+    p_out, _, _, s_out, _ = _table(w_out, 'w_out')
+    spec = _same_sharding(s_in, s_out)
+    if spec is None:
+        raise ValueError('sgns_update_pairs_owned needs striped tables (ShardedTable)')
+    spec = ShardSpec(spec.world, spec.rank, spec.stripe_rows, 0, 0)
+    with torch.cuda.device(dev):
+        need = pairs_owned_scratch_bytes(vocab, n_seq, seq_len, radius)
+        if scratch is None:
+            key = torch.device(dev).index or 0
+            scratch = _pairs_scratch.get(key)
+            if scratch is None or scratch.numel() < need:
+                scratch = _pairs_scratch[key] = torch.empty(need, dtype=torch.uint8, device=dev)
+        assert scratch.is_cuda and scratch.dtype == torch.uint8 and scratch.numel() >= need, 'pairs_owned scratch too small'
+        _check(load().se_sgns_update_pairs_owned(
+            p_in, p_out, vocab, emb, _ptr(tokens, torch.int32, 'tokens'), n_seq, seq_len, int(radius), int(n_neg), int(bool(positives)),
+            int(row_offset), _ptr(alias['prob'], torch.float32) if alias else None, _ptr(alias['alias'], torch.int32) if alias else None,
+            float(lr), int(seed) & (2 ** 64 - 1), int(centre_id_base), ctypes.byref(spec), scratch.data_ptr(), scratch.numel(),
+            stats.data_ptr() if stats is not None else None, _stream()))
+    _launches += 8          # count, 5 scan kernels, fill, update
+
+
+def pairs_owned_scratch_bytes(vocab: int, n_seq: int, seq_len: int, radius: int) -> int:
+    n = int(load().se_pairs_owned_scratch_bytes(int(vocab), int(n_seq), int(seq_len), int(radius)))
+    if n < 0:
+        raise ValueError('pairs_owned_scratch_bytes: bad sizes')
+    return n
 
 
 def host_walk_sgns_step(csr, starts_host: torch.Tensor, walk_len: int, p: float, q: float, node2vec: bool, rule: int,

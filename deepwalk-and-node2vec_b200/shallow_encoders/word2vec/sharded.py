@@ -427,16 +427,21 @@ def sync_replicated(tables, group=None, merge='stable') -> None:
 
 def sgns_update_walks_owner_computes(w_in, w_out, my_walks: torch.Tensor, radius: int, n_neg: int, row_offset: int, lr: float, seed: int,
                                      centre_id_base: int, rank: int, world: int, group=None, stats: Optional[torch.Tensor] = None,
-                                     alias=None, gather_buf: Optional[torch.Tensor] = None, micro_walks: Optional[int] = None) -> None:
-    """One multi-GPU SGNS step with the reference's GLOBAL negative distribution and little NVLink traffic: the positive
-    pairs of this rank's walks run in the window-resident kernel (n_neg = 0); the walks of all ranks are all-gathered
-    (4 bytes per token) and every rank processes, for every centre of every rank, the negatives whose rows it owns
-    (`se_sgns_update_negatives_owned`).  `centre_id_base` is the Philox id of centre 0 of RANK 0's walks; rank r's
-    centres follow at r * n_walks * n_centres, so the negatives are the ones a single GPU would draw for the
-    concatenated batch.  Every rank must call this with the same number of walks.
+                                     alias=None, gather_buf: Optional[torch.Tensor] = None, micro_walks: Optional[int] = None,
+                                     grouped: bool = True) -> None:
+    """One multi-GPU SGNS step with the reference's GLOBAL negative distribution and little NVLink traffic.  The walks of all ranks
+    are all-gathered (4 bytes per token, the only collective); `centre_id_base` is the Philox id of centre 0 of RANK 0's walks, rank
+    r's centres follow at r * n_walks * n_centres, so the negatives are the ones a single GPU would draw for the concatenated batch.
+    Every rank must call this with the same number of walks.
 
-    A step applies positives, then negatives.  `micro_walks` interleaves the two in slices of that many walks per rank
-    (after ONE all-gather), for steps that update the same rows many times (small tables, large batches)."""
+    grouped (default): every rank buckets the centres of the gathered batch by table row and computes EVERY pair -- positive or
+    negative -- whose W_out row it owns (`se_sgns_update_pairs_owned`): W_out never crosses NVLink, a W_in centre row crosses once per
+    run of equal rows.  grouped=False (round 1): the positive pairs of this rank's walks run in the window-resident kernel (n_neg = 0,
+    context rows fetched from their owners) and every rank processes the owned negatives of every centre in walk order
+    (`se_sgns_update_negatives_owned`); a step then applies positives, then negatives.
+
+    `micro_walks` processes the step in slices of that many walks per rank (after ONE all-gather), for steps that update the same
+    rows many times (small tables, large batches)."""
     import torch.distributed as dist
     n_walks, length = my_walks.shape
     n_cen = length - 2 * radius
@@ -450,12 +455,23 @@ def sgns_update_walks_owner_computes(w_in, w_out, my_walks: torch.Tensor, radius
     micro = n_walks if not micro_walks else max(1, min(int(micro_walks), n_walks))
     for lo in range(0, n_walks, micro):
         hi = min(n_walks, lo + micro)
+        if grouped:
+            if micro == n_walks:
+                nat.sgns_update_pairs_owned(w_in, w_out, all_walks, radius, n_neg, row_offset, lr, seed, centre_id_base=centre_id_base,
+                                            alias=alias, stats=stats, positives=True)
+            else:
+                for r in range(world):   # the same slice of every rank's walks (contiguous inside rank r's block of the gathered buffer)
+                    nat.sgns_update_pairs_owned(w_in, w_out, all_walks[r * n_walks + lo:r * n_walks + hi], radius, n_neg, row_offset, lr, seed,
+                                                centre_id_base=centre_id_base + (r * n_walks + lo) * n_cen, alias=alias, stats=stats,
+                                                positives=True)
+            continue
         nat.sgns_update_walks(w_in, w_out, my_walks[lo:hi], radius, 0, row_offset, lr, seed,
                               centre_id_base=centre_id_base + (rank * n_walks + lo) * n_cen, stats=stats)
         if micro == n_walks:
             nat.sgns_update_negatives_owned(w_in, w_out, all_walks, radius, n_neg, row_offset, lr, seed, centre_id_base=centre_id_base,
-                                            alias=alias, stats=stats)
+                                            alias=alias, stats=stats, grouped=False)
         else:
-            for r in range(world):       # the same slice of every rank's walks (contiguous inside rank r's block of the gathered buffer)
+            for r in range(world):
                 nat.sgns_update_negatives_owned(w_in, w_out, all_walks[r * n_walks + lo:r * n_walks + hi], radius, n_neg, row_offset, lr, seed,
-                                                centre_id_base=centre_id_base + (r * n_walks + lo) * n_cen, alias=alias, stats=stats)
+                                                centre_id_base=centre_id_base + (r * n_walks + lo) * n_cen, alias=alias, stats=stats,
+                                                grouped=False)

@@ -54,6 +54,10 @@ extern "C" {
 #define SE_SGNS_WINDOW_REFRESH 16 /* bit flag (se_sgns_update_walks*): the window kernel scatters and re-fetches a token's resident
                                      W_out row when the token is the centre (it is not a context then), so a resident copy is at most r
                                      centres old instead of 2r: for token streams whose frequent tokens sit in many windows at once */
+#define SE_SGNS_BATCHED_POSITIVES 32 /* bit flag (se_sgns_update_walks* with n_neg = 0 and 64 < emb <= 128): the 2r positive pairs of a
+                                        centre are scored against ONE snapshot of the window (one transposed reduction for all 2r dots,
+                                        sigmoids side by side) and then applied in order, instead of pair by pair -- the mini-batch-of-2r
+                                        form; 2-3x faster when the negatives run elsewhere (the owner-computes multi-GPU mode sets it) */
 /* stats layout written by the SGNS kernels (double[SE_STATS_LEN], ACCUMULATED into, caller zeroes):
  *   [0] sum over pairs of positive loss   -log clamp(sigmoid(s+), 1e-6)          (word2vec/loss.py:15)
  *   [1] sum over pairs of negative loss   -sum_k log clamp(sigmoid(-s-), 1e-6)   (word2vec/loss.py:16)
@@ -274,6 +278,22 @@ int se_sgns_update_negatives_owned(float *w_in, float *w_out, int64_t vocab, int
                                    int64_t n_seq, int seq_len, int radius, int n_neg, int row_offset,
                                    const float *alias_prob, const int32_t *alias_idx, float lr, uint64_t seed,
                                    int64_t centre_id_base, const se_shard_spec *spec, double *stats, void *stream);
+/* Owner-computes, grouped: the centres of the batch are first bucketed by table row on the device (counting sort in `scratch`,
+ * se_pairs_owned_scratch_bytes; own kernels); a warp keeps the centre row of a run of equal rows in registers -- one read and one
+ * reduction per run instead of per occurrence (10 M distinct rows against 147 M occurrences per step on S3 at 8 GPUs) -- and the
+ * owned output rows of consecutive occurrences share full passes.  Negatives: same Philox keys, hence the same (centre, negative)
+ * pairs as se_sgns_update_negatives_owned and se_sgns_update_walks (sampling.py:21 distribution over the WHOLE table).
+ * positives != 0: the 2r context tokens of every centre (window rule torch_dataset.py:300-309) are processed as well when
+ * spec->rank owns their W_out row, so that calling it on every rank with the same gathered tokens performs EVERY pair of the batch
+ * exactly once, on the owner of its output row: W_out never crosses NVLink and no separate positive pass is needed
+ * (stats [0], [2], [4] then count the owned positives).  The ORDER of the updates differs from walk order (Hogwild).
+ * Token ids outside [0, vocab) are skipped as centres.  The default of the multi-GPU owner-computes mode. */
+int64_t se_pairs_owned_scratch_bytes(int64_t vocab, int64_t n_seq, int seq_len, int radius);
+int se_sgns_update_pairs_owned(float *w_in, float *w_out, int64_t vocab, int emb, const int32_t *tokens, int64_t n_seq,
+                               int seq_len, int radius, int n_neg, int positives, int row_offset,
+                               const float *alias_prob, const int32_t *alias_idx, float lr, uint64_t seed,
+                               int64_t centre_id_base, const se_shard_spec *spec, void *scratch,
+                               int64_t scratch_bytes, double *stats, void *stream);
 int se_host_walk_sgns_step_sharded(const int64_t *rowptr, const int32_t *col, const float *wcdf, int64_t n_nodes,
                                    int symmetric, const int32_t *starts_host, int64_t n_walks, int walk_len, double p,
                                    double q, int node2vec, int rule, uint64_t seed, int64_t walk_id_base,

@@ -105,8 +105,9 @@ def test_skipgram_forward_and_loss_modules_match_oracle_with_autograd():
         proba = model(inputs, targets)                                   # proba=True default
     np.testing.assert_allclose(proba.cpu().numpy(), sgns_oracle.sigmoid(o['pos_logits']), rtol=1e-4, atol=1e-6)
     assert not model.input_embedding.is_cuda and model.input_embedding.shape == (vocab, emb)
+    assert SkipGram(vocab_size=10, embedding_size=4, max_norm=1.0).max_norm == 1.0     # renormalisation itself: tests/test_gpu_text.py
     with pytest.raises(NotImplementedError):
-        SkipGram(vocab_size=10, embedding_size=4, max_norm=1.0)
+        SkipGram(vocab_size=10, embedding_size=4, max_norm=1.0, shard={'world': 2, 'rank': 0})
 
 
 def test_generate_noise_batch_is_uniform_like_the_reference():

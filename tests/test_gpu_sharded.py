@@ -167,8 +167,9 @@ def test_local_negatives_stay_on_the_owning_shard_and_match_the_oracle(rank, use
     s_in.close(); s_out.close()
 
 
+@pytest.mark.parametrize('grouped', [True, False])
 @pytest.mark.parametrize('use_alias,emb', [(False, 128), (True, 128), (False, 96)])
-def test_owner_computes_negatives_perform_the_same_pair_updates(use_alias, emb):
+def test_owner_computes_negatives_perform_the_same_pair_updates(use_alias, emb, grouped):
     """Positives on the home rank (window kernel, K = 0) + owner-computes negatives on every simulated rank == the pair
     updates of the ordinary fused kernel == the oracle's mini-batch SGD, with the GLOBAL negative distribution."""
     dev = cuda_device()
@@ -191,12 +192,18 @@ def test_owner_computes_negatives_perform_the_same_pair_updates(use_alias, emb):
     s_in.scatter(allrows, _t(w_in, dev)); s_out.scatter(allrows, _t(w_out, dev))
     tok = _t(tokens, dev)
     stats = torch.zeros(nat.STATS_LEN, dtype=torch.float64, device=dev)
-    nat.sgns_update_walks(s_in, s_out, tok, radius, 0, offset, lr, seed, centre_id_base=300, stats=stats)          # positive pairs
+    if not grouped:          # round-1 form: positives on the home rank (window kernel, K = 0), owned negatives in walk order
+        nat.sgns_update_walks(s_in, s_out, tok, radius, 0, offset, lr, seed, centre_id_base=300, stats=stats)
     owned_negs = 0
     for r in range(world):
-        before = stats[5].item()
-        nat.sgns_update_negatives_owned(s_in.as_rank(r), s_out.as_rank(r), tok, radius, k, offset, lr, seed, centre_id_base=300,
-                                        alias=alias, stats=stats)
+        before, before_pos = stats[5].item(), stats[4].item()
+        if grouped:          # every pair -- positive or negative -- on the rank that owns its W_out row, centres bucketed by row
+            nat.sgns_update_pairs_owned(s_in.as_rank(r), s_out.as_rank(r), tok, radius, k, offset, lr, seed, centre_id_base=300,
+                                        alias=alias, stats=stats, positives=True)
+            assert stats[4].item() - before_pos == int((((targets // s_in.stripe_rows) % world) == r).sum())
+        else:
+            nat.sgns_update_negatives_owned(s_in.as_rank(r), s_out.as_rank(r), tok, radius, k, offset, lr, seed, centre_id_base=300,
+                                            alias=alias, stats=stats, grouped=False)
         got_r = stats[5].item() - before
         assert got_r == int((((neg // s_in.stripe_rows) % world) == r).sum())                                 # exactly the rows rank r owns
         owned_negs += got_r
@@ -224,7 +231,8 @@ def test_owner_computes_negatives_perform_the_same_pair_updates(use_alias, emb):
     s_in.close(); s_out.close()
 
 
-def test_owner_computes_with_every_negative_owned_and_a_long_list():
+@pytest.mark.parametrize('grouped', [True, False])
+def test_owner_computes_with_every_negative_owned_and_a_long_list(grouped):
     """world = 1 and N*K = 70 > 64: every drawn negative is owned, the per-warp list holds them all; result == the ordinary
     fused kernel on the same tokens (distinct rows, tiny lr)."""
     dev = cuda_device()
@@ -236,12 +244,87 @@ def test_owner_computes_with_every_negative_owned_and_a_long_list():
     t_in, t_out = w[0].to_tensor().clone(), w[1].to_tensor().clone()
     tok = _t(tokens, dev)
     stats = torch.zeros(nat.STATS_LEN, dtype=torch.float64, device=dev)
-    nat.sgns_update_walks(w[0], w[1], tok, radius, 0, offset, 1e-3, 9, centre_id_base=40, stats=stats)
-    nat.sgns_update_negatives_owned(w[0], w[1], tok, radius, k, offset, 1e-3, 9, centre_id_base=40, stats=stats)
+    if grouped:
+        nat.sgns_update_pairs_owned(w[0], w[1], tok, radius, k, offset, 1e-3, 9, centre_id_base=40, stats=stats, positives=True)
+    else:
+        nat.sgns_update_walks(w[0], w[1], tok, radius, 0, offset, 1e-3, 9, centre_id_base=40, stats=stats)
+        nat.sgns_update_negatives_owned(w[0], w[1], tok, radius, k, offset, 1e-3, 9, centre_id_base=40, stats=stats, grouped=False)
     assert stats[5].item() == n_seq * 2 * radius * k and stats[4].item() == n_seq * 2 * radius
     nat.sgns_update_walks(t_in, t_out, tok, radius, k, offset, 1e-3, 9, centre_id_base=40)
     assert float((w[1].to_tensor() - t_out).abs().max()) < 2e-6 and float((w[0].to_tensor() - t_in).abs().max()) < 2e-6
     w[0].close(); w[1].close()
+
+
+@pytest.mark.parametrize('use_alias,emb,radius,k', [(False, 128, 5, 5), (True, 128, 2, 4), (False, 64, 3, 7)])
+def test_grouped_owner_computes_on_repeated_centres_equals_walk_order(use_alias, emb, radius, k):
+    """Walk-like sequences over a few dozen rows with one hub: a row is the centre hundreds of times, so the bucketed kernel sees
+    runs that span several 32-entry chunks, keeps the centre row in registers across a run and draws two occurrences per Philox
+    round (K = 5, r = 5) or one (K = 7, r = 3: 14 ... 21 drawing lanes).  The (centre, negative) pairs are those of the walk-order
+    kernel -- the owned-negative COUNT is identical on every simulated rank -- and with a tiny learning rate (order of the
+    updates matters at second order only) both kernels land on the same tables; rows nobody names stay bit-identical."""
+    dev = cuda_device()
+    rng = np.random.default_rng(71)
+    n_seq, length, offset, world = 96, 2 * radius + 9, 1, 2
+    vocab = (4096 if emb == 128 else 8192) * 5 + 100
+    ids = rng.choice(vocab - offset, 40, replace=False)
+    pick = rng.integers(0, 40, (n_seq, length))
+    pick[rng.random((n_seq, length)) < 0.3] = 0                    # the hub: ~30 % of all centres
+    tokens = ids[pick].astype(np.int32)
+    alias = None
+    if use_alias:
+        alias = nat.alias_build(rng.integers(1, 50, vocab).astype(np.float64), 0.75, dev)
+    w_in = (rng.standard_normal((vocab, emb)) * 0.3).astype(np.float32)
+    w_out = (rng.standard_normal((vocab, emb)) * 0.3).astype(np.float32)
+    lr, seed = 1e-6, 123
+    tok = _t(tokens, dev)
+    allrows = torch.arange(vocab, device=dev)
+    res = {}
+    for grouped in (False, True, 'walk-order with positives', 'all pairs'):
+        s_in = ShardedTable(vocab, emb, dev, rank=0, world=world, simulate=True)
+        s_out = ShardedTable(vocab, emb, dev, rank=0, world=world, simulate=True)
+        s_in.scatter(allrows, _t(w_in, dev)); s_out.scatter(allrows, _t(w_out, dev))
+        per_rank = []
+        # (with the positives the hub's rows collect thousands of same-signed increments: at lr 1e-6 those are an ulp of the fp32 weights
+        #  and the red.add roundings of the walk-order path pile up to 2.5e-5; ten times larger steps keep rounding out of the comparison)
+        lr = 1e-5 if isinstance(grouped, str) else 1e-6
+        if grouped == 'walk-order with positives':
+            nat.sgns_update_walks(s_in, s_out, tok, radius, 0, offset, lr, seed, centre_id_base=7_000_000_000)
+        for r in range(world):
+            stats = torch.zeros(nat.STATS_LEN, dtype=torch.float64, device=dev)
+            if grouped == 'all pairs':
+                nat.sgns_update_pairs_owned(s_in.as_rank(r), s_out.as_rank(r), tok, radius, k, offset, lr, seed, centre_id_base=7_000_000_000,
+                                            alias=alias, stats=stats, positives=True)
+            else:
+                nat.sgns_update_negatives_owned(s_in.as_rank(r), s_out.as_rank(r), tok, radius, k, offset, lr, seed,
+                                                centre_id_base=7_000_000_000, alias=alias, stats=stats, grouped=grouped is True)
+            per_rank.append(stats.tolist())
+        res[grouped] = (s_in.to_tensor().cpu().numpy().astype(np.float64), s_out.to_tensor().cpu().numpy().astype(np.float64), per_rank)
+        s_in.close(); s_out.close()
+    # every pair on the owner of its output row == positives in the window kernel + owned negatives in walk order
+    a, b = res['walk-order with positives'], res['all pairs']
+    assert sum(st[4] for st in b[2]) == n_seq * (length - 2 * radius) * 2 * radius and sum(st[5] for st in b[2]) == sum(st[5] for st in a[2])
+    ctx_rows = sgns_oracle.windows_from_walks(tokens.astype(np.int64), radius, offset)[1]
+    for r in range(world):
+        assert b[2][r][4] == int((((ctx_rows // (4096 if emb == 128 else 8192)) % world) == r).sum())
+    move = max(np.abs(a[0] - w_in).max(), np.abs(a[1] - w_out).max())
+    assert move > 2e-4                                                               # positives move the few context rows a lot
+    assert np.abs(b[0] - a[0]).max() <= 0.02 * move and np.abs(b[1] - a[1]).max() <= 0.02 * move
+    lr = 1e-6
+    n_cen = length - 2 * radius
+    assert sum(st[5] for st in res[True][2]) == n_seq * n_cen * 2 * radius * k
+    for r in range(world):
+        a, b = res[False][2][r], res[True][2][r]
+        assert a[5] == b[5] and abs(a[3] - b[3]) <= 2 and a[5] > 0             # same owned negatives, same false-positive count (ties aside)
+        assert abs(a[1] - b[1]) <= 1e-5 * abs(a[1])
+    d_in, d_out = res[False][0] - w_in, res[False][1] - w_out
+    assert np.abs(d_in).max() > 20 * lr and np.abs(d_out).max() > 0.05 * lr        # the hub row moved by thousands of pair updates
+    # fp32 accumulation order differs (one reduction per run against one per occurrence): a few ulps of the row values
+    np.testing.assert_allclose(res[True][0], res[False][0], rtol=0, atol=5e-6)
+    np.testing.assert_allclose(res[True][1], res[False][1], rtol=0, atol=5e-6)
+    assert np.abs((res[True][0] - w_in) - d_in).max() <= 0.02 * np.abs(d_in).max()
+    centres = np.unique(tokens[:, radius:length - radius]) + offset
+    untouched = np.setdiff1d(np.arange(vocab), centres)
+    assert np.array_equal(res[True][0][untouched], w_in[untouched].astype(np.float64))
 
 
 def test_host_step_on_sharded_tables_matches_device_calls():
