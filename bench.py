@@ -134,11 +134,17 @@ def parallelism(a, n_gpus):
         return (f'dp{n_gpus} NCCL BASELINE: tables row-sharded by row % {n_gpus}; per micro-batch of {a.a2a_micro_walks} walks: unique ids -> '
                 f'all_to_all ids / rows -> se_sgns_grad on compact tables -> all_to_all gradients -> owners apply; negatives '
                 + ('among the rows each GPU owns' if neg == 'local' else 'uniform over the whole table (reference)'))
+    if neg == 'owner':
+        return (f'dp{n_gpus}: walks sharded by id (replicated CSR) and all-gathered (4 B per token, the only collective); ONE pair of tables row-striped '
+                f'(2 MiB stripes) over {n_gpus} HBMs; negatives drawn uniformly over the whole table (reference); every GPU buckets the centres of the '
+                'gathered batch by table row and computes EVERY pair -- positive or negative -- whose W_out row it owns against its own HBM '
+                '(se_sgns_update_pairs_owned): W_out never crosses NVLink, a W_in centre row is read / reduced over NVLink once per run of equal rows')
     return (f'dp{n_gpus}: walks sharded by id (replicated CSR, no communication); ONE pair of tables row-striped (2 MiB stripes) over '
             f'{n_gpus} HBMs, fused kernel gathers / red.adds peer rows over NVLink; negatives drawn '
             + {'local': 'among the rows each GPU owns', 'global': 'uniformly over the whole table (reference)',
-               'owner': 'uniformly over the whole table (reference), processed by the GPU that owns the negative row (walks all-gathered, '
-                        'centre rows read / updated over NVLink)'}[neg])
+               'owner': 'uniformly over the whole table (reference); walks all-gathered (4 B per token), centres bucketed by table row on every GPU, '
+                        'and EVERY pair -- positive or negative -- computed by the GPU that owns its W_out row against its own HBM '
+                        '(se_sgns_update_pairs_owned): W_out never crosses NVLink, a W_in centre row crosses once per run of equal rows'}[neg])
 
 
 def workload_config(a, n_gpus):
@@ -585,7 +591,7 @@ def run_b200(a, rank, local_rank, world):
         names = {'local': 'striped tables, negatives among the rows the GPU owns (GraphVite-style partitioned sampler: not the reference\'s per-pair draw; '
                           'accuracy = 1 GPU at 8 GPUs, profiles/r02_multi_gpu.md)',
                  'global': 'striped tables, reference draw, negative rows fetched / red.added over NVLink per pair',
-                 'owner': 'striped tables, reference draw, owner-computes (every negative pair on the GPU that owns the negative row; accuracy = 1 GPU)',
+                 'owner': 'striped tables, reference draw, owner-computes (every pair on the GPU that owns its W_out row, centres bucketed by row; accuracy = 1 GPU)',
                  'synced': 'working copy per GPU + row-sharded masters, reference draw, one fused reduce-scatter/all-gather kernel per step, merge = stable '
                            '(throughput mode: statistically inefficient at this step size on 8 GPUs, profiles/r02_multi_gpu.md)'}
 
@@ -647,7 +653,10 @@ def run_b200(a, rank, local_rank, world):
 
     peak, peak_src = measured_peak()
     window = a.kernel == 'window' and not a2a
+    owner_pairs = world > 1 and not a2a and neg_mode == 'owner'      # the stage is se_sgns_update_pairs_owned (+ all-gather + bucketing)
     bpp = bytes_per_pair(a.emb, a.neg, a.radius, window)
+    if owner_pairs:
+        bpp = 2.0 * 4.0 * a.emb * (1.0 + a.neg)        # every output row of a pair is read and reduced once, in the owner's HBM
     bpp_survey = bytes_per_pair(a.emb, a.neg, a.radius, False)
     achieved = pairs_per_step * bpp / (sgns_ms / 1e3) / 1e9
     traffic = recorded_traffic()
@@ -660,12 +669,17 @@ def run_b200(a, rank, local_rank, world):
         'kernel_ms': {'walk_kernel': walk_ms, 'sgns_kernel': sgns_ms},
         'roofline': {
             'bound': 'hbm', 'kernel': 'se_sgns_grad inside the NCCL row exchange (baseline)' if a2a else (
+                f'sgns_owned_pairs_kernel<EXACT={"true" if a.emb == 128 else "false"}, POS=true> via se_sgns_update_pairs_owned (stage time includes the '
+                'all-gather of the walks and the centre bucketing kernels)' if owner_pairs else
                 sgns_kernel_label(a.emb, a.neg, a.kernel == 'window') + ' via se_sgns_update_walks'), 'achieved': achieved, 'peak': peak,
             'unit': 'GB/s', 'frac': achieved / peak, 'peak_source': peak_src,
             'algorithmic_bytes_per_pair': bpp, 'pairs_per_launch': pairs_per_step,
-            'bytes_per_pair_formula': '2*4E*(K + 2/N): context rows resident per window' if window else '2*4E*(1 + K + 1/N) (SURVEY 8d)',
+            'bytes_per_pair_formula': ('2*4E*(1 + K): each GPU processes (1 + K) / G of the output rows of all G GPUs\' pairs = (1 + K) rows per pair of its '
+                                       'own share; centre rows (once per run of equal rows) not counted') if owner_pairs else (
+                '2*4E*(K + 2/N): context rows resident per window' if window else '2*4E*(1 + K + 1/N) (SURVEY 8d)'),
             'survey_unit': {'bytes_per_pair': bpp_survey, 'frac': pairs_per_step * bpp_survey / (sgns_ms / 1e3) / 1e9 / peak},
-            'traffic': (traffic or {}).get('dram_bytes_per_launch'), 'traffic_source': (traffic or {}).get('source'),
+            'traffic': None if owner_pairs else (traffic or {}).get('dram_bytes_per_launch'),
+            'traffic_source': None if owner_pairs else (traffic or {}).get('source'),
             # the window kernel fetches a token's context row once per window instead of once per pair, so its DRAM traffic
             # is below the per-pair algorithmic figure; the DRAM-side rate is traffic / launch time
             'dram_traffic_gbs': ((traffic or {}).get('dram_bytes_per_launch') or 0) / (sgns_ms / 1e3) / 1e9 if traffic and a.kernel == 'window' and world == 1 else None,
