@@ -11,7 +11,7 @@
 //     distinct (row, 32-entry chunk) instead of two per occurrence;
 //   * the owned output rows of consecutive occurrences of a run share one list, so passes run with all eight row slots filled;
 //   * when a centre needs at most 16 drawing lanes (K = 5, r = 5: 15), two occurrences are drawn per Philox round;
-//   * with `positives`, the 2r context tokens of every occurrence (read from the gathered tokens, one round ahead) join the list when
+//   * with `positives`, the 2r context tokens of every occurrence (read from the gathered tokens, staged in shared memory one chunk ahead) join the list when
 //     this GPU owns their W_out row: then EVERY pair of the batch, positive or negative, is computed by the owner of its output row,
 //     W_out never crosses NVLink, and the separate positive pass (window kernel, K = 0: four peer rows per centre with nothing to
 //     hide their latency behind) disappears.
@@ -59,6 +59,7 @@ __global__ void __launch_bounds__(SGNS_THREADS, 2)
 sgns_owned_pairs_kernel(const SgnsArgs a, const int2 *__restrict__ entries, const int64_t *__restrict__ n_entries_p) {
     constexpr int P = NGO_P, SHIFT = NGO_SHIFT;
     __shared__ int own_list[SGNS_THREADS / 32][NGO_LIST];
+    __shared__ int ctx_s[POS ? SGNS_THREADS / 32 : 1][2][POS ? 512 : 1];      // context tokens of this chunk / of the next one
     const int lane = threadIdx.x & 31;
     int *list = own_list[threadIdx.x >> 5];
     const int64_t gid = (int64_t)blockIdx.x * (SGNS_THREADS / 32) + (threadIdx.x >> 5);
@@ -82,19 +83,33 @@ sgns_owned_pairs_kernel(const SgnsArgs a, const int2 *__restrict__ entries, cons
     const uint32_t world = (uint32_t)a.neg_world, me = (uint32_t)a.neg_rank;
     const int shift = a.own_shift;
 
-    // context slot of this lane: context nc of occurrence j + half (positives)
+    // rows are striped round-robin: row id -> owner.  The usual power-of-two GPU count takes a mask instead of a division.
+    const bool pow2 = (world & (world - 1u)) == 0u;
+    auto owned = [&](uint32_t id) -> bool {
+        const uint32_t stripe = id >> shift;
+        return (pow2 ? (stripe & (world - 1u)) : (stripe % world)) == me;
+    };
+    // Positives: context nc of occurrence j + half is this lane's slot.  The context TOKENS of a whole chunk (32 entries x up to 16
+    // contexts) are staged in shared memory with 4-byte cp.async one chunk ahead -- they are random reads of the gathered token
+    // array, a DRAM latency each, and a round of two occurrences is far too short to hide one.
     const int nc = two ? (lane & 15) : lane;
     const int r = a.radius;
-    const int nc_off = nc < r ? nc : nc + 1;                   // window offset of context nc (the centre is skipped)
-    // context row of (occurrence occ of this chunk, context nc), or -1; every lane takes part in the shuffle
-    auto ctx_row = [&](int occ, int eu_, int n_valid_) -> int {
-        const uint32_t uo = (uint32_t)__shfl_sync(FULL, eu_, occ & 31);
-        int t = -1;
-        if (POS && nc < N && occ < n_valid_) {
-            const uint32_t sq = uo / (uint32_t)a.n_cen;
-            t = __ldg(a.tokens + (int64_t)sq * a.seq_len + (int)(uo - sq * (uint32_t)a.n_cen) + nc_off) + a.row_offset;
+    int *ctx = ctx_s[threadIdx.x >> 5][0];
+    auto stage_ctx = [&](int buf, int eu_, int er_) {
+        if (!POS) return;
+        int base = -1;                                         // index of token (sequence, centre position - r) of this lane's entry
+        if (er_ >= 0) {
+            const uint32_t sq = (uint32_t)eu_ / (uint32_t)a.n_cen;
+            base = (int)(sq * (uint32_t)a.seq_len + ((uint32_t)eu_ - sq * (uint32_t)a.n_cen));
         }
-        return t;
+        const int n = lane & 15, off = n < r ? n : n + 1;      // window offset of context n (the centre is skipped)
+#pragma unroll 4
+        for (int i = 0; i < 16; ++i) {
+            const int ent = i * 2 + (lane >> 4);
+            const int b = __shfl_sync(FULL, base, ent);
+            if (n < N && b >= 0) cp_async4(ctx + buf * 512 + ent * 16 + n, a.tokens + b + off);
+        }
+        cp_async_commit();
     };
 
     float loss_pos = 0.f, loss_neg = 0.f;
@@ -108,6 +123,7 @@ sgns_owned_pairs_kernel(const SgnsArgs a, const int2 *__restrict__ entries, cons
         if (i < n_entries) { const int2 t = __ldg(entries + i); eu = t.x; er = t.y; }
         const int first = __shfl_sync(FULL, er, 0);
         if (ok) load_vec<4>(a.w_in + (int64_t)first * E + eoff, nxt);
+        stage_ctx(0, eu, er);
     }
 
     for (int64_t c = c_begin; c < c_end; ++c) {
@@ -116,11 +132,15 @@ sgns_owned_pairs_kernel(const SgnsArgs a, const int2 *__restrict__ entries, cons
             const int64_t i = (c + 1) * 32 + lane;
             if (c + 1 < c_end && i < n_entries) { const int2 t = __ldg(entries + i); nu = t.x; nr = t.y; }
         }
+        const int buf = (int)((c - c_begin) & 1);
+        if (POS) {
+            stage_ctx(buf ^ 1, nu, nr);                        // the next chunk's context tokens travel while this chunk is computed
+            cp_async_wait_group1();                            // ... and this chunk's have arrived
+            __syncwarp();
+        }
         const int prev = __shfl_up_sync(FULL, er, 1);
         const int n_valid = __popc(__ballot_sync(FULL, er >= 0));                        // valid lanes form a prefix
         unsigned heads = __ballot_sync(FULL, er >= 0 && (lane == 0 || er != prev));
-        int ptok = -1;                                         // context row of this lane's slot in the round about to start
-        if (POS) ptok = ctx_row(half, eu, n_valid);
         while (heads) {
             const int b = __ffs(heads) - 1;
             heads &= heads - 1;
@@ -152,17 +172,16 @@ sgns_owned_pairs_kernel(const SgnsArgs a, const int2 *__restrict__ entries, cons
                         if (l_g * 4 + x < N) {
                             const uint32_t id = (uint32_t)draw_row(a.alias_prob, a.alias_idx, (uint32_t)a.vocab, pick_word(wb, x), pick_word(wc, x));
                             ids[x] = (int)id;
-                            own[x] = ((id >> shift) % world) == me;
+                            own[x] = owned(id);
                         }
                     }
                 }
-                // ---- and which of the 2r context rows?  (their tokens were fetched during the previous round) ----------------------
+                // ---- and which of the 2r context rows?  (their tokens were staged while the previous chunk was computed) ----------
                 bool own_p = false;
                 int pid = 0;
-                if (POS) {
-                    if (ptok >= 0 && jj < e) { pid = ptok; own_p = (((uint32_t)ptok >> shift) % world) == me; }
-                    const int jn = (j + per < e) ? j + per : e;                  // first occurrence of the next round (warp-uniform)
-                    ptok = (jn < n_valid) ? ctx_row(jn + half, eu, n_valid) : -1;
+                if (POS && nc < N && jj < e) {
+                    pid = ctx[buf * 512 + jj * 16 + nc] + a.row_offset;
+                    own_p = owned((uint32_t)pid);
                 }
                 const int cnt = (int)own[0] + (int)own[1] + (int)own[2] + (int)own[3] + (int)own_p;
                 int incl = cnt;
@@ -286,10 +305,10 @@ extern "C" int se_sgns_update_pairs_owned(float *w_in, float *w_out, int64_t voc
     const int64_t sr = spec->stripe_rows;
     const int64_t n_units = n_seq * (seq_len - 2 * radius);
     if ((sr & (sr - 1)) || emb % 4 != 0 || emb <= 32 || emb > 128 || n_neg > 7 || ((2 * radius + 3) / 4) * n_neg > 32 ||
-        ((uintptr_t)w_in % 16) || ((uintptr_t)w_out % 16) || n_units >= 0x7fffffffll || vocab >= 0x7fffffffll) {
+        ((uintptr_t)w_in % 16) || ((uintptr_t)w_out % 16) || n_seq * seq_len >= 0x7fffffffll || vocab >= 0x7fffffffll) {
         se::set_error("%s: needs 32 < emb <= 128 (multiple of 4), n_neg <= 7, ceil(2r/4)*n_neg <= 32, 16-byte aligned tables, a power-of-two "
-                      "stripe_rows and fewer than 2^31 centres (emb %d, n_neg %d, radius %d, stripe_rows %lld, centres %lld)",
-                      fn, emb, n_neg, radius, (long long)sr, (long long)n_units);
+                      "stripe_rows and fewer than 2^31 tokens (emb %d, n_neg %d, radius %d, stripe_rows %lld, tokens %lld)",
+                      fn, emb, n_neg, radius, (long long)sr, (long long)(n_seq * seq_len));
         return SE_ERR_UNSUPPORTED;
     }
     SE_REQUIRE(scratch && ((uintptr_t)scratch % 16) == 0 && scratch_bytes >= se_pairs_owned_scratch_bytes(vocab, n_seq, seq_len, radius),
