@@ -19,6 +19,8 @@
 // of (centre, output row) pairs is unchanged -- only their order is.  Within a run the register copy of the centre row is advanced after
 // every batch of passes (at most one draw round + 7 rows), a finer grain than the single-GPU kernel's 2r (1 + K) rows per centre; across
 // GPUs and warps the usual Hogwild rules apply (a chunk boundary ends a run, so a hub row is refreshed from memory every 32 occurrences).
+#include <type_traits>
+
 #include "sgns_common.cuh"
 #include "scan.cuh"
 
@@ -26,7 +28,7 @@ namespace se {
 namespace {
 
 constexpr int NGO_P = 8, NGO_SHIFT = 2;      // rows per pass; lanes per row after the transposed reduction (32 / 8 = 4)
-constexpr int NGO_LIST = 168;                // a remainder of < 8 ids + one draw round of at most 128 negatives + 32 contexts
+constexpr int NGO_LIST = 176;                // a remainder of < 8 ids + one draw round of at most 128 negatives + 32 contexts (+ 8: vector reads of a ragged pass)
 
 __device__ __forceinline__ int centre_row(const SgnsArgs &a, uint32_t u) {
     const uint32_t sq = u / (uint32_t)a.n_cen;
@@ -58,7 +60,7 @@ template <bool EXACT, bool POS>
 __global__ void __launch_bounds__(SGNS_THREADS, 2)
 sgns_owned_pairs_kernel(const SgnsArgs a, const int2 *__restrict__ entries, const int64_t *__restrict__ n_entries_p) {
     constexpr int P = NGO_P, SHIFT = NGO_SHIFT;
-    __shared__ int own_list[SGNS_THREADS / 32][NGO_LIST];
+    __shared__ __align__(16) int own_list[SGNS_THREADS / 32][NGO_LIST];        // NGO_LIST * 4 bytes is a multiple of 16
     __shared__ int ctx_s[POS ? SGNS_THREADS / 32 : 1][2][POS ? 512 : 1];      // context tokens of this chunk / of the next one
     const int lane = threadIdx.x & 31;
     int *list = own_list[threadIdx.x >> 5];
@@ -204,17 +206,21 @@ sgns_owned_pairs_kernel(const SgnsArgs a, const int2 *__restrict__ entries, cons
                 __syncwarp();
 
                 float acc[4] = {0.f, 0.f, 0.f, 0.f};
-                for (int c0 = 0; c0 < todo; c0 += P) {
-                    const int m = min(P, todo - c0);
+                // one pass = up to eight listed rows: gather, dots, one transposed reduction, sigmoids side by side, updates.  Nearly all
+                // passes are full; their copy of the code carries no per-row predicates
+                auto do_pass = [&](auto full_c, const int c0, const int m) {
+                    constexpr bool FULLP = decltype(full_c)::value;
+                    const int4 la = *reinterpret_cast<const int4 *>(list + c0), lb = *reinterpret_cast<const int4 *>(list + c0 + 4);
+                    const int raw[P] = {la.x, la.y, la.z, la.w, lb.x, lb.y, lb.z, lb.w};
                     int tid[P];
                     float rowv[P][4];
                     float dot[P];
 #pragma unroll
-                    for (int t = 0; t < P; ++t) tid[t] = (t < m) ? (list[c0 + t] & 0x7fffffff) : 0;
+                    for (int t = 0; t < P; ++t) tid[t] = (FULLP || t < m) ? (raw[t] & 0x7fffffff) : 0;
 #pragma unroll
                     for (int t = 0; t < P; ++t) {
-                        rowv[t][0] = rowv[t][1] = rowv[t][2] = rowv[t][3] = 0.f;
-                        if (t < m && ok) load_vec<4>(a.w_out + (int64_t)tid[t] * E + eoff, rowv[t]);
+                        if (!(FULLP && EXACT)) rowv[t][0] = rowv[t][1] = rowv[t][2] = rowv[t][3] = 0.f;
+                        if ((FULLP || t < m) && ok) load_vec<4>(a.w_out + (int64_t)tid[t] * E + eoff, rowv[t]);
                     }
 #pragma unroll
                     for (int t = 0; t < P; ++t) {
@@ -225,7 +231,7 @@ sgns_owned_pairs_kernel(const SgnsArgs a, const int2 *__restrict__ entries, cons
                     }
                     const float sc = transposed_reduce<P>(dot, lane);
                     float step_mine = 0.f;
-                    if (owner_t < m) {
+                    if (FULLP || owner_t < m) {
                         const bool positive = POS && list[c0 + owner_t] < 0;
                         const float xs = positive ? sc : -sc;                         // loss = -log clamp(sigmoid(+-s), 1e-6)   (loss.py:15-16)
                         const float ex = __expf(-xs);
@@ -241,13 +247,17 @@ sgns_owned_pairs_kernel(const SgnsArgs a, const int2 *__restrict__ entries, cons
 #pragma unroll
                     for (int t = 0; t < P; ++t) {
                         const float step = __shfl_sync(FULL, step_mine, t << SHIFT);
-                        if (t < m) {
+                        if (FULLP || t < m) {
                             float d[4];
 #pragma unroll
                             for (int x = 0; x < 4; ++x) { acc[x] = fmaf(step, rowv[t][x], acc[x]); d[x] = step * cen[x]; }
                             if (ok) red_vec<4>(a.w_out + (int64_t)tid[t] * E + eoff, d, false);      // my own HBM: device scope is enough
                         }
                     }
+                };
+                for (int c0 = 0; c0 < todo; c0 += P) {
+                    if (todo - c0 >= P) do_pass(std::true_type{}, c0, P);
+                    else do_pass(std::false_type{}, c0, todo - c0);
                 }
 #pragma unroll
                 for (int x = 0; x < 4; ++x) { cen[x] += acc[x]; tot[x] += acc[x]; }
