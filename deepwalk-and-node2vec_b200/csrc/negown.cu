@@ -4,7 +4,7 @@
 // centre OCCURRENCE (147 M per step on S3 at 8 GPUs against 10 M distinct rows), fills on average 6 of the 8 row slots of a pass, and
 // waits for the centre row before it can start on the negatives -- per-centre fixed work paid G times, which is what holds the mode at
 // 0.55 of linear scaling on 8 GPUs (profiles/r02_multi_gpu.md, section 3).  Here the centre occurrences of the all-gathered batch are first
-// bucketed by table row (counting sort: count / scan / fill, kernels of this file), then one warp owns a contiguous span of the sorted
+// bucketed by table row (counting sort: count / scan / two-pass fill, kernels of this file), then one warp owns a contiguous span of the sorted
 // list, 32 entries at a time:
 //   * a run of entries with the same row keeps the centre row in registers: it is read ONCE per run (prefetched while the previous run is
 //     computed) and the accumulated update goes back with ONE vector reduction at the end of the run -- over NVLink that is two rows per
@@ -44,14 +44,52 @@ cen_count_kernel(const SgnsArgs a, unsigned long long *__restrict__ cnt) {
     }
 }
 
+// Bucket fill in two passes.  Writing every centre straight to its row's range is 147 M random 8-byte stores into a 1.2 GB array
+// (12 ms per step on S3 at 8 GPUs).  Pass 1 scatters the centres, in token order, into at most 2048 COARSE buckets of 2^cshift
+// consecutive rows (a coarse bucket's range is known from the row-level scan): a block takes a tile of 16 K centres, histograms it in
+// shared memory, reserves ONE range per non-empty bucket with a single global atomic, and writes its entries there -- few write
+// heads, so sectors fill up in L2, and 8x fewer global atomics than entries.  Pass 2 reads that array in order -- the threads in
+// flight cover a few coarse buckets at a time -- and places every entry in its row's range, inside a window of a few MB.
+constexpr int COARSE_BUCKETS = 2048, COARSE_TILE = 16384;
+
 __global__ void __launch_bounds__(256)
-cen_fill_kernel(const SgnsArgs a, const int64_t *__restrict__ start, unsigned long long *__restrict__ cnt, int2 *__restrict__ entries) {
-    for (int64_t u = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; u < a.n_units; u += (int64_t)gridDim.x * blockDim.x) {
-        const int row = centre_row(a, (uint32_t)u);
-        if (row >= 0 && row < a.vocab) {
-            const int64_t pos = start[row] + (int64_t)atomicAdd(cnt + row, ~0ull) - 1;       // the range fills from its end; order is immaterial
-            entries[pos] = make_int2((int)u, row);
+cen_coarse_kernel(const SgnsArgs a, const int64_t *__restrict__ start, int cshift, unsigned long long *__restrict__ ccur, int2 *__restrict__ tmp) {
+    __shared__ int hist[COARSE_BUCKETS];
+    __shared__ int base[COARSE_BUCKETS];
+    for (int64_t t0 = (int64_t)blockIdx.x * COARSE_TILE; t0 < a.n_units; t0 += (int64_t)gridDim.x * COARSE_TILE) {
+        const int64_t t1 = min(a.n_units, t0 + COARSE_TILE);
+        for (int b = threadIdx.x; b < COARSE_BUCKETS; b += blockDim.x) hist[b] = 0;
+        __syncthreads();
+        for (int64_t u = t0 + threadIdx.x; u < t1; u += blockDim.x) {
+            const int row = centre_row(a, (uint32_t)u);
+            if (row >= 0 && row < a.vocab) atomicAdd(&hist[row >> cshift], 1);
         }
+        __syncthreads();
+        for (int b = threadIdx.x; b < COARSE_BUCKETS; b += blockDim.x) {
+            const int n = hist[b];
+            if (n > 0) base[b] = (int)(start[(int64_t)b << cshift] + (int64_t)atomicAdd(ccur + b, (unsigned long long)n));
+            hist[b] = 0;                                       // becomes the block's cursor inside its reserved range
+        }
+        __syncthreads();
+        for (int64_t u = t0 + threadIdx.x; u < t1; u += blockDim.x) {
+            const int row = centre_row(a, (uint32_t)u);
+            if (row >= 0 && row < a.vocab) {
+                const int b = row >> cshift;
+                tmp[base[b] + atomicAdd(&hist[b], 1)] = make_int2((int)u, row);
+            }
+        }
+        __syncthreads();
+    }
+}
+
+__global__ void __launch_bounds__(256)
+cen_fine_kernel(const int2 *__restrict__ tmp, const int64_t *__restrict__ n_entries_p, const int64_t *__restrict__ start,
+                unsigned long long *__restrict__ cnt, int2 *__restrict__ entries) {
+    const int64_t n = *n_entries_p;
+    for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (int64_t)gridDim.x * blockDim.x) {
+        const int2 t = tmp[i];
+        const int64_t pos = start[t.y] + (int64_t)atomicAdd(cnt + t.y, ~0ull) - 1;            // the range fills from its end; order is immaterial
+        entries[pos] = t;
     }
 }
 
@@ -290,11 +328,14 @@ int launch_owned_pairs(const SgnsArgs &a, const int2 *entries, const int64_t *n_
 }  // namespace
 }  // namespace se
 
-// scratch layout (bytes): cnt[vocab + 1] u64 | start[vocab + 1] i64 | scan scratch | entries[n_centres] int2 (16-byte aligned)
+using se::COARSE_BUCKETS;
+
+// scratch layout (bytes): cnt[vocab + 1] u64 | start[vocab + 1] i64 | coarse cursors[2048] u64 | scan scratch |
+//                         entries[n_centres] int2 (16-byte aligned) | coarse-ordered copy[n_centres] int2
 extern "C" int64_t se_pairs_owned_scratch_bytes(int64_t vocab, int64_t n_seq, int seq_len, int radius) {
     if (vocab < 1 || n_seq < 0 || radius < 1 || seq_len < 2 * radius + 1) return -1;
     const int64_t n_units = n_seq * (seq_len - 2 * radius);
-    return 8 * (2 * (vocab + 1) + se::scan_scratch_elems(vocab + 1)) + 8 * n_units + 64;
+    return 8 * (2 * (vocab + 1) + COARSE_BUCKETS + se::scan_scratch_elems(vocab + 1)) + 16 * n_units + 64;
 }
 
 extern "C" int se_sgns_update_pairs_owned(float *w_in, float *w_out, int64_t vocab, int emb, const int32_t *tokens, int64_t n_seq,
@@ -340,16 +381,23 @@ extern "C" int se_sgns_update_pairs_owned(float *w_in, float *w_out, int64_t voc
 
     unsigned long long *cnt = reinterpret_cast<unsigned long long *>(scratch);
     int64_t *start = reinterpret_cast<int64_t *>(cnt + vocab + 1);
-    int64_t *scan_scratch = start + vocab + 1;
+    unsigned long long *ccur = reinterpret_cast<unsigned long long *>(start + vocab + 1);
+    int64_t *scan_scratch = reinterpret_cast<int64_t *>(ccur + COARSE_BUCKETS);
     int64_t *after = scan_scratch + se::scan_scratch_elems(vocab + 1);
     int2 *entries = reinterpret_cast<int2 *>((reinterpret_cast<uintptr_t>(after) + 15) & ~(uintptr_t)15);
+    int2 *tmp = entries + n_units;
+    int cshift = 0;                                            // coarse bucket = 2^cshift consecutive rows, at most COARSE_BUCKETS of them
+    while (((vocab - 1) >> cshift) >= COARSE_BUCKETS) ++cshift;
 
     SE_CUDA(cudaMemsetAsync(cnt, 0, sizeof(unsigned long long) * (size_t)(vocab + 1), st));
+    SE_CUDA(cudaMemsetAsync(ccur, 0, sizeof(unsigned long long) * COARSE_BUCKETS, st));
     int64_t cb = (n_units + 255) / 256; if (cb > (int64_t)sms * 16) cb = (int64_t)sms * 16; if (cb < 1) cb = 1;
     se::cen_count_kernel<<<(int)cb, 256, 0, st>>>(a, cnt);
     int rc = se::exclusive_scan(reinterpret_cast<const int64_t *>(cnt), vocab + 1, start, scan_scratch, st);      // start[vocab] = valid centres
     if (rc != SE_OK) return rc;
-    se::cen_fill_kernel<<<(int)cb, 256, 0, st>>>(a, start, cnt, entries);
+    int64_t tb = (n_units + se::COARSE_TILE - 1) / se::COARSE_TILE; if (tb > (int64_t)sms * 8) tb = (int64_t)sms * 8; if (tb < 1) tb = 1;
+    se::cen_coarse_kernel<<<(int)tb, 256, 0, st>>>(a, start, cshift, ccur, tmp);
+    se::cen_fine_kernel<<<(int)cb, 256, 0, st>>>(tmp, start + vocab, start, cnt, entries);
     rc = se::check_cuda(cudaGetLastError(), "centre bucketing");
     if (rc != SE_OK) return rc;
     if (positives)

@@ -582,7 +582,7 @@ def sgns_update_pairs_owned(w_in, w_out, tokens: torch.Tensor, radius: int, n_ne
             int(row_offset), _ptr(alias['prob'], torch.float32) if alias else None, _ptr(alias['alias'], torch.int32) if alias else None,
             float(lr), int(seed) & (2 ** 64 - 1), int(centre_id_base), ctypes.byref(spec), scratch.data_ptr(), scratch.numel(),
             stats.data_ptr() if stats is not None else None, _stream()))
-    _launches += 8          # count, 5 scan kernels, fill, update
+    _launches += 9          # count, 5 scan kernels, coarse + fine fill, update
 
 
 def pairs_owned_scratch_bytes(vocab: int, n_seq: int, seq_len: int, radius: int) -> int:
