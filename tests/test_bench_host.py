@@ -31,7 +31,7 @@ def test_workload_config_names_the_parallelism():
     cfg = bench.workload_config(a, 8)
     assert cfg['nodes'] == 10_000_000 and cfg['edges'] == 250_000_000 and cfg['walk_len'] == 80 and cfg['emb'] == 128
     # the N > 1 headline keeps the reference's negative distribution (uniform over the WHOLE table), like N = 1: owner-computes on striped tables
-    assert 'row-striped' in cfg['parallelism'] and 'owns the negative row' in cfg['parallelism']
+    assert 'row-striped' in cfg['parallelism'] and 'whose W_out row it owns' in cfg['parallelism'] and 'se_sgns_update_pairs_owned' in cfg['parallelism']
     assert cfg['negative_sampling'] == 'uniform (reference)' == bench.workload_config(_args([]), 1)['negative_sampling']
     a = _args(['--gpus', '8', '--negatives', 'local'])
     cfg = bench.workload_config(a, 8)
