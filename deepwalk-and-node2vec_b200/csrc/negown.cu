@@ -30,6 +30,15 @@ namespace {
 constexpr int NGO_P = 8, NGO_SHIFT = 2;      // rows per pass; lanes per row after the transposed reduction (32 / 8 = 4)
 constexpr int NGO_LIST = 176;                // a remainder of < 8 ids + one draw round of at most 128 negatives + 32 contexts (+ 8: vector reads of a ragged pass)
 
+// 4-byte asynchronous copies for the context tokens staged a chunk ahead (kept here: sgns_common.cuh is part of the window kernel's
+// profiled source set, profiles/sgns_traffic.json)
+__device__ __forceinline__ void cp_async4(int *smem_dst, const int32_t *gsrc) {
+    const unsigned saddr = (unsigned)__cvta_generic_to_shared(smem_dst);
+    asm volatile("cp.async.ca.shared.global [%0], [%1], 4;" ::"r"(saddr), "l"(gsrc) : "memory");
+}
+__device__ __forceinline__ void cp_async_commit() { asm volatile("cp.async.commit_group;" ::: "memory"); }
+__device__ __forceinline__ void cp_async_wait_group1() { asm volatile("cp.async.wait_group 1;" ::: "memory"); }
+
 __device__ __forceinline__ int centre_row(const SgnsArgs &a, uint32_t u) {
     const uint32_t sq = u / (uint32_t)a.n_cen;
     return __ldg(a.tokens + (int64_t)sq * a.seq_len + a.radius + (int)(u - sq * (uint32_t)a.n_cen)) + a.row_offset;

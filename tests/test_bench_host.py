@@ -63,3 +63,12 @@ def test_reference_arm_can_still_time_the_port():
     assert out.returncode == 0, out.stderr[-2000:]
     line = json.loads(out.stdout.strip().splitlines()[-1])
     assert line['cpu_baseline']['kind'] == 'port' and line['value'] > 0
+
+
+def test_recorded_dram_traffic_belongs_to_the_current_window_kernel_sources():
+    # profiles/sgns_traffic.json is stamped with a hash of the window kernel's source set (tools_dev/make_traffic_json.py); bench.py reports
+    # roofline.traffic only while that stamp matches.  A change to those files must come with a new `ncu --set full` capture.
+    rec = bench.recorded_traffic()
+    assert rec is not None and rec['dram_bytes_per_launch'], rec
+    algorithmic = 183_500_800 * bench.bytes_per_pair(128, 5, 5, window=True)
+    assert 0.9 < rec['dram_bytes_per_launch'] / algorithmic < 1.1            # DRAM traffic = the kernel's algorithmic bytes (no wasted re-reads)
