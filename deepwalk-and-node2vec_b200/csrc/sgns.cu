@@ -15,6 +15,9 @@
 #include "sgns_common.cuh"
 
 namespace se {
+
+int launch_win_wide(const SgnsArgs &a, cudaStream_t stream);        // sgns_win_wide.cu: window-resident kernel for 128 < emb <= 512 (R float4 per lane)
+
 namespace {
 
 template <int MODE, int VEC, int G, int R>
@@ -570,10 +573,12 @@ sgns_ctx_kernel(const SgnsArgs a) {
 // Returns SE_ERR_UNSUPPORTED when the shape is not covered (caller tries the next kernel).
 // ------------------------------------------------------------------------------------------------------------------
 int launch_win(const SgnsArgs &a, cudaStream_t stream) {
-    if (a.emb % 4 != 0 || a.emb < 16 || a.emb > 128 || a.n_neg > 7 || a.radius > 8 || a.scatter_store || a.no_window) return SE_ERR_UNSUPPORTED;
+    if (a.emb % 4 != 0 || a.emb < 16 || a.emb > 512 || a.n_neg > 7 || a.radius > 8 || a.scatter_store || a.no_window) return SE_ERR_UNSUPPORTED;
     if (((uintptr_t)a.w_in % 16) || ((uintptr_t)a.w_out % 16)) return SE_ERR_UNSUPPORTED;
     int rc = SE_ERR_UNSUPPORTED;
-    if (a.emb > 64) {
+    if (a.emb > 128) {
+        rc = launch_win_wide(a, stream);
+    } else if (a.emb > 64) {
         rc = launch_win_g32(a, stream);
     } else if (a.emb > 32) {
         rc = launch_win_g16(a, stream);

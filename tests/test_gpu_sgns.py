@@ -306,7 +306,8 @@ def test_fast_and_generic_kernels_agree(emb, radius, k):
 
 
 @pytest.mark.parametrize('emb,radius,k,length,n_seq', [(128, 5, 5, 80, 300), (128, 2, 3, 10, 700), (96, 3, 2, 9, 50), (128, 1, 7, 3, 40), (128, 8, 1, 40, 9), (128, 9, 2, 25, 30),
-                                                       (48, 2, 3, 10, 100), (64, 3, 5, 20, 50), (36, 1, 2, 5, 64)])
+                                                       (48, 2, 3, 10, 100), (64, 3, 5, 20, 50), (36, 1, 2, 5, 64),
+                                                       (256, 5, 5, 40, 60), (192, 2, 3, 10, 300)])           # wide rows: sgns_win_wide.cu
 def test_window_resident_kernel_equals_sequential_oracle(emb, radius, k, length, n_seq):
     """sgns_win_kernel keeps the context rows of the window in shared memory and scatters each token's accumulated update
     once, when it leaves the window.  The result must equal a SEQUENTIAL oracle (up to the staleness of concurrent warps):
@@ -423,7 +424,8 @@ def _repeating_sequences(rng, n_seq, length, pool_size, vocab, offset):
     return out
 
 
-@pytest.mark.parametrize('emb,radius,k', [(128, 5, 0), (128, 2, 3), (100, 3, 2), (64, 2, 3), (48, 5, 3), (32, 2, 5), (20, 3, 1)])
+@pytest.mark.parametrize('emb,radius,k', [(128, 5, 0), (128, 2, 3), (100, 3, 2), (64, 2, 3), (48, 5, 3), (32, 2, 5), (20, 3, 1),
+                                          (256, 5, 3), (200, 2, 2), (320, 3, 5)])                            # wide rows: sgns_win_wide.cu (R = 2, 2, 4)
 def test_window_kernel_with_repeated_tokens_equals_the_sequential_oracle(emb, radius, k):
     """tokens that repeat INSIDE a window (A-B-A walks, sentences).  Window positions holding the same row
     alias one shared-memory slot, so a lane group applies the pairs of its sequence exactly like a sequential pair-by-pair SGD

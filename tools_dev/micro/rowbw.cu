@@ -58,7 +58,66 @@ void run(float *tab, uint32_t vocab, float *sink, int blocks_per_sm, const char 
            cudaGetErrorString(cudaGetLastError()));
 }
 
-int main() {
+// mode "mix": the row mix of the S3 window kernel without its arithmetic.  One warp per "centre": the centre row of W_in is read at the
+// start and reduced at the end; N contexts follow, each gathering K random rows of W_out and reducing into the same rows with values that
+// depend on the loaded data (so a red waits for its loads, as in the kernel); per centre one more W_out row is read (the context row that
+// enters the window) and a different one is reduced (the row that leaves).  Bytes per centre = 512 * 2 * (1 + N K + 1).
+template <int K, int N>
+__global__ void __launch_bounds__(256) kmix(float *w_in, float *w_out, uint32_t vocab, int64_t centres, float *sink) {
+    const int lane = threadIdx.x & 31;
+    const int64_t warp = ((int64_t)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+    const int64_t nw = ((int64_t)gridDim.x * blockDim.x) >> 5;
+    float keep = 0.f;
+    for (int64_t c = warp; c < centres; c += nw) {
+        const uint32_t base = (uint32_t)c * (uint32_t)(N * K + 3);
+        const float4 cen = __ldcg(reinterpret_cast<const float4 *>(w_in + (int64_t)__umulhi(hash32(base * 2654435761u + 1u), vocab) * 128) + lane);
+        const float4 ent = __ldcg(reinterpret_cast<const float4 *>(w_out + (int64_t)__umulhi(hash32((base + 1) * 2654435761u + 1u), vocab) * 128) + lane);
+        float4 acc = make_float4(0.f, 0.f, 0.f, 0.f);
+        for (int n = 0; n < N; ++n) {
+            float4 r[K];
+            uint32_t id[K];
+#pragma unroll
+            for (int i = 0; i < K; ++i) id[i] = __umulhi(hash32((base + 3 + n * K + i) * 2654435761u + 1u), vocab);
+#pragma unroll
+            for (int i = 0; i < K; ++i) r[i] = __ldcg(reinterpret_cast<const float4 *>(w_out + (int64_t)id[i] * 128) + lane);
+#pragma unroll
+            for (int i = 0; i < K; ++i) {
+                const float s = (r[i].x * cen.x + r[i].y * cen.y) * 1e-30f;
+                acc.x += s; acc.y += r[i].z * 1e-30f;
+                red4(w_out + (int64_t)id[i] * 128 + lane * 4, make_float4(s, s, s, s));
+            }
+        }
+        red4(w_out + (int64_t)__umulhi(hash32((base + 2) * 2654435761u + 1u), vocab) * 128 + lane * 4, make_float4(ent.x * 1e-30f, acc.y, 0.f, 0.f));
+        red4(w_in + (int64_t)__umulhi(hash32(base * 2654435761u + 1u), vocab) * 128 + lane * 4, acc);
+        keep += acc.x;
+    }
+    if (keep == 123.456f) *sink = keep;
+}
+
+template <int K, int N>
+void run_mix(float *w_in, float *w_out, uint32_t vocab, float *sink, int blocks_per_sm) {
+    const int64_t centres = 18350080 / 4;                        // a quarter of one S3 launch (262,144 walks x 70 centres)
+    cudaEvent_t e0, e1; cudaEventCreate(&e0); cudaEventCreate(&e1);
+    const int grid = 148 * blocks_per_sm;
+    kmix<K, N><<<grid, 256>>>(w_in, w_out, vocab, centres / 8, sink);
+    cudaEventRecord(e0);
+    kmix<K, N><<<grid, 256>>>(w_in, w_out, vocab, centres, sink);
+    cudaEventRecord(e1); cudaEventSynchronize(e1);
+    float ms; cudaEventElapsedTime(&ms, e0, e1);
+    const double bytes = (double)centres * 512.0 * 2.0 * (1 + N * K + 1);
+    printf("S3 row mix (K=%d, N=%d), no arithmetic   blocks/SM=%d (%d warps/SM)  %8.2f ms  %8.1f GB/s  (%s)\n", K, N, blocks_per_sm, blocks_per_sm * 8, ms,
+           bytes / ms / 1e6, cudaGetErrorString(cudaGetLastError()));
+}
+
+int main(int argc, char **argv) {
+    if (argc > 1 && argv[1][0] == 'm') {                         // ./rowbw mix: only the S3 row-mix ceiling (two tables of 10 M x 128 floats, as S3)
+        const uint32_t vocab = 10000001;
+        float *w_in, *w_out, *sink;
+        cudaMalloc(&w_in, (size_t)vocab * 512); cudaMemset(w_in, 0, (size_t)vocab * 512);
+        cudaMalloc(&w_out, (size_t)vocab * 512); cudaMemset(w_out, 0, (size_t)vocab * 512); cudaMalloc(&sink, 4);
+        for (int bps : {2, 3, 4, 8}) run_mix<5, 10>(w_in, w_out, vocab, sink, bps);
+        return 0;
+    }
     const uint32_t vocab = 10000001;
     float *tab, *sink;
     cudaMalloc(&tab, (size_t)vocab * 512); cudaMemset(tab, 0, (size_t)vocab * 512); cudaMalloc(&sink, 4);
