@@ -661,7 +661,8 @@ def run_b200(a, rank, local_rank, world):
         bpp = 2.0 * 4.0 * a.emb * (1.0 + a.neg)        # every output row of a pair is read and reduced once, in the owner's HBM
     bpp_survey = bytes_per_pair(a.emb, a.neg, a.radius, False)
     achieved = pairs_per_step * bpp / (sgns_ms / 1e3) / 1e9
-    traffic = recorded_traffic()
+    # the ncu capture is one launch of THIS configuration (E = 128, K = 5, r = 5, 262,144 walks of 80): other shapes carry no traffic figure
+    traffic = recorded_traffic() if (a.emb, a.neg, a.radius, a.kernel, pairs_per_step) == (128, 5, 5, 'window', 183_500_800) else None
     line = {
         'metric': METRIC, 'value': value, 'unit': UNIT, 'n_gpus': world, 'steps': a.steps, 'warmup': a.warmup,
         'ms_per_step': ms_total / a.steps, 'higher_is_better': True, 'scaling': 'weak', 'vs_baseline': None, 'dtype': 'f32',

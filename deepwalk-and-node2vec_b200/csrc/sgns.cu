@@ -569,7 +569,8 @@ sgns_ctx_kernel(const SgnsArgs a) {
 
 
 // ------------------------------------------------------------------------------------------------------------------
-// Window-resident kernel family: sgns_win.cuh, instantiated per lane-group width in sgns_win_g*.cu.
+// Window-resident kernel family: sgns_win.cuh, instantiated per lane-group width in sgns_win_g*.cu (16 <= emb <= 128), and
+// sgns_win_wide.cu (128 < emb <= 512, R float4 per lane).
 // Returns SE_ERR_UNSUPPORTED when the shape is not covered (caller tries the next kernel).
 // ------------------------------------------------------------------------------------------------------------------
 int launch_win(const SgnsArgs &a, cudaStream_t stream) {
