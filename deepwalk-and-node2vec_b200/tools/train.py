@@ -119,6 +119,14 @@ def train(cfg, keep: bool = False, quiet: bool = False):
     return trainer, dataset
 
 
+def owner_centre_id_base(epoch: int, lo: int, share: int, world: int, n_walks_global: int, n_cen: int) -> int:
+    """Philox id of centre 0 of RANK 0's walks in the owner-computes step that starts at walk `lo` of every rank's share of `epoch`: a function
+    of (epoch, lo) only, so every rank derives the same base whatever its own iteration count is (ranks may hold one walk more or less when
+    len(dataset) % world != 0), and consecutive steps / epochs get disjoint id ranges of world * share * n_cen centres each."""
+    steps_per_epoch = -(-n_walks_global // (share * world))
+    return (epoch * steps_per_epoch + lo // share) * world * share * n_cen
+
+
 def fit_fused(cfg, dataset, trainer, end_of_epoch, rank: int = 0, world: int = 1):
     """Walk kernel + fused SGNS kernel; one launch per `batch_size` walks so that a launch is the reference's mini-batch.
     world > 1: this rank's share of every batch (walks rank, rank + world, ...) against the striped tables."""
@@ -156,10 +164,7 @@ def fit_fused(cfg, dataset, trainer, end_of_epoch, rank: int = 0, world: int = 1
                                                                  # a ragged last batch falls back to fetching the rows
                 from shallow_encoders.word2vec.sharded import sgns_update_walks_owner_computes
                 w_in, w_out = trainer.model.tables
-                # Philox id of centre 0 of rank 0's walks in this step: a function of (epoch, lo) only, so every rank derives the same base
-                # whatever its own iteration count is
-                steps_per_epoch = -(-n_walks_global // (share * world))
-                cid_base = (epoch * steps_per_epoch + lo // share) * world * share * n_cen
+                cid_base = owner_centre_id_base(epoch, lo, share, world, n_walks_global, n_cen)
                 sgns_update_walks_owner_computes(w_in, w_out, chunk, r, cfg.train.loss.negative_samples, dataset.row_offset, lr_batch / pairs,
                                                  seed, cid_base, rank, world, stats=stats)
             else:

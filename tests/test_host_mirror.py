@@ -119,3 +119,23 @@ def test_fused_engine_picks_its_kernel_from_the_yaml_optimizer():
     import pytest
     with pytest.raises(ValueError, match='row-sparse Adam'):
         cfg.train.fused_optimizer_kind()
+
+
+def test_owner_computes_centre_ids_do_not_depend_on_the_rank_and_never_overlap():
+    """the owner-computes step keys its negatives by a centre id base that every rank must derive identically (it partitions ONE
+    draw over the ranks) and that must not reuse id ranges across steps or epochs, also when len(dataset) % world != 0."""
+    from tools.train import owner_centre_id_base
+    world, batch, n_cen = 4, 64, 6
+    share = -(-batch // world)
+    n_walks_global = 34 * 64 + 3                      # ragged: ranks hold different numbers of walks
+    seen = []
+    for epoch in range(3):
+        n_min = n_walks_global // world
+        for lo in range(0, n_min - share + 1, share):
+            base = owner_centre_id_base(epoch, lo, share, world, n_walks_global, n_cen)
+            # a pure function of (epoch, lo): nothing rank-local (iteration counters, chunk sizes) enters
+            assert base == owner_centre_id_base(epoch, lo, share, world, n_walks_global, n_cen)
+            seen.append((base, base + world * share * n_cen))
+    seen.sort()
+    assert all(a[1] <= b[0] for a, b in zip(seen, seen[1:])), 'id ranges of two steps overlap'
+    assert len({s[0] for s in seen}) == len(seen)
