@@ -168,13 +168,14 @@ def test_local_negatives_stay_on_the_owning_shard_and_match_the_oracle(rank, use
 
 
 @pytest.mark.parametrize('grouped', [True, False])
-@pytest.mark.parametrize('use_alias,emb', [(False, 128), (True, 128), (False, 96)])
-def test_owner_computes_negatives_perform_the_same_pair_updates(use_alias, emb, grouped):
+@pytest.mark.parametrize('use_alias,emb,world', [(False, 128, 2), (True, 128, 2), (False, 96, 2), (False, 128, 3), (True, 128, 4)])
+def test_owner_computes_negatives_perform_the_same_pair_updates(use_alias, emb, world, grouped):
     """Positives on the home rank (window kernel, K = 0) + owner-computes negatives on every simulated rank == the pair
-    updates of the ordinary fused kernel == the oracle's mini-batch SGD, with the GLOBAL negative distribution."""
+    updates of the ordinary fused kernel == the oracle's mini-batch SGD, with the GLOBAL negative distribution.
+    world = 2 / 4 take the mask path of the ownership test (power-of-two GPU counts), world = 3 the modulo path."""
     dev = cuda_device()
     rng = np.random.default_rng(51)
-    radius, k, n_seq, offset, world = 2, 4, 10, 1, 2
+    radius, k, n_seq, offset = 2, 4, 10, 1
     vocab = (4096 if emb == 128 else 16384) * 5 + 100          # 96 floats per row: 6 MiB stripes of 16384 rows
     alias = None
     prob = ali = None
