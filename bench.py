@@ -167,8 +167,8 @@ def workload_config(a, n_gpus):
 def sgns_kernel_label(emb, neg, window):
     """Name of the kernel `se_sgns_update_walks` dispatches to for this shape (csrc/sgns.cu::launch, launch_win)."""
     t = 1 + neg
-    if window and emb % 4 == 0 and 128 < emb <= 512 and 1 <= neg <= 7:
-        return f'sgns_winw_kernel<R={2 if emb <= 256 else 4}, T={t}> (E={emb}; csrc/sgns_win_wide.cu)'
+    if window and emb % 4 == 0 and 128 < emb <= 256 and 1 <= neg <= 7:
+        return f'sgns_winw_kernel<R=2, T={t}> (E={emb}; csrc/sgns_win_wide.cu)'
     if window and emb % 4 == 0 and 16 <= emb <= 128 and neg <= 7:
         g = 32 if emb > 64 else (16 if emb > 32 else 8)
         return f'sgns_win_kernel<G={g}, T={t}, EXACT={"true" if emb == 128 else "false"}> (E={emb})'

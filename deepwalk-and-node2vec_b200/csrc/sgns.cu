@@ -16,7 +16,7 @@
 
 namespace se {
 
-int launch_win_wide(const SgnsArgs &a, cudaStream_t stream);        // sgns_win_wide.cu: window-resident kernel for 128 < emb <= 512 (R float4 per lane)
+int launch_win_wide(const SgnsArgs &a, cudaStream_t stream);        // sgns_win_wide.cu: window-resident kernel for 128 < emb <= 256 (two float4 per lane)
 
 namespace {
 
@@ -570,11 +570,11 @@ sgns_ctx_kernel(const SgnsArgs a) {
 
 // ------------------------------------------------------------------------------------------------------------------
 // Window-resident kernel family: sgns_win.cuh, instantiated per lane-group width in sgns_win_g*.cu (16 <= emb <= 128), and
-// sgns_win_wide.cu (128 < emb <= 512, R float4 per lane).
+// sgns_win_wide.cu (128 < emb <= 256, two float4 per lane).
 // Returns SE_ERR_UNSUPPORTED when the shape is not covered (caller tries the next kernel).
 // ------------------------------------------------------------------------------------------------------------------
 int launch_win(const SgnsArgs &a, cudaStream_t stream) {
-    if (a.emb % 4 != 0 || a.emb < 16 || a.emb > 512 || a.n_neg > 7 || a.radius > 8 || a.scatter_store || a.no_window) return SE_ERR_UNSUPPORTED;
+    if (a.emb % 4 != 0 || a.emb < 16 || a.emb > 256 || a.n_neg > 7 || a.radius > 8 || a.scatter_store || a.no_window) return SE_ERR_UNSUPPORTED;
     if (((uintptr_t)a.w_in % 16) || ((uintptr_t)a.w_out % 16)) return SE_ERR_UNSUPPORTED;
     int rc = SE_ERR_UNSUPPORTED;
     if (a.emb > 128) {

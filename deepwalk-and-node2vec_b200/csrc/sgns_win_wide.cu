@@ -1,4 +1,4 @@
-// Window-resident SGNS kernel for WIDE rows (128 < emb <= 512), sm_100a: the scheme of sgns_win.cuh with R float4 per lane.
+// Window-resident SGNS kernel for WIDE rows (128 < emb <= 256), sm_100a: the scheme of sgns_win.cuh with R = 2 float4 per lane.
 //
 // One warp owns one centre; a row of up to 128 R floats is R coalesced 512-byte chunks (lane l holds floats (32 i + l) 4 .. + 3 of
 // chunk i).  The W_out rows of the 2r+1 tokens around the centre stay RESIDENT in shared memory (ring of 2r+2 physical slots per
@@ -10,9 +10,12 @@
 // arithmetic as word2vec/loss.py:15-16.  Before this kernel rows wider than 128 floats went to sgns_fast_kernel, which gathers
 // and scatters every context row 2r times through L2.
 //
-// Geometry: blocks of 4 warps.  R = 2 (emb <= 256): 24 KB of ring per warp at r = 5, two blocks of 96 KB per SM (one block up to
-//           r = 8); R = 4 (emb <= 512): 48 KB per warp, one block of 192 KB per SM up to r = 5.  If the ring does not fit the
-//           launcher reports SE_ERR_UNSUPPORTED and the caller falls back to sgns_fast_kernel.
+// Geometry: blocks of 4 warps, 24 KB of ring per warp at r = 5: two blocks of 96 KB per SM (one block up to r = 8).  If the ring does not
+//           fit the launcher reports SE_ERR_UNSUPPORTED and the caller falls back to sgns_fast_kernel.
+// Measured (profiles/r02e_summary.md): S4 token stream at E = 256: 0.478 G pairs/s against 0.314 G for sgns_fast_kernel; on HBM-resident
+// tables (S3 shape) 0.476 against 0.494 G -- 8 warps per SM are few for DRAM latency.  R = 4 (emb <= 512, 48 KB of ring per warp, 4 warps
+// per SM) was built and measured too: 0.174 G against 0.224 G for sgns_fast_kernel on the S4 stream -- slower, so rows wider than 256
+// floats stay on sgns_fast_kernel and only R = 2 is instantiated.
 // The file is separate from sgns_win.cuh on purpose: that header is the profiled source set of the S3 bench kernel
 // (profiles/sgns_traffic.json is stamped with its hash).
 #include "sgns_common.cuh"
@@ -21,7 +24,7 @@ namespace se {
 namespace {
 
 template <int R, int T, int THREADS>
-__global__ void __launch_bounds__(THREADS, (R <= 2) ? 2 : 1)
+__global__ void __launch_bounds__(THREADS, 2)
 sgns_winw_kernel(const SgnsArgs a) {
     constexpr int G = 32;
     constexpr int K = T - 1;
@@ -316,10 +319,10 @@ int launch_winw_t(const SgnsArgs &a, cudaStream_t stream) {
 
 }  // namespace
 
-// 128 < emb <= 512, emb % 4 == 0, 1 <= n_neg <= 7, radius <= 8; SE_ERR_UNSUPPORTED otherwise (caller tries the next kernel)
+// 128 < emb <= 256, emb % 4 == 0, 1 <= n_neg <= 7, radius <= 8; SE_ERR_UNSUPPORTED otherwise (caller tries the next kernel)
 int launch_win_wide(const SgnsArgs &a, cudaStream_t stream) {
-    if (a.emb <= 128 || a.emb > 512 || a.emb % 4 != 0 || a.radius > 8) return SE_ERR_UNSUPPORTED;
-    return a.emb <= 256 ? launch_winw_t<2>(a, stream) : launch_winw_t<4>(a, stream);
+    if (a.emb <= 128 || a.emb > 256 || a.emb % 4 != 0 || a.radius > 8) return SE_ERR_UNSUPPORTED;
+    return launch_winw_t<2>(a, stream);
 }
 
 }  // namespace se

@@ -425,7 +425,7 @@ def _repeating_sequences(rng, n_seq, length, pool_size, vocab, offset):
 
 
 @pytest.mark.parametrize('emb,radius,k', [(128, 5, 0), (128, 2, 3), (100, 3, 2), (64, 2, 3), (48, 5, 3), (32, 2, 5), (20, 3, 1),
-                                          (256, 5, 3), (200, 2, 2), (320, 3, 5)])                            # wide rows: sgns_win_wide.cu (R = 2, 2, 4)
+                                          (256, 5, 3), (200, 2, 2), (224, 3, 5)])                            # wide rows: sgns_win_wide.cu
 def test_window_kernel_with_repeated_tokens_equals_the_sequential_oracle(emb, radius, k):
     """tokens that repeat INSIDE a window (A-B-A walks, sentences).  Window positions holding the same row
     alias one shared-memory slot, so a lane group applies the pairs of its sequence exactly like a sequential pair-by-pair SGD
