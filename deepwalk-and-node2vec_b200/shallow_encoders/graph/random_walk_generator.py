@@ -71,8 +71,44 @@ class RandomWalk(ABC):
             self._index = {name: i for i, name in enumerate(self.node_names)}
         return torch.tensor([self._index[str(n)] for n in nodes], dtype=torch.int32, device=self._device)
 
+    # The reference's per-node accessors (:41-53).  The kernels never call them (they read the CSR); they are kept so that code written
+    # against the reference's RandomWalk keeps working, for networkx graphs and for CSR graphs alike.
+    def _csr_row(self, node: str):
+        c = self._graph
+        if self._index is None:
+            self._index = {name: i for i, name in enumerate(self.node_names)}
+        v = self._index[str(node)]
+        lo, hi = int(c.rowptr[v].item()), int(c.rowptr[v + 1].item())
+        return lo, hi
+
     def get_node_neighbors(self, node: str) -> List[str]:
+        """Neighbours in the order the CDF is built over (networkx adjacency order; `col` of a CSR graph)."""
+        if isinstance(self._graph, CSRGraph):
+            lo, hi = self._csr_row(node)
+            names = self.node_names
+            return [names[j] for j in self._graph.col[lo:hi].tolist()]
         return list(self._graph.neighbors(node))
+
+    def get_node_unnormalized_edge_weights(self, node: str) -> list:
+        """Edge weights aligned with `get_node_neighbors`; all 1 unless EVERY edge of the graph carries a `weight` (nx.is_weighted, :45-48).
+        (The reference re-scans all edges on every call; the answer cannot change during training, so it is computed once.)"""
+        if isinstance(self._graph, CSRGraph):
+            lo, hi = self._csr_row(node)
+            if self._graph.w is None:
+                return [1] * (hi - lo)
+            w = self._graph.w[lo:hi].tolist()
+            return [int(x) for x in w] if self._graph.w_is_int else w
+        if not hasattr(self, '_nx_weighted'):
+            self._nx_weighted = nx.is_weighted(self._graph)
+        neighbors = list(self._graph.neighbors(node))
+        if not self._nx_weighted:
+            return [1] * len(neighbors)
+        return [self._graph[node][neighbor]['weight'] for neighbor in neighbors]
+
+    def get_node_normalized_edge_weights(self, node: str) -> List[float]:
+        weights = self.get_node_unnormalized_edge_weights(node)
+        total = sum(weights)
+        return [w / total for w in weights]
 
     # -- walking ---------------------------------------------------------------------------------------------
     @property

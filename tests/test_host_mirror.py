@@ -139,3 +139,55 @@ def test_owner_computes_centre_ids_do_not_depend_on_the_rank_and_never_overlap()
     seen.sort()
     assert all(a[1] <= b[0] for a, b in zip(seen, seen[1:])), 'id ranges of two steps overlap'
     assert len({s[0] for s in seen}) == len(seen)
+
+
+def test_random_walk_weight_accessors_follow_the_reference():
+    """a1 of the scope table: get_node_neighbors / get_node_unnormalized_edge_weights / get_node_normalized_edge_weights
+    (graph/random_walk_generator.py:41-53) on networkx graphs (weighted only when EVERY edge carries a weight) and on CSR graphs.
+    Where the reference can be imported (here; on the GPU box from baseline/_ref) the three accessors are compared with it."""
+    import networkx as nx
+    from shallow_encoders.graph.csr import CSRGraph
+    from shallow_encoders.graph.random_walk_generator import DeepWalk
+    g = nx.karate_club_graph()                                     # every edge has an int weight
+    g = nx.relabel_nodes(g, {v: f'n{v + 1:02d}' for v in g.nodes})
+    ours = DeepWalk(g, 5, device='cpu')
+    for node in ('n01', 'n17', 'n34'):
+        nb = ours.get_node_neighbors(node)
+        assert nb == list(g.neighbors(node))
+        w = ours.get_node_unnormalized_edge_weights(node)
+        assert w == [g[node][x]['weight'] for x in nb] and all(isinstance(x, int) for x in w)
+        nw = ours.get_node_normalized_edge_weights(node)
+        assert nw == [x / sum(w) for x in w]
+    h = g.copy()
+    del h['n01']['n02']['weight']                                  # one edge without a weight: the whole graph counts as unweighted
+    assert DeepWalk(h, 5, device='cpu').get_node_unnormalized_edge_weights('n34') == [1] * h.degree('n34')
+    # the same answers from a CSR graph (host tensors are enough: the accessors do not launch anything)
+    names = sorted(g.nodes)
+    idx = {n: i for i, n in enumerate(names)}
+    rowptr, col, w = [0], [], []
+    for n in names:
+        for x in g.neighbors(n):
+            col.append(idx[x]); w.append(float(g[n][x]['weight']))
+        rowptr.append(len(col))
+    import numpy as np
+    csr = CSRGraph.from_arrays(np.array(rowptr), np.array(col), np.array(w), w_is_int=True, names=names, device='cpu')
+    on_csr = DeepWalk(csr, 5, device='cpu')
+    for node in ('n01', 'n17', 'n34'):
+        assert on_csr.get_node_neighbors(node) == ours.get_node_neighbors(node)
+        assert on_csr.get_node_unnormalized_edge_weights(node) == ours.get_node_unnormalized_edge_weights(node)
+        assert on_csr.get_node_normalized_edge_weights(node) == ours.get_node_normalized_edge_weights(node)
+    from oracle import ref_import
+    root = ref_import.reference_root()
+    if root:        # the reference module itself, loaded under a private name (it only needs random / abc / networkx)
+        import importlib.util
+        import sys
+        spec = importlib.util.spec_from_file_location('_ref_random_walk_generator', os.path.join(root, 'shallow_encoders', 'graph', 'random_walk_generator.py'))
+        ref_rwg = importlib.util.module_from_spec(spec)
+        sys.dont_write_bytecode = True
+        spec.loader.exec_module(ref_rwg)
+        for graph in (g, h):
+            ref, mine = ref_rwg.DeepWalk(graph, 5), DeepWalk(graph, 5, device='cpu')
+            for node in graph.nodes:
+                assert ref.get_node_neighbors(node) == mine.get_node_neighbors(node)
+                assert ref.get_node_unnormalized_edge_weights(node) == mine.get_node_unnormalized_edge_weights(node)
+                assert ref.get_node_normalized_edge_weights(node) == mine.get_node_normalized_edge_weights(node)
