@@ -191,3 +191,49 @@ def test_random_walk_weight_accessors_follow_the_reference():
                 assert ref.get_node_neighbors(node) == mine.get_node_neighbors(node)
                 assert ref.get_node_unnormalized_edge_weights(node) == mine.get_node_unnormalized_edge_weights(node)
                 assert ref.get_node_normalized_edge_weights(node) == mine.get_node_normalized_edge_weights(node)
+
+
+def test_split_algorithms_reproduce_the_reference_draws():
+    """shallow_encoders/split/core.py: the three split algorithms of the downstream yardstick return the reference's arrays for the same
+    seed (sklearn's train_test_split; numpy's legacy seed + shuffle sequence for the per-class sample split)."""
+    import importlib.util
+    import sys
+    from oracle import ref_import
+    from shallow_encoders.split import SplitAlgorithm, TrainTestRatioSplit, TrainValTestRatioSplit, TrainValTestStratifiedNSamplesSplit
+    from shallow_encoders.split.core import TrainTestRatioSplit as same_class
+    assert same_class is TrainTestRatioSplit and issubclass(TrainValTestRatioSplit, SplitAlgorithm)
+    rng = np.random.default_rng(3)
+    X = rng.standard_normal((300, 5))
+    y = rng.integers(0, 4, 300)
+    algo = TrainTestRatioSplit(train_ratio=0.5, test_all=True)
+    out = algo(X, y)
+    assert algo.random_state == 42 and out['X_test'].shape == X.shape and out['X_train'].shape[0] == 150 and out['X_test'] is not X
+    three = TrainValTestRatioSplit(train_ratio=0.6, val_ratio=0.8, stratify=True, random_state=7)(X, y)
+    assert [three[k].shape[0] for k in ('X_train', 'X_val', 'X_test')] == [180, 60, 60]
+    per_class = TrainValTestStratifiedNSamplesSplit(train_samples=20, val_samples=10, test_samples=15, random_state=1)(X, y)
+    assert [per_class[k].shape[0] for k in ('y_train', 'y_val', 'y_test')] == [80, 40, 60]
+    assert all((per_class['y_train'] == c).sum() == 20 for c in range(4))
+    with pytest.raises(AssertionError):
+        TrainValTestStratifiedNSamplesSplit(train_samples=200, val_samples=10)(X, y)          # a class has fewer than 200 members
+    root = ref_import.reference_root()
+    if not root:
+        return
+    spec = importlib.util.spec_from_file_location('_ref_split_core', os.path.join(root, 'shallow_encoders', 'split', 'core.py'))
+    ref = importlib.util.module_from_spec(spec)
+    sys.dont_write_bytecode = True
+    spec.loader.exec_module(ref)
+    cases = [('TrainTestRatioSplit', dict(train_ratio=0.75)), ('TrainTestRatioSplit', dict(train_ratio=0.5, stratify=True, test_all=True, random_state=5)),
+             ('TrainValTestRatioSplit', dict(train_ratio=0.6, val_ratio=0.8)), ('TrainValTestRatioSplit', dict(train_ratio=0.5, val_ratio=0.7, stratify=True, random_state=9)),
+             ('TrainValTestStratifiedNSamplesSplit', dict(train_samples=20, val_samples=10, test_samples=15, random_state=1)),
+             ('TrainValTestStratifiedNSamplesSplit', dict(train_samples=5, val_samples=7))]
+    import shallow_encoders.split as ours
+    for name, kwargs in cases:
+        want, got = getattr(ref, name)(**kwargs)(X, y), getattr(ours, name)(**kwargs)(X, y)
+        assert want.keys() == got.keys()
+        for key in want:
+            assert np.array_equal(want[key], got[key]), (name, kwargs, key)
+    moved = ours.TrainTestRatioSplit(train_ratio=0.5)
+    moved.random_state = 11                                    # the downstream tool re-seeds the algorithm per experiment
+    ref_moved = ref.TrainTestRatioSplit(train_ratio=0.5)
+    ref_moved.random_state = 11
+    assert np.array_equal(moved(X, y)['y_train'], ref_moved(X, y)['y_train'])
