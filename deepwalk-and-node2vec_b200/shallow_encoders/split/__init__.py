@@ -1,3 +1,7 @@
-"""Split algorithms of the downstream yardstick (reference package shallow_encoders/split): same names, same `_target_` paths."""
-from shallow_encoders.split.core import (SplitAlgorithm, TrainTestRatioSplit, TrainValTestRatioSplit,  # noqa: F401
-                                         TrainValTestStratifiedNSamplesSplit)
+"""Split algorithms of the downstream yardstick under the reference's package path, so that YAML `_target_` strings such as
+`shallow_encoders.split.TrainTestRatioSplit` (configs/sge_sg_cora.yaml:69-71) and `shallow_encoders.split.core.<name>` both resolve."""
+from shallow_encoders.split import core as _core
+
+__all__ = ['SplitAlgorithm', 'TrainTestRatioSplit', 'TrainValTestRatioSplit', 'TrainValTestStratifiedNSamplesSplit']
+for _name in __all__:
+    globals()[_name] = getattr(_core, _name)
