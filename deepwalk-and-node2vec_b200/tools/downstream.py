@@ -4,11 +4,25 @@ tools/graph_model_downstream_classification.py:94-148 of the reference (that mod
 imported here): X = input embedding rows 1.. ('<unk>' skipped, :116), optional feature concat (:120-123), labels mapped to
 integers, `n_experiments` splits with random_state = i (:134-136), LogisticRegression(**classifier_params) fit on the train
 split and scored on the test split (:85-91); mean and best accuracy (:146-148).
+
+Command line, like the reference's tool (tools/graph_model_downstream_classification.py:300-335):
+
+    python tools/downstream.py --config-name=sge_sg_karate_club [a.b=c ...] [--device-classifier]
+
+loads the experiment's checkpoint (`downstream.checkpoint`, default last.ckpt; the reference reads `analysis.checkpoint`, accepted too),
+runs node classification when the data set has labels and `downstream.node_classification.enable`, edge classification when
+`downstream.edge_classification.enable`, prints the reference's result lines and writes them to <experiment>/analysis/downstream.json.
 """
+import os
+import sys
 from typing import Dict, List, Optional, Tuple
 
 import numpy as np
 from sklearn.linear_model import LogisticRegression
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+if ROOT not in sys.path:
+    sys.path.insert(0, ROOT)
 
 
 def node_classification_device(embedding, itos: List[str], labels: Dict[str, str], split_algorithm, n_experiments: int,
@@ -102,3 +116,57 @@ def edge_classification(embedding, csr, train_ratio: float, n_experiments: int, 
         total += acc
         best = max(best, acc)
     return total / n_experiments, best
+
+
+def run_downstream(cfg, device_classifier: bool = False) -> Dict[str, Dict[str, float]]:
+    """The body of the reference's `main` (:301-331) for a loaded config: checkpoint -> model -> the enabled downstream tasks."""
+    import json
+    from shallow_encoders.config_parser.core import instantiate
+    assert cfg.datamodule.is_graph, 'This script supports only graph datasets!'
+    base = os.path.join(cfg.path.output_dir, cfg.datamodule.dataset_name, cfg.train.experiment)
+    dataset = cfg.datamodule.instantiate_dataset()
+    checkpoint = cfg.downstream.get('checkpoint') or (cfg.analysis or {}).get('checkpoint', 'last.ckpt')
+    trainer = cfg.instantiate_trainer(dataset=dataset, checkpoint_path=os.path.join(base, 'checkpoints', checkpoint))
+    results: Dict[str, Dict[str, float]] = {}
+    nc = cfg.downstream.get('node_classification') or {}
+    if nc.get('enable') and dataset.has_labels:
+        split_algorithm = instantiate(nc['split_algorithm'])
+        itos = dataset.vocab.get_itos()
+        if device_classifier and not dataset.has_features:      # (features live on the host: the sklearn path concatenates them)
+            mean_acc, best_acc = node_classification_device(trainer.model.tables[0], itos, dataset.labels, split_algorithm, nc['n_experiments'],
+                                                            nc.get('classifier_params'))
+        else:
+            mean_acc, best_acc = node_classification(trainer.model.input_embedding.numpy(), itos, dataset.labels, split_algorithm,
+                                                     nc['n_experiments'], nc.get('classifier_params'),
+                                                     features=dataset.features if dataset.has_features else None)      # :120-123
+        results['node_classification'] = {'mean_accuracy': mean_acc, 'best_accuracy': best_acc}
+        print(f"Node classification accuracy: {100 * mean_acc:.2f}% (averaged over {nc['n_experiments']} experiments).")
+        print(f'Best accuracy score: {100 * best_acc:.2f}%.')
+    ec = cfg.downstream.get('edge_classification') or {}
+    if ec.get('enable'):
+        csr = dataset._dataset.walk_generator.csr
+        mean_acc, best_acc = edge_classification(trainer.model.tables[0], csr, ec['train_ratio'], ec['n_experiments'], ec['operator_name'],
+                                                 ec.get('classifier_params'), row_offset=dataset.row_offset)
+        results['edge_classification'] = {'mean_accuracy': mean_acc, 'best_accuracy': best_acc}
+        print(f"Edge classification accuracy: {100 * mean_acc:.2f}% (averaged over {ec['n_experiments']} experiments).")
+        print(f'Best accuracy score: {100 * best_acc:.2f}%.')
+    os.makedirs(os.path.join(base, 'analysis'), exist_ok=True)
+    with open(os.path.join(base, 'analysis', 'downstream.json'), 'w', encoding='utf-8') as f:
+        json.dump(results, f, indent=1)
+    return results
+
+
+def main(argv=None):
+    import argparse
+    from shallow_encoders.config_parser import load_config
+    ap = argparse.ArgumentParser(description=__doc__, formatter_class=argparse.RawDescriptionHelpFormatter)
+    ap.add_argument('--config-name', required=True)
+    ap.add_argument('--device-classifier', action='store_true',
+                    help='fit the node classifier on the device (tools/device_classifier.py) instead of sklearn on a host copy of the embeddings')
+    ap.add_argument('overrides', nargs='*')
+    a = ap.parse_args(argv)
+    return run_downstream(load_config(a.config_name, a.overrides), device_classifier=a.device_classifier)
+
+
+if __name__ == '__main__':
+    main()

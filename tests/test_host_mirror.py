@@ -237,3 +237,47 @@ def test_split_algorithms_reproduce_the_reference_draws():
     ref_moved = ref.TrainTestRatioSplit(train_ratio=0.5)
     ref_moved.random_state = 11
     assert np.array_equal(moved(X, y)['y_train'], ref_moved(X, y)['y_train'])
+
+
+def test_downstream_cli_runs_the_enabled_tasks_with_the_yaml_values(tmp_path, monkeypatch):
+    """tools/downstream.py::run_downstream = the reference tool's main (tools/graph_model_downstream_classification.py:300-331): the tasks and
+    their parameters come from the `downstream` block of the YAML, the checkpoint from <output>/<dataset>/<experiment>/checkpoints.
+    (Control flow only: the classifiers and the device are replaced by recorders; the tasks themselves are tested elsewhere.)"""
+    import json
+    import types
+    from tools import downstream
+    cfg = load_config('sge_sg_karate_club', [f'path.output_dir={tmp_path}'])
+    calls = {}
+
+    class _Model:
+        tables = ('W_IN', 'W_OUT')
+        input_embedding = types.SimpleNamespace(numpy=lambda: 'HOST_EMBEDDING')
+
+    dataset = types.SimpleNamespace(has_labels=True, labels={'n01': 'a'}, has_features=False, features=None, row_offset=1,
+                                    vocab=types.SimpleNamespace(get_itos=lambda: ['<unk>', 'n01']),
+                                    _dataset=types.SimpleNamespace(walk_generator=types.SimpleNamespace(csr='CSR')))
+    monkeypatch.setattr(type(cfg.datamodule), 'instantiate_dataset', lambda self: dataset)
+
+    def fake_trainer(self, dataset=None, checkpoint_path=None, **kw):
+        calls['checkpoint'] = checkpoint_path
+        return types.SimpleNamespace(model=_Model())
+    monkeypatch.setattr(type(cfg), 'instantiate_trainer', fake_trainer)
+
+    def fake_nc(embedding, itos, labels, split_algorithm, n_experiments, classifier_params=None, features=None):
+        calls['nc'] = (embedding, itos, type(split_algorithm).__name__, split_algorithm._train_ratio, n_experiments, classifier_params, features)
+        return 0.75, 1.0
+
+    def fake_ec(embedding, csr, train_ratio, n_experiments, operator, classifier_params=None, row_offset=1, seed=0):
+        calls['ec'] = (embedding, csr, train_ratio, n_experiments, operator, classifier_params, row_offset)
+        return 0.6, 0.7
+    monkeypatch.setattr(downstream, 'node_classification', fake_nc)
+    monkeypatch.setattr(downstream, 'edge_classification', fake_ec)
+    out = downstream.run_downstream(cfg)
+    nc, ec = cfg.downstream['node_classification'], cfg.downstream['edge_classification']
+    base = os.path.join(str(tmp_path), cfg.datamodule.dataset_name, cfg.train.experiment)
+    assert calls['checkpoint'] == os.path.join(base, 'checkpoints', 'last.ckpt')
+    assert calls['nc'] == ('HOST_EMBEDDING', ['<unk>', 'n01'], 'TrainTestRatioSplit', nc['split_algorithm']['train_ratio'], nc['n_experiments'],
+                           nc.get('classifier_params'), None)
+    assert calls['ec'] == ('W_IN', 'CSR', ec['train_ratio'], ec['n_experiments'], ec['operator_name'], ec.get('classifier_params'), 1)
+    assert out == {'node_classification': {'mean_accuracy': 0.75, 'best_accuracy': 1.0}, 'edge_classification': {'mean_accuracy': 0.6, 'best_accuracy': 0.7}}
+    assert json.load(open(os.path.join(base, 'analysis', 'downstream.json'))) == out
