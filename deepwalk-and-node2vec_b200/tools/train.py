@@ -114,6 +114,8 @@ def train(cfg, keep: bool = False, quiet: bool = False):
     else:
         raise ValueError(f'unknown train.engine "{cfg.train.engine}"')
     torch.cuda.synchronize()
+    if scalars is not None:
+        scalars.close()
     if not quiet:
         print(f'trained {cfg.train.max_epochs} epochs in {time.time() - t0:.1f}s; checkpoints in {dirs["checkpoints"]}')
     return trainer, dataset
