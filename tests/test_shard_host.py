@@ -168,6 +168,57 @@ def test_row_exchange_fetch_and_push_over_gloo_world_size_2():
     assert res == {0: 'ok', 1: 'ok'}, res
 
 
+def _owner_step_worker(rank, world, port, q):
+    import torch
+    import torch.distributed as dist
+    from shallow_encoders import _native as nat
+    from shallow_encoders.word2vec import sharded
+    os.environ.update(MASTER_ADDR='127.0.0.1', MASTER_PORT=str(port), RANK=str(rank), WORLD_SIZE=str(world))
+    try:
+        dist.init_process_group('gloo', rank=rank, world_size=world)
+        calls = []
+        # the kernels are replaced by recorders: this test covers the HOST side of the multi-GPU headline step (all-gather layout, keys)
+        nat.sgns_update_pairs_owned = lambda w_in, w_out, tokens, radius, n_neg, row_offset, lr, seed, centre_id_base=0, alias=None, stats=None, \
+            positives=True, scratch=None: calls.append(('pairs', tokens.clone(), radius, n_neg, row_offset, lr, seed, centre_id_base, positives))
+        n_walks, length, radius = 6, 9, 2
+        mine = (torch.arange(n_walks * length, dtype=torch.int32).reshape(n_walks, length) + 1000 * rank)
+        sharded.sgns_update_walks_owner_computes('W_IN', 'W_OUT', mine, radius, 3, 1, 0.01, seed=77, centre_id_base=5000, rank=rank, world=world)
+        sharded.sgns_update_walks_owner_computes('W_IN', 'W_OUT', mine, radius, 3, 1, 0.01, seed=77, centre_id_base=5000, rank=rank, world=world,
+                                                 micro_walks=4)
+        dist.destroy_process_group()
+        q.put((rank, [(c[0], c[1].tolist(), *c[2:]) for c in calls]))
+    except Exception:   # noqa: BLE001
+        import traceback
+        q.put((rank, traceback.format_exc()))
+
+
+def test_owner_computes_step_gathers_the_same_batch_on_every_rank_over_gloo_world_size_2():
+    """The multi-GPU headline step (`sgns_update_walks_owner_computes`, grouped): after ONE all-gather every rank hands the SAME token matrix
+    (rank r's walks in block r) and the SAME Philox keys to `se_sgns_update_pairs_owned`, so the ranks partition one draw; with micro-batches
+    the slices of every rank's block follow with their own centre id bases.  Kernels are recorders here (world size 2, gloo, CPU)."""
+    ctx = mp.get_context('spawn')
+    q = ctx.Queue()
+    port = 29000 + os.getpid() % 300
+    procs = [ctx.Process(target=_owner_step_worker, args=(r, 2, port, q)) for r in range(2)]
+    for p in procs:
+        p.start()
+    res = dict(q.get(timeout=180) for _ in range(2))
+    for p in procs:
+        p.join(timeout=30)
+    assert isinstance(res[0], list) and isinstance(res[1], list), res
+    assert res[0] == res[1], 'ranks disagree on the gathered batch or its keys'
+    n_walks, length, radius, n_cen = 6, 9, 2, 5
+    block = lambda r: [[1000 * r + w * length + j for j in range(length)] for w in range(n_walks)]      # noqa: E731
+    first = res[0][0]
+    assert first == ('pairs', block(0) + block(1), radius, 3, 1, 0.01, 77, 5000, True)
+    micro = res[0][1:]
+    want = []
+    for lo, hi in ((0, 4), (4, 6)):
+        for r in range(2):
+            want.append(('pairs', block(r)[lo:hi], radius, 3, 1, 0.01, 77, 5000 + (r * n_walks + lo) * n_cen, True))
+    assert micro == want
+
+
 def test_replica_chunks_partition_the_table_in_float4_units():
     """se_replica_chunk (csrc/replica.cu): rank r owns a contiguous element range, the ranges tile [0, round_up4(n)) exactly."""
     from shallow_encoders import _native as nat
