@@ -281,3 +281,55 @@ def test_downstream_cli_runs_the_enabled_tasks_with_the_yaml_values(tmp_path, mo
     assert calls['ec'] == ('W_IN', 'CSR', ec['train_ratio'], ec['n_experiments'], ec['operator_name'], ec.get('classifier_params'), 1)
     assert out == {'node_classification': {'mean_accuracy': 0.75, 'best_accuracy': 1.0}, 'edge_classification': {'mean_accuracy': 0.6, 'best_accuracy': 0.7}}
     assert json.load(open(os.path.join(base, 'analysis', 'downstream.json'))) == out
+
+
+def test_cora_loader_parses_the_asset_files_like_the_reference(tmp_path, monkeypatch):
+    """a6: CoraDataset on `assets/cora/{cora.cites, cora.content}` (graph/datasets.py:183-221).  The real files are not shipped, so two small
+    files in the same layout stand in: `<cited>\t<citing>` lines (with a repeated edge) and `<paper id>\t<1433 binary words>\t<subject>` lines.
+    Graph (nodes, edges, per-node neighbour order = the CDF order of the walk rule), labels and features must equal what the unmodified
+    reference builds from the same files (run in its own process, where it can be imported)."""
+    import json
+    import subprocess
+    import sys
+    import shallow_encoders.graph.datasets as ours_mod
+    rng = np.random.default_rng(12)
+    ids = rng.choice(np.arange(1000, 99999), 40, replace=False)
+    cora = tmp_path / 'cora'
+    cora.mkdir()
+    pairs = [(int(ids[a]), int(ids[b])) for a, b in rng.integers(0, 40, (90, 2)) if a != b]
+    pairs.append(pairs[3])                                                                 # a duplicate citation
+    pairs += [(int(ids[i]), int(ids[(i + 1) % 40])) for i in range(40)]                    # a ring: no isolated paper
+    (cora / 'cora.cites').write_text(''.join(f'{t}\t{s}\n' for t, s in pairs))
+    subjects = ['Neural_Networks', 'Theory', 'Rule_Learning']
+    words = rng.integers(0, 2, (40, 1433))
+    (cora / 'cora.content').write_text(''.join(f'{int(ids[i])}\t' + '\t'.join(map(str, words[i])) + f'\t{subjects[i % 3]}\n' for i in range(40)))
+    monkeypatch.setattr(ours_mod, 'ASSETS_PATH', str(tmp_path))
+    ds = DATASET_REGISTRY['graph_cora'](walks_per_node=2, walk_length=5, method='node2vec', method_params={'p': 1.0, 'q': 2.0})
+    g = ds.graph
+    assert len(ds) == 2 * 40 and ds.has_labels and ds.has_features and g.number_of_nodes() == 40
+    assert ds.labels[f'n{int(ids[4])}'] == subjects[1] and np.array_equal(ds.features[f'n{int(ids[7])}'], words[7])
+    from oracle import ref_import
+    root = ref_import.reference_root()
+    if not root:
+        return
+    code = f"""
+import sys, json
+sys.path.insert(0, {os.path.dirname(os.path.dirname(os.path.abspath(__file__)))!r})
+from oracle import ref_import
+ref_import.import_reference()
+import shallow_encoders.graph.datasets as d
+d.ASSETS_PATH = {str(tmp_path)!r}
+ds = d.CoraDataset(walks_per_node=2, walk_length=5)
+g = ds.graph
+print(json.dumps({{'n': len(ds), 'adj': {{n: list(g.neighbors(n)) for n in g.nodes}}, 'labels': ds.labels,
+                  'features': {{k: [int(x) for x in v] for k, v in ds.features.items()}}}}))
+"""
+    out = subprocess.run([sys.executable, '-c', code], capture_output=True, text=True, timeout=300, env={**os.environ, 'PYTHONDONTWRITEBYTECODE': '1'})
+    assert out.returncode == 0, out.stderr[-2000:]
+    ref = json.loads(out.stdout.strip().splitlines()[-1])
+    assert ref['n'] == len(ds)
+    assert set(ref['adj']) == set(g.nodes)
+    for node, neighbours in ref['adj'].items():
+        assert list(g.neighbors(node)) == neighbours, node                                 # same CDF order as the reference's graph
+    assert ref['labels'] == ds.labels
+    assert all(np.array_equal(np.array(ref['features'][k]), ds.features[k]) for k in ref['features']) and set(ref['features']) == set(ds.features)
