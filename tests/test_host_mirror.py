@@ -333,3 +333,38 @@ print(json.dumps({{'n': len(ds), 'adj': {{n: list(g.neighbors(n)) for n in g.nod
         assert list(g.neighbors(node)) == neighbours, node                                 # same CDF order as the reference's graph
     assert ref['labels'] == ds.labels
     assert all(np.array_equal(np.array(ref['features'][k]), ds.features[k]) for k in ref['features']) and set(ref['features']) == set(ds.features)
+
+
+def test_registered_toy_graphs_equal_the_reference_constructors():
+    """a6: `graph_triplets` and `graph_karate_club` (graph/datasets.py:126-180): node names, per-node neighbour order (= CDF order), edge
+    weights and labels equal what the unmodified reference constructs (run in its own process)."""
+    import json
+    import subprocess
+    import sys
+    from oracle import ref_import
+    if not ref_import.reference_root():
+        pytest.skip('reference not available')
+    code = f"""
+import sys, json
+sys.path.insert(0, {os.path.dirname(os.path.dirname(os.path.abspath(__file__)))!r})
+from oracle import ref_import
+ref_import.import_reference()
+import shallow_encoders.graph.datasets as d
+out = {{}}
+for name, cls in (('graph_triplets', d.GraphTriplets), ('graph_karate_club', d.KarateClubDataset)):
+    ds = cls(walks_per_node=3, walk_length=4)
+    g = ds.graph
+    out[name] = {{'n': len(ds), 'adj': {{n: [[x, g[n][x].get('weight')] for x in g.neighbors(n)] for n in g.nodes}},
+                 'labels': ds.labels if ds.has_labels else None, 'has_features': ds.has_features}}
+print(json.dumps(out))
+"""
+    run = subprocess.run([sys.executable, '-c', code], capture_output=True, text=True, timeout=300, env={**os.environ, 'PYTHONDONTWRITEBYTECODE': '1'})
+    assert run.returncode == 0, run.stderr[-2000:]
+    ref = json.loads(run.stdout.strip().splitlines()[-1])
+    for name, want in ref.items():
+        ds = DATASET_REGISTRY[name](walks_per_node=3, walk_length=4)
+        g = ds.graph
+        assert len(ds) == want['n'] and set(g.nodes) == set(want['adj']) and ds.has_features == want['has_features']
+        for node, neighbours in want['adj'].items():
+            assert [[x, g[node][x].get('weight')] for x in g.neighbors(node)] == neighbours, (name, node)
+        assert (ds.labels if ds.has_labels else None) == want['labels'], name
