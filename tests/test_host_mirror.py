@@ -368,3 +368,38 @@ print(json.dumps(out))
         for node, neighbours in want['adj'].items():
             assert [[x, g[node][x].get('weight')] for x in g.neighbors(node)] == neighbours, (name, node)
         assert (ds.labels if ds.has_labels else None) == want['labels'], name
+
+
+def test_metric_meter_behaves_like_the_reference():
+    """word2vec/utils/meter.py: running means per metric name, `get_all` in insertion order with an optional flush, KeyError subclass for an
+    unknown name.  Compared with the reference module where it can be loaded (it needs only torch)."""
+    import importlib.util
+    import sys
+    from oracle import ref_import
+    from shallow_encoders.word2vec.utils.meter import MetricMeter, UnknownMetricException
+    meters = [MetricMeter()]
+    root = ref_import.reference_root()
+    if root:
+        spec = importlib.util.spec_from_file_location('_ref_meter', os.path.join(root, 'shallow_encoders', 'word2vec', 'utils', 'meter.py'))
+        ref = importlib.util.module_from_spec(spec)
+        sys.dont_write_bytecode = True
+        spec.loader.exec_module(ref)
+        meters.append(ref.MetricMeter())
+    results = []
+    for m in meters:
+        assert m.is_empty
+        for step, (a, b) in enumerate([(1.0, 4.0), (2.0, 5.0), (6.0, 0.5)]):
+            m.push('loss', torch.tensor(a) if step == 1 else a)
+            m.push('recall', b)
+        assert not m.is_empty
+        got = [float(m.get('loss')), float(m.get('recall'))]
+        kept = [(k, float(v)) for k, v in m.get_all(flush=False)]
+        assert not m.is_empty
+        flushed = [(k, float(v)) for k, v in m.get_all()]
+        assert m.is_empty
+        with pytest.raises(KeyError):
+            m.get('loss')
+        results.append((got, kept, flushed))
+    assert results[0][0] == [3.0, 9.5 / 3] and results[0][1] == [('loss', 3.0), ('recall', 9.5 / 3)] == results[0][2]
+    assert all(r == results[0] for r in results)
+    assert issubclass(UnknownMetricException, KeyError)
