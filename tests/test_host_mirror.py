@@ -439,3 +439,42 @@ def test_the_reference_yamls_load_unmodified():
             assert cfg.train.fused_optimizer_kind() == ('adam' if raw['train']['optimizer']['_target_'].endswith('Adam') else 'sgd')
         if 'downstream' in raw and raw['downstream']:
             assert cfg.downstream['node_classification']['split_algorithm']['_target_'].startswith('shallow_encoders.split.')
+
+
+def test_collate_equals_the_reference_on_random_batches():
+    """a9: W2VCollateFunctional (torch_dataset.py:280-322), both modes, on 24 random batches (ragged sentence lengths, clipping by max_length,
+    radius 1..4) against the unmodified reference run in its own process -- beyond the fixed cases of tests/golden/collate.npz."""
+    import json
+    import subprocess
+    import sys
+    from oracle import ref_import
+    if not ref_import.reference_root():
+        pytest.skip('reference not available')
+    rng = np.random.default_rng(2024)
+    cases = []
+    for i in range(24):
+        radius = int(rng.integers(1, 5))
+        max_length = int(rng.integers(2 * radius + 1, 2 * radius + 12))
+        batch = [rng.integers(0, 50, int(rng.integers(2 * radius + 1, 30))).tolist() for _ in range(int(rng.integers(1, 6)))]
+        cases.append({'mode': 'sg' if i % 2 == 0 else 'cbow', 'radius': radius, 'max_length': max_length, 'batch': batch})
+    code = f"""
+import sys, json, torch
+sys.path.insert(0, {os.path.dirname(os.path.dirname(os.path.abspath(__file__)))!r})
+from oracle import ref_import
+ref_import.import_reference()
+from shallow_encoders.word2vec.dataloader.torch_dataset import W2VCollateFunctional
+out = []
+for c in json.loads(sys.stdin.read()):
+    f = W2VCollateFunctional(mode=c['mode'], context_radius=c['radius'], max_length=c['max_length'])
+    a, b = f([torch.tensor(s, dtype=torch.long) for s in c['batch']])
+    out.append([a.tolist(), b.tolist(), str(a.dtype), str(b.dtype)])
+print(json.dumps(out))
+"""
+    run = subprocess.run([sys.executable, '-c', code], input=json.dumps(cases), capture_output=True, text=True, timeout=300,
+                         env={**os.environ, 'PYTHONDONTWRITEBYTECODE': '1'})
+    assert run.returncode == 0, run.stderr[-2000:]
+    ref = json.loads(run.stdout.strip().splitlines()[-1])
+    for c, (ra, rb, da, db) in zip(cases, ref):
+        f = W2VCollateFunctional(mode=c['mode'], context_radius=c['radius'], max_length=c['max_length'])
+        a, b = f([torch.tensor(s, dtype=torch.long) for s in c['batch']])
+        assert a.tolist() == ra and b.tolist() == rb and str(a.dtype) == da and str(b.dtype) == db, c
