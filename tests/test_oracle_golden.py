@@ -107,3 +107,67 @@ def test_vocab_golden_order():
     itos = [str(s) for s in z['karate_itos']]
     assert itos[0] == '<unk>' and itos[1:] == [f'n{i:02d}' for i in range(1, 35)]
     assert [str(s) for s in z['triplets_itos']] == ['<unk>', 'a1', 'a2', 'a3', 'b1', 'b2', 'b3', 'c1', 'c2', 'c3']
+
+
+@pytest.mark.parametrize('seed,weights,method,p,q', [(11, None, 'node2vec', 0.5, 2.0), (12, 'int', 'node2vec', 4.0, 0.25), (13, 'float', 'node2vec', 1.0, 0.5),
+                                                     (14, 'float', 'deepwalk', 1.0, 1.0), (15, 'int', 'dfs', 1.0, 1.0)])
+def test_walk_oracles_match_the_live_reference_on_fresh_random_graphs(seed, weights, method, p, q):
+    """Beyond the committed fixtures: wherever the reference can be loaded (/root/reference here, baseline/_ref on the GPU box) its
+    DeepWalk.walk / Node2Vec.walk run under a replayed uniform stream on a NEW random graph (unsorted adjacency, optional int / float
+    weights) and both oracles -- the python restatement and the C one the GPU tests compare against -- must reproduce every walk."""
+    import importlib.util
+    import random
+    import types
+    import networkx as nx
+    from oracle import ref_import
+    root = ref_import.reference_root()
+    if not root:
+        pytest.skip('reference not available')
+    spec = importlib.util.spec_from_file_location('_ref_rwg_live', os.path.join(root, 'shallow_encoders', 'graph', 'random_walk_generator.py'))
+    ref = importlib.util.module_from_spec(spec)
+    sys.dont_write_bytecode = True
+    spec.loader.exec_module(ref)
+    rnd = random.Random(seed)
+    n, m, length = 60, 240, 12
+    names = [f'n{i:03d}' for i in range(n)]
+    order = list(range(n))
+    rnd.shuffle(order)
+    edges = {(min(a, b), max(a, b)) for a, b in zip(order, order[1:])}           # a spanning path: no isolated node
+    while len(edges) < m:
+        a, b = rnd.randrange(n), rnd.randrange(n)
+        if a != b:
+            edges.add((min(a, b), max(a, b)))
+    edges = list(edges)
+    rnd.shuffle(edges)                                                            # random insertion order -> unsorted adjacency lists
+    g = nx.Graph()
+    for a, b in edges:
+        a, b = (b, a) if rnd.random() < 0.5 else (a, b)
+        if weights == 'float':
+            g.add_edge(names[a], names[b], weight=rnd.uniform(0.25, 4.0))
+        elif weights == 'int':
+            g.add_edge(names[a], names[b], weight=rnd.randint(1, 9))
+        else:
+            g.add_edge(names[a], names[b])
+    og = walk_oracle.OracleGraph.from_networkx(g)
+    rng = np.random.default_rng(seed)
+    starts = rng.permutation(np.repeat(np.arange(n, dtype=np.int32), 2))
+    uniforms = rng.random((len(starts), length - 1))
+
+    class _Replay(random.Random):
+        def __init__(self, draws):
+            super().__init__(0)
+            self.draws, self.i = [float(x) for x in draws], 0
+
+        def random(self):
+            self.i += 1
+            return self.draws[self.i - 1]
+    replay = _Replay(uniforms.reshape(-1))
+    ref.random = types.SimpleNamespace(choices=replay.choices)                    # the module's `random.choices` now consumes the recorded stream
+    gen = ref.random_walk_factory(method, g, length, {'p': p, 'q': q} if method == 'node2vec' else {})
+    idx = {name: i for i, name in enumerate(og.names)}
+    want = np.array([[idx[t] for t in gen.walk(og.names[s]).split(' ')] for s in starts], dtype=np.int32)
+    assert replay.i == uniforms.size                                              # exactly one draw per transition
+    node2vec = method == 'node2vec'
+    assert np.array_equal(walk_oracle.walks(og, starts, length, uniforms, p, q, node2vec=node2vec), want)
+    rowptr, col, w, w_is_int = og.to_csr()
+    assert np.array_equal(c_walks(rowptr, col, w, w_is_int, starts, length, p, q, node2vec, 0, uniforms), want)
