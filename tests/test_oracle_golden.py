@@ -171,3 +171,47 @@ def test_walk_oracles_match_the_live_reference_on_fresh_random_graphs(seed, weig
     assert np.array_equal(walk_oracle.walks(og, starts, length, uniforms, p, q, node2vec=node2vec), want)
     rowptr, col, w, w_is_int = og.to_csr()
     assert np.array_equal(c_walks(rowptr, col, w, w_is_int, starts, length, p, q, node2vec, 0, uniforms), want)
+
+
+@pytest.mark.parametrize('vocab,emb,b,n,k,scale,seed', [(50, 8, 16, 4, 1, 1.0, 1), (300, 48, 32, 10, 3, 0.3, 2), (40, 128, 24, 4, 5, 6.0, 3)])
+def test_sgns_oracle_matches_the_live_reference_modules(vocab, emb, b, n, k, scale, seed):
+    """Beyond the committed fixtures: the reference's own SkipGram (word2vec/model.py:79-91) and NegativeSamplingLoss (loss.py:14-22), loaded
+    from the reference tree where it is available, evaluated in fp64 with torch autograd on a fresh random batch (duplicate rows, and with
+    scale 6 logits deep in the clamp region); the numpy oracle the GPU kernels are tested against must give the same loss triple and the same
+    dense gradients to 1e-12."""
+    import importlib.util
+    import torch
+    from oracle import ref_import
+    root = ref_import.reference_root()
+    if not root:
+        pytest.skip('reference not available')
+    mods = {}
+    for name in ('model', 'loss'):
+        spec = importlib.util.spec_from_file_location(f'_ref_w2v_{name}_live', os.path.join(root, 'shallow_encoders', 'word2vec', f'{name}.py'))
+        mods[name] = importlib.util.module_from_spec(spec)
+        sys.dont_write_bytecode = True
+        spec.loader.exec_module(mods[name])
+    rng = np.random.default_rng(seed)
+    w_in = rng.standard_normal((vocab, emb)) * scale / np.sqrt(emb)
+    w_out = rng.standard_normal((vocab, emb)) * scale / np.sqrt(emb) * 4
+    inputs = rng.integers(0, vocab, (b, 1))
+    targets = rng.integers(0, vocab, (b, n))
+    noise = rng.integers(0, vocab, (b, n, k))
+    model = mods['model'].SkipGram(vocab_size=vocab, embedding_size=emb).double()
+    with torch.no_grad():
+        model._input_embedding.weight.copy_(torch.from_numpy(w_in))
+        model._output_embedding.weight.copy_(torch.from_numpy(w_out))
+    t_in, t_tg, t_nz = torch.from_numpy(inputs), torch.from_numpy(targets), torch.from_numpy(noise)
+    pos = model(t_in, t_tg, proba=False)                                         # trainer.py:135-139
+    neg = model(t_in, t_nz.view(b, -1), proba=False).view(b, n, -1)
+    out = mods['loss'].NegativeSamplingLoss()(pos, neg)
+    out['loss'].backward()
+    o = sgns_oracle.training_step(w_in, w_out, inputs, targets, noise)
+    for key in ('loss', 'positive-loss', 'negative-loss'):
+        ref_value = float(out[key].detach())
+        assert abs(o[key] - ref_value) <= 1e-12 * max(1.0, abs(ref_value)), key
+    g_in, g_out = model._input_embedding.weight.grad.numpy(), model._output_embedding.weight.grad.numpy()
+    den = max(np.abs(g_in).max(), np.abs(g_out).max())
+    assert np.abs(o['grad_in'] - g_in).max() <= 1e-12 * den and np.abs(o['grad_out'] - g_out).max() <= 1e-12 * den
+    if scale > 5:
+        assert (1.0 / (1.0 + np.exp(-o['neg_logits'])) > 1 - 1e-6).any() or (1.0 / (1.0 + np.exp(o['pos_logits'])) > 1 - 1e-6).any()   # clamp region reached
