@@ -215,3 +215,36 @@ def test_sgns_oracle_matches_the_live_reference_modules(vocab, emb, b, n, k, sca
     assert np.abs(o['grad_in'] - g_in).max() <= 1e-12 * den and np.abs(o['grad_out'] - g_out).max() <= 1e-12 * den
     if scale > 5:
         assert (1.0 / (1.0 + np.exp(-o['neg_logits'])) > 1 - 1e-6).any() or (1.0 / (1.0 + np.exp(o['pos_logits'])) > 1 - 1e-6).any()   # clamp region reached
+
+
+def test_lazy_adam_oracle_equals_dense_torch_adam_while_the_batch_touches_the_same_rows():
+    """The row-sparse Adam kernel (csrc/adam.cu) is checked against `sgns_oracle.lazy_adam_step`; the oracle itself is pinned here, on the
+    host: five steps on the SAME batch (every step touches the same rows, so per-row step counts equal torch's global step) must equal
+    torch.optim.Adam on dense fp64 tables driven by autograd through the reference's loss arithmetic -- untouched rows included
+    (zero gradient and zero moments: dense Adam does not move them either)."""
+    import torch
+    rng = np.random.default_rng(9)
+    vocab, emb, b, n, k, lr = 60, 16, 20, 4, 3, 0.1
+    w_in = rng.standard_normal((vocab, emb)) * 0.3
+    w_out = rng.standard_normal((vocab, emb)) * 0.3
+    inputs, targets, noise = rng.integers(0, vocab, (b, 1)), rng.integers(0, vocab, (b, n)), rng.integers(0, vocab, (b, n, k))
+    ti, to = torch.nn.Parameter(torch.from_numpy(w_in.copy())), torch.nn.Parameter(torch.from_numpy(w_out.copy()))
+    opt = torch.optim.Adam([ti, to], lr=lr)
+    state = {key: np.zeros((vocab, emb)) for key in ('m_in', 'v_in', 'm_out', 'v_out')}
+    state['t_in'], state['t_out'] = np.zeros(vocab, dtype=np.int64), np.zeros(vocab, dtype=np.int64)
+    a, c = w_in.copy(), w_out.copy()
+    t_inputs, t_targets, t_noise = torch.from_numpy(inputs), torch.from_numpy(targets), torch.from_numpy(noise)
+    for _ in range(5):
+        centre = ti[t_inputs[:, 0]]                                               # model.py:83-90 + loss.py:15-19 in plain torch
+        pos = torch.einsum('be,bne->bn', centre, to[t_targets])
+        neg = torch.einsum('be,bnke->bnk', centre, to[t_noise])
+        loss = -(torch.log(torch.clamp(torch.sigmoid(pos), min=1e-6)).mean() + torch.log(torch.clamp(torch.sigmoid(-neg), min=1e-6)).sum(-1).mean())
+        opt.zero_grad()
+        loss.backward()
+        opt.step()
+        o = sgns_oracle.lazy_adam_step(a, c, state, inputs, targets, noise, lr)
+        assert abs(o['loss'] - float(loss.detach())) < 1e-12
+    np.testing.assert_allclose(a, ti.detach().numpy(), rtol=0, atol=1e-12)
+    np.testing.assert_allclose(c, to.detach().numpy(), rtol=0, atol=1e-12)
+    untouched = np.setdiff1d(np.arange(vocab), inputs)
+    assert np.array_equal(a[untouched], w_in[untouched]) and (state['t_in'][np.unique(inputs)] == 5).all()
