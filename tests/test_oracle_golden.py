@@ -248,3 +248,19 @@ def test_lazy_adam_oracle_equals_dense_torch_adam_while_the_batch_touches_the_sa
     np.testing.assert_allclose(c, to.detach().numpy(), rtol=0, atol=1e-12)
     untouched = np.setdiff1d(np.arange(vocab), inputs)
     assert np.array_equal(a[untouched], w_in[untouched]) and (state['t_in'][np.unique(inputs)] == 5).all()
+
+
+def test_philox_restatement_passes_the_published_known_answer_vectors():
+    """tests/philox_ref.py predicts every in-kernel draw of the GPU tests (walk tries, negatives, negative edges).  It is the published
+    Philox4x32-10 (Salmon et al., SC'11): the three known-answer vectors of the Random123 distribution (kat_vectors: counter / key all zero,
+    all ones, digits of pi) come out bit for bit, so the kernels -- pinned to this restatement on the GPU -- run a standard generator."""
+    import philox_ref
+    kat = [((0, 0, 0, 0), (0, 0), (0x6627e8d5, 0xe169c58d, 0xbc57ac4c, 0x9b00dbd8)),
+           ((0xffffffff,) * 4, (0xffffffff,) * 2, (0x408f276d, 0x41c83b0e, 0xa20bc7c6, 0x6d5451fd)),
+           ((0x243f6a88, 0x85a308d3, 0x13198a2e, 0x03707344), (0xa4093822, 0x299f31d0), (0xd16cfe09, 0x94fdcceb, 0x5001e420, 0x24126ea1))]
+    for ctr, key, want in kat:
+        got = philox_ref.philox4x32_10(*[np.array([c], dtype=np.uint32) for c in ctr], *key)
+        assert tuple(int(g[0]) for g in got) == want
+    # the keyed form used by the kernels: (id low, id high, sub, stream) as the counter, the 64-bit seed as the key
+    a = philox_ref.philox(0x299f31d0a4093822, np.array([0x85a308d3243f6a88], dtype=np.uint64), 0x13198a2e, 0x03707344)
+    assert tuple(int(x[0]) for x in a) == kat[2][2]
