@@ -58,3 +58,15 @@ def test_wrappers_refuse_cpu_tensors():
     idx = torch.zeros((2, 1), dtype=torch.int64)
     with pytest.raises(RuntimeError, match='no CPU fallback'):
         nat.skipgram_scores(t, t, idx, idx, True)
+
+
+def test_product_path_fails_loudly_when_the_native_library_is_missing(monkeypatch, tmp_path):
+    """No CPU fallback anywhere: with the shared library absent (or exporting fewer symbols than include/se_b200.h declares) `load()` raises
+    and names the build command; nothing routes around it."""
+    from shallow_encoders import _native as nat
+    monkeypatch.setattr(nat, '_lib', None)
+    monkeypatch.setattr(nat, 'LIB_PATH', str(tmp_path / 'libse_b200.so'))
+    with pytest.raises(RuntimeError, match='no CPU fallback'):
+        nat.load()
+    with pytest.raises(RuntimeError, match='no CPU fallback'):
+        nat.version()
